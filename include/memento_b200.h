@@ -1,0 +1,130 @@
+/* libmemento_b200 -- C ABI of the B200-native memento hot path.
+ *
+ * The reference (atarashansky/scrna-parameter-estimation, package `memento`) is pure Python and has
+ * no FFI; its seams are the Python functions cited below.  Each entry point here replaces the
+ * arithmetic of one of them and is what a maintainer of the reference would bind with ctypes
+ * (see INTEGRATION.md for the stub).  Conventions:
+ *
+ *  - every call takes (int device, void* stream): the CUDA device ordinal and a cudaStream_t;
+ *    work is enqueued on that stream, nothing synchronises the host;
+ *  - all pointers are DEVICE pointers owned by the caller (plain pointers and sizes, no C++ types);
+ *    the library allocates no device memory and keeps no global state;
+ *  - return value 0 = ok, 1 = invalid argument, 2 = CUDA error; mm_last_error() gives the message
+ *    of the last failing call on the calling thread;
+ *  - "segment" = one (gene, group) slice of the group-sorted CSC matrix: global segment index
+ *    s = gene * R + group, nonzeros seg_ptr[s] .. seg_ptr[s+1];
+ *  - counts are float32, row ids int32 (cells renumbered so that each group is a contiguous row
+ *    range), offsets int64, statistics float64.
+ */
+#ifndef MEMENTO_B200_H
+#define MEMENTO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int mm_version(void);
+const char* mm_last_error(void);
+
+/* Per-cell UMI totals of a CSR matrix, optionally restricted to the genes with gene_mask[g] != 0
+ * (gene_mask may be NULL).  out[n_rows].
+ * Replaces: memento/estimator.py:64-69 (total=True) and :73 (X.multiply(mask).sum(axis=1)). */
+int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32_t* indices,
+                    const float* data, int64_t n_rows, const uint8_t* gene_mask, double* out);
+
+/* One pass over the group-sorted CSC matrix: for every segment s,
+ *   out[0*n_seg+s] = sum x          out[1*n_seg+s] = max x
+ *   out[2*n_seg+s] = sum x/sf       out[3*n_seg+s] = sum x/sf^2     out[4*n_seg+s] = sum x^2/sf^2
+ * inv_sf[cell] = 1/size_factor in the same (group-sorted) cell order as `rows`.
+ * big_list: int32 scratch of nnz/32768 + 2 entries.
+ * Replaces: memento/estimator.py:175-185 (_hyper_1d_relative, sparse form; three sparse mat-vecs and
+ * a squared copy) and the obs_mean / obs_max passes of memento/main.py:201, :206. */
+int mm_seg_moments(int device, void* stream, const float* vals, const int32_t* rows,
+                   const int64_t* seg_ptr, int64_t n_seg, const double* inv_sf, double* out,
+                   int32_t* big_list);
+
+/* Covariance sums of gene pairs within every group: for pair k and group r,
+ *   out[k*R + r] = sum over cells of the group of x_{c,i} * x_{c,j} / sf_c^2
+ * by a merge join of the two sorted row-id lists.
+ * Replaces: memento/estimator.py:225-228 (_hyper_cov_relative sparse form, which materialises two
+ * cells x n_pairs matrices). */
+int mm_pair_products(int device, void* stream, const float* vals, const int32_t* rows,
+                     const int64_t* seg_ptr, int32_t R, const int32_t* idx1, const int32_t* idx2,
+                     int64_t n_pairs, const double* inv_sf, double* out);
+
+/* Compression of segments [seg_lo, seg_lo + n_seg) to their distinct (count, size-factor bin)
+ * values.  cell_bin[cell] in [0, n_bins); bin_inv_sf[n_bins] = 1/approx_size_factor of the bin;
+ * estimator 0 = hyper_relative, 1 = mean_only.  Outputs at pool offset seg_ptr[s] - seg_ptr[seg_lo]:
+ * `entries` (32-byte prepared bootstrap records), raw_key = count << 8 | bin, raw_cnt = multiplicity
+ * (raw_* may be NULL); seg_U[s - seg_lo] = number of distinct nonzero categories, or -1 when the
+ * reference's "U <= 1 => all NaN" rule applies.  Scratch: big_list int32[n_seg + 1], scratch_key /
+ * scratch_cnt 3 * (pool size) entries each.
+ * Replaces: memento/bootstrap.py:40-71 (_unique_expr: random-projection hash + np.unique). */
+int mm_seg_unique(int device, void* stream, const float* vals, const int32_t* rows,
+                  const int64_t* seg_ptr, int64_t seg_lo, int64_t n_seg, int32_t R,
+                  const uint8_t* cell_bin, const double* bin_inv_sf, int32_t n_bins,
+                  const double* group_q, const int32_t* group_ncells, const int32_t* group_nbins,
+                  int32_t estimator, void* entries, uint32_t* raw_key, int32_t* raw_cnt,
+                  int32_t* seg_U, int32_t* big_list, uint32_t* scratch_key, int32_t* scratch_cnt);
+
+/* Fused bootstrap of segments [seg_lo, seg_lo + n_seg) (n_seg <= 65535 per call): for every
+ * replicate b < num_boot draw multinomial resample counts over the segment's categories
+ * (Philox4x32-10, counter = (b, segment), key = seed), accumulate the moments and write
+ *   out_mean[s*num_boot + b] = bootstrapped mean,  out_rv[...] = residual variance
+ * (NaN where mean <= 0 or variance <= 0).  mv_fit[R][3] = quadratic log-log trend per group,
+ * highest power first.  seg_skip (nullable): segments not to compute.
+ * Replaces: memento/bootstrap.py:74-116 (_bootstrap_1d), estimator.py:171-174 (tuple form),
+ * hypothesis_test.py:186 -> estimator.py:103-111 (_residual_variance per replicate). */
+int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t* seg_ptr,
+                    int64_t seg_lo, int64_t n_seg, int32_t R, const int32_t* seg_U,
+                    const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
+                    int32_t estimator, int32_t num_boot, uint64_t seed, double* out_mean,
+                    double* out_rv);
+
+/* Deterministic replay: the same statistics from HOST-SUPPLIED resample counts.  Tables are in the
+ * reference's order: x / inv_sf [sum U], W = per table a (num_boot x U_t) int64 block starting at
+ * W + num_boot * tab_ptr[t].  Outputs [n_tab][num_boot]: mean, variance, residual variance.
+ * Replaces: memento/estimator.py:171-174 evaluated on bootstrap.py:103's gene_rvs. */
+int mm_bootstrap_1d_replay(int device, void* stream, const double* x, const double* inv_sf,
+                           const int64_t* W, const int64_t* tab_ptr, const int32_t* n_cells,
+                           const double* q, const double* mv_fit, int32_t n_tab, int32_t num_boot,
+                           int32_t estimator, double* out_mean, double* out_var, double* out_rv);
+
+/* Imputation of invalid replicates (<= 0 or NaN) by a uniformly random valid replicate of the same
+ * row, then log; column 0 = log of the point estimate.  seg_ok = a-priori validity of the row;
+ * seg_good (out) = seg_ok and at least one valid replicate of both statistics.  src_mean / src_rv
+ * (nullable) replay host-supplied source indices instead of drawing.  boot_* are [n_seg][num_boot+1].
+ * Replaces: memento/hypothesis_test.py:23-33 (_fill), :167-200 of _ht_1d. */
+int mm_fill_log(int device, void* stream, const double* raw_mean, const double* raw_rv,
+                const uint8_t* seg_ok, const double* true_mean, const double* true_rv,
+                const int32_t* src_mean, const int32_t* src_rv, int64_t seg_lo, int64_t n_seg,
+                int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
+                uint8_t* seg_good, int32_t* n_valid);
+
+/* Batched small solves: for each of n_mask group-validity masks, the (T x R) linear functional C
+ * with coef[t] = sum_r C[t,r] * y[r] equal to "residualise y and treatment on [1, covariate] with
+ * weights, then weighted marginal slope".  covariate [R][n_cov], treatment [R][T], weights [R],
+ * masks [n_mask][R]; scratch [n_mask][R][n_cov+T]; cmat [n_mask][T][R].  one_sample != 0: weighted
+ * average over groups.
+ * Replaces: memento/hypothesis_test.py:262-271 (three sklearn LinearRegression fits per gene) and
+ * :218-228 (_cross_coef). */
+int mm_wls_functional(int device, void* stream, const double* covariate, const double* treatment,
+                      const double* weights, const uint8_t* masks, int32_t R, int32_t n_cov,
+                      int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat);
+
+/* Per gene: coefficient of every bootstrap column, SE (population std of columns 1..), and the ASL:
+ * approx != 0 -> two-sided normal tail; else extreme count c and (c+1)/(n+1) (out_extreme carries c
+ * for the GEV tail stage).  boot1 may be NULL (one statistic).  coef_ws (nullable) receives the
+ * coefficient rows [n_gene][n_stat][T][num_boot+1].  Outputs [n_gene][n_stat][T].
+ * Replaces: memento/hypothesis_test.py:242-300 (_regress_1d), :367-414 (_regress_2d), :57-92. */
+int mm_regress_asl(int device, void* stream, const double* boot0, const double* boot1,
+                   const uint8_t* seg_good, const int32_t* mask_id, const double* cmat,
+                   int32_t n_gene, int32_t R, int32_t T, int32_t num_boot, int32_t approx,
+                   double* coef_ws, double* out_coef, double* out_se, double* out_asl,
+                   int32_t* out_extreme, int32_t* out_nnull);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMENTO_B200_H */

@@ -18,14 +18,26 @@ GEV_KS_ALPHA = 0.05         # :110
 
 
 # --------------------------------------------------------------------------- imputation
-def fill_invalid(val):
+def fill_invalid(val, record=None):
     """Replace entries <=0 or NaN by random picks among the valid ones (in place); None when
-    nothing is valid.  reference: hypothesis_test.py:23-33."""
-    bad = np.less_equal(val, 0., where=~np.isnan(val)) | np.isnan(val)
+    nothing is valid.  reference: hypothesis_test.py:23-33.
+
+    ``np.random.choice(valid, n)`` is ``valid[np.random.randint(0, len(valid), n)]`` on the same
+    stream (checked in tests); drawing the indices explicitly lets a test record which replicate
+    every invalid entry was filled from (``record``: dict that receives ``src``, the source
+    replicate index per entry, -1 where the entry was kept)."""
+    with np.errstate(invalid="ignore"):
+        bad = ~(val > 0)
     n_bad = bad.sum()
     if n_bad == val.shape[0]:
         return None
-    val[bad] = np.random.choice(val[~bad], n_bad)
+    valid_pos = np.flatnonzero(~bad)
+    pick = np.random.randint(0, valid_pos.shape[0], n_bad)
+    if record is not None:
+        src = np.full(val.shape[0], -1, dtype=np.int32)
+        src[bad] = valid_pos[pick]
+        record["src"] = src
+    val[bad] = val[valid_pos[pick]]
     return val
 
 
@@ -156,7 +168,7 @@ def regress(covariate, treatment, boots, n_cells, resample_rep=False, **asl_kwar
 
 # --------------------------------------------------------------------------- per-gene drivers
 def ht_1d_gene(true_mean, true_res_var, cells, approx_sf, covariate, treatment, n_cells,
-               num_boot, mv_fit, q, weighted_estimator, return_boot=False, **kwargs):
+               num_boot, mv_fit, q, weighted_estimator, return_boot=False, recorder=None, **kwargs):
     """All groups of one gene: bootstrap, residual variance, imputation, regression.
     reference: hypothesis_test.py:144-215.  Returns the 6-tuple the reference returns."""
     R = treatment.shape[0]
@@ -169,10 +181,17 @@ def ht_1d_gene(true_mean, true_res_var, cells, approx_sf, covariate, treatment, 
             continue
         with np.errstate(divide="ignore"):
             boot_mean[r, 0], boot_var[r, 0] = np.log(true_mean[r]), np.log(true_res_var[r])
-        mean, var = resample.bootstrap_1d(cells[r], approx_sf[r], q[r], weighted_estimator, num_boot)
+        table = resample.unique_table(cells[r], approx_sf[r])
+        mean, var = resample.bootstrap_1d(cells[r], approx_sf[r], q[r], weighted_estimator, num_boot,
+                                          precomputed=table)
         res_var = moments.residual_variance(mean, var, mv_fit[r])
-        filled_mean = fill_invalid(mean)
-        filled_var = fill_invalid(res_var)
+        rec_m, rec_v = {}, {}
+        filled_mean = fill_invalid(mean, rec_m)
+        filled_var = fill_invalid(res_var, rec_v)
+        if recorder is not None:
+            recorder.append({"group": r, "inv_sf": table[0].reshape(-1), "values": table[2][:, 0],
+                             "mult": table[3], "n_cells": cells[r].shape[0],
+                             "src_mean": rec_m.get("src"), "src_rv": rec_v.get("src")})
         if filled_mean is None or filled_var is None:
             continue
         boot_mean[r, 1:] = np.log(filled_mean)

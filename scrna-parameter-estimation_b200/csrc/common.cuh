@@ -1,0 +1,125 @@
+// Shared device/host helpers for libmemento_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#ifndef MM_EXPORT
+#define MM_EXPORT extern "C" __attribute__((visibility("default")))
+#endif
+
+namespace mm {
+
+// ---------------------------------------------------------------- error handling (host)
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);      // cudaGetLastError -> status
+int enter(int device);                   // cudaSetDevice + clear error; returns status
+
+#define MM_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            mm::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                          __FILE__, __LINE__);                                     \
+            return 2;                                                              \
+        }                                                                          \
+    } while (0)
+
+#define MM_REQUIRE(cond, msg)                                  \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            mm::set_error("invalid argument: %s (%s)", msg, #cond); \
+            return 1;                                          \
+        }                                                      \
+    } while (0)
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// streaming (read-once) loads: keep them out of L1 so the gathered per-cell vectors stay cached
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ld_stream4(const int4* p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (counter based)
+struct Philox {
+    uint32_t key0, key1;
+    uint4 ctr;
+    uint4 out;
+    int have;  // unread words in `out`
+
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+        key0 = (uint32_t)seed;
+        key1 = (uint32_t)(seed >> 32);
+        ctr = make_uint4(c0, c1, c2, c3);
+        have = 0;
+    }
+    __device__ __forceinline__ static uint4 round10(uint4 c, uint32_t k0, uint32_t k1) {
+        constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+            uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+            k0 += W0;
+            k1 += W1;
+        }
+        return c;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (have == 0) {
+            out = round10(ctr, key0, key1);
+            ctr.z += 1;  // c2 is the per-stream block counter
+            have = 4;
+        }
+        uint32_t v = have == 4 ? out.x : have == 3 ? out.y : have == 2 ? out.z : out.w;
+        --have;
+        return v;
+    }
+    // uniform in (0, 1): 24 random bits, never 0 or 1
+    __device__ __forceinline__ float uniform() { return ((next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+};
+
+}  // namespace mm

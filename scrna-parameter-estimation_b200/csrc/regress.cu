@@ -1,0 +1,438 @@
+// Per-gene meta-regression across groups and the ASL p-value, batched over genes.
+//
+//  * mm_fill_log      -- invalid-replicate imputation + log transform of the bootstrap rows
+//                        (reference hypothesis_test.py:23-33 _fill, :174, :189-197)
+//  * mm_regress_asl   -- coef[t, b] = sum_r C[t, r] * boot[r, b] for every bootstrap column, then
+//                        SE, extreme counts and the ASL (reference hypothesis_test.py:242-300
+//                        _regress_1d / _cross_coef, :57-92 _compute_asl).  C is the (T x R) linear
+//                        functional equivalent to "residualise on [1, covariate] with weights Nc, then
+//                        marginal weighted slope on each residualised treatment column" -- it depends
+//                        only on the design and on which groups are valid for the gene, so it is
+//                        computed once per distinct validity mask (mm_wls_functional) and shared.
+//                        This replaces three sklearn LinearRegression fits per gene.
+//  * mm_wls_functional-- the batched small solves: weighted modified Gram-Schmidt of [1, covariate]
+//                        restricted to the valid groups, in float64, one CTA per distinct mask.
+#include "common.cuh"
+
+namespace mm {
+
+constexpr int kRegThreads = 256;
+constexpr int kMaxT = 4;   // treatment columns handled per pass
+
+// ------------------------------------------------------------------ fill + log
+struct FillParams {
+    const double* raw_mean;     // [n_seg][B]
+    const double* raw_rv;       // [n_seg][B]
+    const unsigned char* seg_ok;  // [n_seg] a-priori validity (true-moment conditions); 0 => NaN row
+    const double* true_mean;    // [n_seg]
+    const double* true_rv;      // [n_seg]
+    const int* src_mean;        // replay: [n_seg][B] source replicate for invalid entries (-1 keep); nullable
+    const int* src_rv;          // replay, nullable
+    long long seg_lo;           // global index of the first segment (RNG counter)
+    int B;
+    unsigned long long seed;
+    double* boot_mean;          // [n_seg][B+1] log values, column 0 = log true value
+    double* boot_var;           // [n_seg][B+1]
+    unsigned char* seg_good;    // [n_seg] final validity
+    int* n_valid;               // [n_seg][2]
+};
+
+__device__ __forceinline__ double pick_valid(const double* row, int B, int n_valid, Philox& rng) {
+    for (int it = 0; it < 256; ++it) {
+        int j = (int)(rng.uniform() * (float)B);
+        if (j >= B) j = B - 1;
+        double v = row[j];
+        if (v > 0.0) return v;
+    }
+    // very sparse valid set: take the floor(u * n_valid)-th valid entry by scanning
+    int want = (int)(rng.uniform() * (float)n_valid);
+    if (want >= n_valid) want = n_valid - 1;
+    for (int j = 0; j < B; ++j) {
+        double v = row[j];
+        if (v > 0.0 && want-- == 0) return v;
+    }
+    return nan("");
+}
+
+__global__ void __launch_bounds__(kRegThreads)
+fill_log_kernel(FillParams P) {
+    __shared__ int s_cnt[2];
+    const long long seg = blockIdx.x;
+    const int B = P.B;
+    double* om = P.boot_mean + seg * (long long)(B + 1);
+    double* ov = P.boot_var + seg * (long long)(B + 1);
+    const double* rm = P.raw_mean + seg * (long long)B;
+    const double* rr = P.raw_rv + seg * (long long)B;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    bool ok = P.seg_ok[seg] != 0;
+    if (ok) {
+        int cm = 0, cr = 0;
+        for (int b = threadIdx.x; b < B; b += kRegThreads) {
+            cm += (rm[b] > 0.0);
+            cr += (rr[b] > 0.0);
+        }
+        cm = warp_sum_int(cm);
+        cr = warp_sum_int(cr);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], cm); atomicAdd(&s_cnt[1], cr); }
+    }
+    __syncthreads();
+    const int nvm = s_cnt[0], nvr = s_cnt[1];
+    ok = ok && nvm > 0 && nvr > 0;
+    if (threadIdx.x == 0) {
+        P.seg_good[seg] = ok ? 1 : 0;
+        P.n_valid[2 * seg] = nvm;
+        P.n_valid[2 * seg + 1] = nvr;
+    }
+    if (!ok) {
+        for (int b = threadIdx.x; b <= B; b += kRegThreads) { om[b] = nan(""); ov[b] = nan(""); }
+        return;
+    }
+    if (threadIdx.x == 0) { om[0] = log(P.true_mean[seg]); ov[0] = log(P.true_rv[seg]); }
+    for (int b = threadIdx.x; b < B; b += kRegThreads) {
+        double m = rm[b], v = rr[b];
+        if (!(m > 0.0)) {
+            if (P.src_mean) m = rm[P.src_mean[seg * (long long)B + b]];
+            else {
+                Philox rng;
+                rng.init(P.seed, (uint32_t)b, (uint32_t)(P.seg_lo + seg), 0u, 0xF111u);
+                m = pick_valid(rm, B, nvm, rng);
+            }
+        }
+        if (!(v > 0.0)) {
+            if (P.src_rv) v = rr[P.src_rv[seg * (long long)B + b]];
+            else {
+                Philox rng;
+                rng.init(P.seed, (uint32_t)b, (uint32_t)(P.seg_lo + seg), 0u, 0xF112u);
+                v = pick_valid(rr, B, nvr, rng);
+            }
+        }
+        om[b + 1] = log(m);
+        ov[b + 1] = log(v);
+    }
+}
+
+// ------------------------------------------------------------------ WLS functional (batched small solves)
+// For each distinct validity mask k: rows = valid groups; Z = [covariate | treatment] (R x (P + T)),
+// weights w.  Weighted-centre every column, orthogonalise the treatment columns against the
+// covariate columns (modified Gram-Schmidt in the w-inner product, rank-revealing), then
+// C[t, r] = w_r * a~_tr / sum_r w_r a~_tr^2.  One CTA per mask; the work matrix lives in global scratch.
+struct WlsParams {
+    const double* covariate;    // [R][P]
+    const double* treatment;    // [R][T]
+    const double* weights;      // [R]  (cells per group)
+    const unsigned char* masks; // [n_mask][R]
+    int R, Pc, T, n_mask;
+    int one_sample;             // treatment is all ones: weighted average over groups
+    double* scratch;            // [n_mask][R][Pc + T]
+    double* cmat;               // [n_mask][T][R]
+};
+
+__device__ double block_sum(double v, double* sred) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < kRegThreads / 32; ++w) tot += sred[w];
+    return tot;
+}
+
+__global__ void __launch_bounds__(kRegThreads)
+wls_functional_kernel(WlsParams P) {
+    __shared__ double sred[kRegThreads / 32];
+    const int k = blockIdx.x;
+    const int R = P.R, Pc = P.Pc, T = P.T, K = Pc + T;
+    const unsigned char* mask = P.masks + (long long)k * R;
+    double* Z = P.scratch + (long long)k * R * K;
+    double* C = P.cmat + (long long)k * T * R;
+    const int tid = threadIdx.x;
+
+    double wl = 0.0;
+    for (int r = tid; r < R; r += kRegThreads) wl += mask[r] ? P.weights[r] : 0.0;
+    const double wsum = block_sum(wl, sred);
+
+    if (P.one_sample) {
+        for (int i = tid; i < T * R; i += kRegThreads) {
+            int r = i % R;
+            C[i] = mask[r] ? P.weights[r] / wsum : 0.0;
+        }
+        return;
+    }
+    // load + weighted centring (the intercept of the reference's LinearRegression)
+    for (int c = 0; c < K; ++c) {
+        double s = 0.0;
+        for (int r = tid; r < R; r += kRegThreads) {
+            double v = c < Pc ? P.covariate[(long long)r * Pc + c] : P.treatment[(long long)r * T + (c - Pc)];
+            s += mask[r] ? P.weights[r] * v : 0.0;
+        }
+        double mu = block_sum(s, sred) / wsum;
+        for (int r = tid; r < R; r += kRegThreads) {
+            double v = c < Pc ? P.covariate[(long long)r * Pc + c] : P.treatment[(long long)r * T + (c - Pc)];
+            Z[(long long)r * K + c] = mask[r] ? v - mu : 0.0;
+        }
+    }
+    __syncthreads();
+    // modified Gram-Schmidt over the covariate columns; later columns (incl. treatment) are deflated
+    for (int c = 0; c < Pc; ++c) {
+        double s = 0.0, s0 = 0.0;
+        for (int r = tid; r < R; r += kRegThreads) {
+            double z = Z[(long long)r * K + c];
+            s += P.weights[r] * z * z;
+            double v0 = P.covariate[(long long)r * Pc + c];
+            s0 += mask[r] ? P.weights[r] * v0 * v0 : 0.0;
+        }
+        double nrm2 = block_sum(s, sred);
+        double ref2 = block_sum(s0, sred);
+        // numerically dependent column (e.g. an explicit intercept, or a dummy emptied by the mask)
+        if (!(nrm2 > 1e-20 * (ref2 > 0.0 ? ref2 : 1.0))) continue;
+        for (int c2 = c + 1; c2 < K; ++c2) {
+            double d = 0.0;
+            for (int r = tid; r < R; r += kRegThreads)
+                d += P.weights[r] * Z[(long long)r * K + c] * Z[(long long)r * K + c2];
+            double proj = block_sum(d, sred) / nrm2;
+            for (int r = tid; r < R; r += kRegThreads)
+                Z[(long long)r * K + c2] -= proj * Z[(long long)r * K + c];
+            __syncthreads();
+        }
+    }
+    for (int t = 0; t < T; ++t) {
+        double s = 0.0;
+        for (int r = tid; r < R; r += kRegThreads) {
+            double a = Z[(long long)r * K + Pc + t];
+            s += P.weights[r] * a * a;
+        }
+        double ss = block_sum(s, sred);
+        for (int r = tid; r < R; r += kRegThreads)
+            C[(long long)t * R + r] = mask[r] ? P.weights[r] * Z[(long long)r * K + Pc + t] / ss : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------ regression + ASL
+struct RegParams {
+    const double* boot[2];      // [n_gene][R][B+1]; boot[1] may be null (single statistic, 2D path)
+    int n_stat;
+    const unsigned char* seg_good;  // [n_gene][R]
+    const int* mask_id;         // [n_gene]
+    const double* cmat;         // [n_mask][T][R]
+    int R, T, B;
+    int approx;                 // 1: normal approximation of the ASL
+    double* coef_ws;            // optional [n_gene][n_stat][T][B+1] coefficient rows (for the GEV tail stage)
+    double* out_coef;           // [n_gene][n_stat][T]
+    double* out_se;
+    double* out_asl;
+    int* out_extreme;           // [n_gene][n_stat][T] extreme count (-1 when not applicable)
+    int* out_nnull;             // [n_gene][n_stat][T] null size
+};
+
+__global__ void __launch_bounds__(kRegThreads)
+regress_asl_kernel(RegParams P) {
+    __shared__ double s_stat[2][kMaxT];
+    __shared__ double s_red[kRegThreads / 32][2 * kMaxT][2];
+    __shared__ int s_cnt[kRegThreads / 32][2 * kMaxT][2];
+    __shared__ double s_mm[kRegThreads / 32][2 * kMaxT][2];
+    __shared__ int s_nvalid[kRegThreads / 32];
+    const int g = blockIdx.x;
+    const int R = P.R, T = P.T, B1 = P.B + 1, NS = P.n_stat;
+    const unsigned char* good = P.seg_good + (long long)g * R;
+    const double* C = P.cmat + (long long)P.mask_id[g] * T * R;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    int n_good = 0;
+    for (int r = 0; r < R; ++r) n_good += good[r];
+    const long long obase = (long long)g * NS * T;
+    if (n_good == 0) {   // reference hypothesis_test.py:203-204
+        for (int i = tid; i < NS * T; i += kRegThreads) {
+            P.out_coef[obase + i] = nan(""); P.out_se[obase + i] = nan(""); P.out_asl[obase + i] = nan("");
+            P.out_extreme[obase + i] = -1; P.out_nnull[obase + i] = 0;
+        }
+        return;
+    }
+
+    for (int t0 = 0; t0 < T; t0 += kMaxT) {
+        const int tn = min(kMaxT, T - t0);
+        // observed statistic = column 0
+        if (tid < NS * tn) {
+            int s = tid / tn, t = tid % tn;
+            const double* bt = P.boot[s] + (long long)g * R * B1;
+            double acc = 0.0;
+            for (int r = 0; r < R; ++r)
+                if (good[r]) acc = fma(C[(long long)(t0 + t) * R + r], bt[(long long)r * B1], acc);
+            s_stat[s][t] = acc;
+        }
+        __syncthreads();
+
+        double sum[2][kMaxT], sq[2][kMaxT], mn[2][kMaxT], mx[2][kMaxT];
+        int hi[2][kMaxT], lo[2][kMaxT];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                sum[s][t] = 0; sq[s][t] = 0; hi[s][t] = 0; lo[s][t] = 0;
+                mn[s][t] = INFINITY; mx[s][t] = -INFINITY;
+            }
+        int nvalid = 0;
+        for (int b = tid; b < B1; b += kRegThreads) {
+            double acc[2][kMaxT];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t) acc[s][t] = 0.0;
+            bool finite = true;
+            for (int r = 0; r < R; ++r) {
+                if (!good[r]) continue;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (s < NS) {
+                        double v = P.boot[s][((long long)g * R + r) * B1 + b];
+                        finite = finite && isfinite(v);
+#pragma unroll
+                        for (int t = 0; t < kMaxT; ++t)
+                            if (t < tn) acc[s][t] = fma(C[(long long)(t0 + t) * R + r], v, acc[s][t]);
+                    }
+                }
+            }
+            // reference :249-251: a column with a non-finite value in any valid group is dropped
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s < NS) {
+#pragma unroll
+                    for (int t = 0; t < kMaxT; ++t) {
+                        if (t < tn) {
+                            double c = finite ? acc[s][t] : nan("");
+                            if (P.coef_ws)
+                                P.coef_ws[(((long long)g * NS + s) * T + t0 + t) * B1 + b] = c;
+                            if (finite) {
+                                mn[s][t] = fmin(mn[s][t], c);
+                                mx[s][t] = fmax(mx[s][t], c);
+                                if (b > 0) {
+                                    double st = s_stat[s][t];
+                                    double d = c - st, a = fabs(st);
+                                    sum[s][t] += d;
+                                    sq[s][t] = fma(d, d, sq[s][t]);
+                                    hi[s][t] += (d > a);
+                                    lo[s][t] += (d < -a);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (finite && b > 0) ++nvalid;
+        }
+        // block reduction
+        nvalid = warp_sum_int(nvalid);
+        if (lane == 0) s_nvalid[warp] = nvalid;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                if (s < NS && t < tn) {
+                    double a = warp_sum(sum[s][t]), b2 = warp_sum(sq[s][t]);
+                    int h = warp_sum_int(hi[s][t]), l = warp_sum_int(lo[s][t]);
+                    double vmin = mn[s][t], vmax = mx[s][t];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, o));
+                        vmax = fmax(vmax, __shfl_xor_sync(kFull, vmax, o));
+                    }
+                    if (lane == 0) {
+                        s_red[warp][s * kMaxT + t][0] = a; s_red[warp][s * kMaxT + t][1] = b2;
+                        s_cnt[warp][s * kMaxT + t][0] = h; s_cnt[warp][s * kMaxT + t][1] = l;
+                        s_mm[warp][s * kMaxT + t][0] = vmin; s_mm[warp][s * kMaxT + t][1] = vmax;
+                    }
+                }
+            }
+        __syncthreads();
+        if (tid < NS * tn) {
+            int s = tid / tn, t = tid % tn, j = s * kMaxT + t;
+            double a = 0, b2 = 0, vmin = INFINITY, vmax = -INFINITY;
+            int h = 0, l = 0, n = 0;
+            for (int w = 0; w < kRegThreads / 32; ++w) {
+                a += s_red[w][j][0]; b2 += s_red[w][j][1];
+                h += s_cnt[w][j][0]; l += s_cnt[w][j][1];
+                vmin = fmin(vmin, s_mm[w][j][0]); vmax = fmax(vmax, s_mm[w][j][1]);
+                n += s_nvalid[w];
+            }
+            const double stat = s_stat[s][t];
+            const long long o = obase + (long long)s * T + t0 + t;
+            double mu = a / n, var = b2 / n - mu * mu;
+            if (var < 0) var = 0;
+            double sd = sqrt(var);
+            double asl;
+            int extreme = -1;
+            if (!(vmin < vmax)) {
+                asl = nan("");   // all coefficients identical (reference :62-64)
+            } else if (P.approx) {
+                double astat = fabs(stat), k = 1.0 / (sd * 1.4142135623730951);
+                asl = 0.5 * erfc((astat - mu) * k) + 0.5 * erfc((astat + mu) * k);   // :79-83
+            } else {
+                extreme = h + l;
+                asl = (double)(extreme + 1) / (double)(n + 1);                        // :92 (and the GEV fallback)
+            }
+            P.out_coef[o] = stat;
+            P.out_se[o] = (n > 0) ? sd : nan("");
+            P.out_asl[o] = asl;
+            P.out_extreme[o] = extreme;
+            P.out_nnull[o] = n;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+MM_EXPORT int mm_fill_log(int device, void* stream, const double* raw_mean, const double* raw_rv,
+                          const uint8_t* seg_ok, const double* true_mean, const double* true_rv,
+                          const int32_t* src_mean, const int32_t* src_rv, int64_t seg_lo, int64_t n_seg,
+                          int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
+                          uint8_t* seg_good, int32_t* n_valid) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(n_seg >= 0 && num_boot > 0, "n_seg/num_boot");
+    if (n_seg == 0) return 0;
+    MM_REQUIRE(raw_mean && raw_rv && seg_ok && true_mean && true_rv && boot_mean && boot_var && seg_good && n_valid,
+               "null pointer");
+    MM_REQUIRE(n_seg < 2147483647LL, "n_seg");
+    FillParams P;
+    P.raw_mean = raw_mean; P.raw_rv = raw_rv; P.seg_ok = seg_ok; P.true_mean = true_mean; P.true_rv = true_rv;
+    P.src_mean = src_mean; P.src_rv = src_rv; P.seg_lo = seg_lo; P.B = num_boot; P.seed = seed;
+    P.boot_mean = boot_mean; P.boot_var = boot_var; P.seg_good = seg_good; P.n_valid = n_valid;
+    fill_log_kernel<<<(unsigned)n_seg, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    return check_launch("mm_fill_log");
+}
+
+MM_EXPORT int mm_wls_functional(int device, void* stream, const double* covariate, const double* treatment,
+                                const double* weights, const uint8_t* masks, int32_t R, int32_t n_cov,
+                                int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(R > 0 && n_cov >= 0 && T > 0 && n_mask >= 0, "R/n_cov/T/n_mask");
+    if (n_mask == 0) return 0;
+    MM_REQUIRE(treatment && weights && masks && scratch && cmat && (covariate || n_cov == 0), "null pointer");
+    WlsParams P;
+    P.covariate = covariate; P.treatment = treatment; P.weights = weights; P.masks = masks;
+    P.R = R; P.Pc = n_cov; P.T = T; P.n_mask = n_mask; P.one_sample = one_sample;
+    P.scratch = scratch; P.cmat = cmat;
+    wls_functional_kernel<<<n_mask, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    return check_launch("mm_wls_functional");
+}
+
+MM_EXPORT int mm_regress_asl(int device, void* stream, const double* boot0, const double* boot1,
+                             const uint8_t* seg_good, const int32_t* mask_id, const double* cmat,
+                             int32_t n_gene, int32_t R, int32_t T, int32_t num_boot, int32_t approx,
+                             double* coef_ws, double* out_coef, double* out_se, double* out_asl,
+                             int32_t* out_extreme, int32_t* out_nnull) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(n_gene >= 0 && R > 0 && T > 0 && num_boot > 0, "n_gene/R/T/num_boot");
+    if (n_gene == 0) return 0;
+    MM_REQUIRE(boot0 && seg_good && mask_id && cmat && out_coef && out_se && out_asl && out_extreme && out_nnull,
+               "null pointer");
+    RegParams P;
+    P.boot[0] = boot0; P.boot[1] = boot1; P.n_stat = boot1 ? 2 : 1; P.seg_good = seg_good; P.mask_id = mask_id;
+    P.cmat = cmat; P.R = R; P.T = T; P.B = num_boot; P.approx = approx; P.coef_ws = coef_ws;
+    P.out_coef = out_coef; P.out_se = out_se; P.out_asl = out_asl; P.out_extreme = out_extreme;
+    P.out_nnull = out_nnull;
+    regress_asl_kernel<<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    return check_launch("mm_regress_asl");
+}

@@ -1,0 +1,16 @@
+"""memento_b200: B200-native drop-in for memento's estimation + bootstrap-testing hot path.
+
+    import memento_b200 as memento
+    memento.setup_memento(adata, q_column='q')
+    memento.create_groups(adata, label_columns=['stim', 'cell'])
+    memento.compute_1d_moments(adata)
+    memento.ht_1d_moments(adata, covariate=cov, treatment=tr, num_boot=10000, resampling='bootstrap')
+
+Same call signatures and ``adata.uns['memento']`` schema as the reference (memento/main.py).
+"""
+from .main import (compute_1d_moments, compute_2d_moments, create_groups, ht_1d_moments,  # noqa: F401
+                   ht_2d_moments, setup_memento)
+from .getters import get_1d_ht_result, get_1d_moments, get_groups  # noqa: F401
+from .anndata_lite import AnnDataLite  # noqa: F401
+
+__version__ = "0.1.0"

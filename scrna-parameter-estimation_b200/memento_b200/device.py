@@ -1,0 +1,199 @@
+"""Device-resident data layout and thin wrappers over the C ABI.
+
+Layout in HBM: the count matrix is kept as a *group-sorted CSC*:
+``vals`` float32 [nnz], ``rows`` int32 [nnz], ``seg_ptr`` int64 [G*R + 1] where segment
+``s = gene * R + group`` holds the nonzeros of one gene in one group; cells are renumbered so that
+each group is a contiguous row range, rows ascend inside a segment.  Per-cell vectors
+(``inv_sf`` float64, ``cell_bin`` uint8) are stored in the same renumbered order.
+
+PyTorch is used for device buffers, streams and the ingest-time re-layout (a stable sort of the
+nonzeros by (gene, group) key); every reduction / resampling / regression kernel is ours.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+BIG_SEG = 32768          # must match kBigSeg in csrc/moments.cu
+ENTRY_BYTES = 32         # sizeof(BootEntry)
+
+
+class StageTimer:
+    """Accumulates CUDA-event timings per named stage (used by bench.py for the roofline)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.pending = []
+        self.ms = {}
+        self.calls = {}
+
+    def start(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def stop(self, name, ev0):
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(torch.cuda.current_stream(self.device))
+        self.pending.append((name, ev0, ev1))
+
+    def collect(self):
+        torch.cuda.synchronize(self.device)
+        for name, e0, e1 in self.pending:
+            self.ms[name] = self.ms.get(name, 0.0) + e0.elapsed_time(e1)
+            self.calls[name] = self.calls.get(name, 0) + 1
+        self.pending = []
+        return dict(self.ms)
+
+
+class _NullTimer:
+    def start(self):
+        return None
+
+    def stop(self, name, ev0):
+        pass
+
+
+NULL_TIMER = _NullTimer()
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.MementoCudaError("memento_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    _lib.load()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def to_device(arr, device, dtype=None, pinned=False):
+    a = np.ascontiguousarray(arr)
+    if dtype is not None and a.dtype != dtype:
+        a = a.astype(dtype)
+    t = torch.from_numpy(a)
+    if pinned:
+        t = t.pin_memory()
+    return t.to(device, non_blocking=pinned)
+
+
+class CsrOnDevice:
+    """The input matrix as uploaded: indptr int64, indices int32, data float32."""
+
+    def __init__(self, X, device, pinned=False):
+        self.shape = X.shape
+        self.device = device
+        data = X.data
+        if data.dtype != np.float32:
+            data32 = data.astype(np.float32)
+            if not np.array_equal(data32.astype(data.dtype), data):
+                raise ValueError("counts are not exactly representable in float32")
+            data = data32
+        self.h2d_bytes = data.nbytes + X.indices.size * 4 + (X.shape[0] + 1) * 8
+        self.indptr = to_device(X.indptr, device, np.int64, pinned)
+        self.indices = to_device(X.indices, device, np.int32, pinned)
+        self.data = to_device(data, device, np.float32, pinned)
+        self.nnz = int(self.data.numel())
+
+    def row_sums(self, gene_mask=None, timer=NULL_TIMER):
+        out = torch.empty(self.shape[0], dtype=torch.float64, device=self.device)
+        ev = timer.start()
+        _lib.call("mm_csr_row_sums", self.device, self.indptr, self.indices, self.data, self.shape[0],
+                  gene_mask, out)
+        timer.stop("csr_row_sums", ev)
+        return out
+
+
+class SegMatrix:
+    """Group-sorted CSC (see module docstring).  Immutable once built."""
+
+    def __init__(self, vals, rows, seg_ptr, n_genes, n_groups, n_cells):
+        self.vals, self.rows, self.seg_ptr = vals, rows, seg_ptr
+        self.G, self.R, self.n_cells = int(n_genes), int(n_groups), int(n_cells)
+        self.device = vals.device
+        self.nnz = int(vals.numel())
+        self._big = None
+
+    @property
+    def n_seg(self):
+        return self.G * self.R
+
+    # ------------------------------------------------------------------ construction (ingest plumbing)
+    @staticmethod
+    def from_csr(csr, group_of_cell=None, n_groups=1, rank_of_cell=None):
+        """Re-layout of the uploaded CSR: stable sort of the nonzeros by key gene * R + group.
+        ``group_of_cell`` / ``rank_of_cell`` are int32 device vectors in ORIGINAL cell order."""
+        n_cells, n_genes = csr.shape
+        dev = csr.device
+        counts = csr.indptr[1:] - csr.indptr[:-1]
+        row_of_nnz = torch.repeat_interleave(torch.arange(n_cells, device=dev, dtype=torch.int32), counts)
+        return SegMatrix._from_coo(csr.data, row_of_nnz, csr.indices, n_cells, n_genes, group_of_cell,
+                                   n_groups, rank_of_cell)
+
+    @staticmethod
+    def _from_coo(vals, row_of_nnz, col_of_nnz, n_cells, n_genes, group_of_cell, n_groups, rank_of_cell):
+        dev = vals.device
+        key = col_of_nnz.to(torch.int64)
+        if group_of_cell is not None:
+            key = key * n_groups + group_of_cell[row_of_nnz.long()].to(torch.int64)
+            new_rows = rank_of_cell[row_of_nnz.long()]
+        else:
+            new_rows = row_of_nnz
+        order = torch.argsort(key, stable=True)
+        seg_len = torch.bincount(key, minlength=n_genes * n_groups)
+        seg_ptr = torch.zeros(n_genes * n_groups + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(seg_len, 0, out=seg_ptr[1:])
+        return SegMatrix(vals[order].contiguous(), new_rows[order].to(torch.int32).contiguous(), seg_ptr,
+                         n_genes, n_groups, n_cells)
+
+    def regroup(self, group_of_cell, n_groups, rank_of_cell):
+        """From an ungrouped (R == 1) matrix to a grouped one."""
+        assert self.R == 1
+        seg_len = self.seg_ptr[1:] - self.seg_ptr[:-1]
+        col_of_nnz = torch.repeat_interleave(torch.arange(self.G, device=self.device, dtype=torch.int32), seg_len)
+        return SegMatrix._from_coo(self.vals, self.rows, col_of_nnz, self.n_cells, self.G, group_of_cell,
+                                   n_groups, rank_of_cell)
+
+    def select_genes(self, gene_idx):
+        """New matrix with only the genes ``gene_idx`` (ascending numpy int array)."""
+        dev = self.device
+        gi = torch.as_tensor(np.asarray(gene_idx, dtype=np.int64), device=dev)
+        R = self.R
+        seg_ids = (gi[:, None] * R + torch.arange(R, device=dev)[None, :]).reshape(-1)
+        lo = self.seg_ptr[seg_ids]
+        ln = self.seg_ptr[seg_ids + 1] - lo
+        new_ptr = torch.zeros(seg_ids.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(ln, 0, out=new_ptr[1:])
+        total = int(new_ptr[-1].item())
+        # source index of every kept nonzero: lo[seg] + (position - new_ptr[seg])
+        seg_of = torch.repeat_interleave(torch.arange(seg_ids.numel(), device=dev), ln, output_size=total)
+        src = lo[seg_of] + (torch.arange(total, device=dev) - new_ptr[seg_of])
+        return SegMatrix(self.vals[src].contiguous(), self.rows[src].contiguous(), new_ptr, gi.numel(), R,
+                         self.n_cells)
+
+    # ------------------------------------------------------------------ kernels
+    def moments(self, inv_sf, timer=NULL_TIMER):
+        """(5, G, R) float64 on the device: sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2."""
+        out = torch.empty(5 * self.n_seg, dtype=torch.float64, device=self.device)
+        if self._big is None:
+            self._big = torch.zeros(self.nnz // BIG_SEG + 2, dtype=torch.int32, device=self.device)
+        ev = timer.start()
+        _lib.call("mm_seg_moments", self.device, self.vals, self.rows, self.seg_ptr, self.n_seg, inv_sf, out,
+                  self._big)
+        timer.stop("seg_moments", ev)
+        return out.view(5, self.G, self.R)
+
+    def moments_bytes(self):
+        """Algorithmic bytes of one mm_seg_moments launch."""
+        return self.nnz * 8 + (self.n_seg + 1) * 8 + self.n_cells * 8 + 5 * self.n_seg * 8
+
+    def pair_products(self, idx1, idx2, inv_sf, timer=NULL_TIMER):
+        n = int(idx1.numel())
+        out = torch.empty(n * self.R, dtype=torch.float64, device=self.device)
+        ev = timer.start()
+        _lib.call("mm_pair_products", self.device, self.vals, self.rows, self.seg_ptr, self.R, idx1, idx2, n,
+                  inv_sf, out)
+        timer.stop("pair_products", ev)
+        return out.view(n, self.R)

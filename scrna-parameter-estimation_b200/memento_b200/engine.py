@@ -1,0 +1,200 @@
+"""Tiled 1D hypothesis-test engine: compression -> bootstrap -> imputation/log -> WLS functional ->
+regression + ASL, over tiles of genes.  Everything between the uploads and the result download
+runs in our CUDA kernels (csrc/); the only host step per tile is grouping the genes by their
+group-validity mask (a (tile_genes x R) byte matrix) so that the small solves are shared.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .device import ENTRY_BYTES, NULL_TIMER
+
+
+class GroupDesign:
+    """Per-group vectors on the device, in group order (length R)."""
+
+    def __init__(self, device, n_cells, q, mv_fit, n_bins_present, bin_inv_sf):
+        self.R = len(n_cells)
+        self.n_cells_host = np.asarray(n_cells, dtype=np.int64)
+        self.n_cells = torch.as_tensor(np.asarray(n_cells, dtype=np.int32), device=device)
+        self.q = torch.as_tensor(np.asarray(q, dtype=np.float64), device=device)
+        self.mv_fit = torch.as_tensor(np.ascontiguousarray(mv_fit, dtype=np.float64), device=device)
+        self.n_bins_present = torch.as_tensor(np.asarray(n_bins_present, dtype=np.int32), device=device)
+        self.bin_inv_sf = torch.as_tensor(np.asarray(bin_inv_sf, dtype=np.float64), device=device)
+        self.n_bins = int(self.bin_inv_sf.numel())
+
+
+def tile_plan(seg, num_boot, workspace_bytes=6 << 30):
+    """Genes per tile: bounded by the bootstrap grid (65535 segments) and by the workspace
+    (32 bytes per (segment, replicate): raw mean/rv + log mean/var)."""
+    per_seg = 32 * (num_boot + 1)
+    max_seg = max(seg.R, min(65535, workspace_bytes // per_seg))
+    return max(1, max_seg // seg.R)
+
+
+def unique_tables(seg, design, cell_bin, gene_lo, n_genes, estimator, timer=NULL_TIMER, want_raw=False):
+    """Run mm_seg_unique on genes [gene_lo, gene_lo + n_genes).  Returns a dict of device tensors."""
+    dev = seg.device
+    R = seg.R
+    seg_lo, n_seg = gene_lo * R, n_genes * R
+    lo, hi = (int(v) for v in seg.seg_ptr[[seg_lo, seg_lo + n_seg]].tolist())
+    pool = max(hi - lo, 1)
+    entries = torch.empty(pool * ENTRY_BYTES, dtype=torch.uint8, device=dev)
+    raw_key = torch.empty(pool, dtype=torch.int32, device=dev) if want_raw else None
+    raw_cnt = torch.empty(pool, dtype=torch.int32, device=dev) if want_raw else None
+    seg_U = torch.empty(n_seg, dtype=torch.int32, device=dev)
+    big = torch.zeros(n_seg + 1, dtype=torch.int32, device=dev)
+    seg_len = seg.seg_ptr[seg_lo + 1:seg_lo + n_seg + 1] - seg.seg_ptr[seg_lo:seg_lo + n_seg]
+    need_scratch = bool((seg_len > 6144).any().item())
+    sc_n = 3 * pool if need_scratch else 1
+    sk = torch.empty(sc_n, dtype=torch.int32, device=dev)
+    sc = torch.empty(sc_n, dtype=torch.int32, device=dev)
+    ev = timer.start()
+    _lib.call("mm_seg_unique", dev, seg.vals, seg.rows, seg.seg_ptr, seg_lo, n_seg, R, cell_bin,
+              design.bin_inv_sf, design.n_bins, design.q, design.n_cells, design.n_bins_present,
+              estimator, entries, raw_key, raw_cnt, seg_U, big, sk, sc)
+    timer.stop("seg_unique", ev)
+    return {"entries": entries, "raw_key": raw_key, "raw_cnt": raw_cnt, "seg_U": seg_U, "pool_lo": lo,
+            "pool": pool, "nnz": hi - lo, "seg_lo": seg_lo, "n_seg": n_seg}
+
+
+def unique_bytes(tab, n_cells):
+    """Algorithmic bytes of one mm_seg_unique launch: nnz * (4 + 4) in, per-cell bin gather,
+    seg_ptr, and the entry records written."""
+    total_U = int(tab["seg_U"].clamp(min=0).sum().item())
+    return tab["nnz"] * 8 + n_cells * 1 + (tab["n_seg"] + 1) * 8 + total_U * ENTRY_BYTES + tab["n_seg"] * 4
+
+
+def wls_functional(device, covariate, treatment, weights, masks, one_sample, timer=NULL_TIMER):
+    """masks: (n_mask, R) uint8 numpy.  Returns cmat (n_mask, T, R) on the device."""
+    R, P = covariate.shape
+    T = treatment.shape[1]
+    n_mask = masks.shape[0]
+    cov_d = torch.as_tensor(np.ascontiguousarray(covariate, dtype=np.float64), device=device)
+    tr_d = torch.as_tensor(np.ascontiguousarray(treatment, dtype=np.float64), device=device)
+    w_d = torch.as_tensor(np.ascontiguousarray(weights, dtype=np.float64), device=device)
+    m_d = torch.as_tensor(np.ascontiguousarray(masks, dtype=np.uint8), device=device)
+    scratch = torch.empty(max(1, n_mask * R * (P + T)), dtype=torch.float64, device=device)
+    cmat = torch.empty(n_mask * T * R, dtype=torch.float64, device=device)
+    ev = timer.start()
+    _lib.call("mm_wls_functional", device, cov_d if P > 0 else None, tr_d, w_d, m_d, R, P, T, n_mask,
+              1 if one_sample else 0, scratch, cmat)
+    timer.stop("wls_functional", ev)
+    return cmat.view(n_mask, T, R)
+
+
+def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, treatment, weights, one_sample,
+                 approx, want_coef_rows, timer=NULL_TIMER):
+    """Shared tail of the 1D and 2D tests for one tile.  boot*: (n_gene*R, B+1) device tensors,
+    seg_good: (n_gene*R,) uint8 device.  Returns dict of host arrays (n_gene, n_stat, T) + coef rows."""
+    n_gene = seg_good.numel() // R
+    n_stat = 2 if boot1 is not None else 1
+    good_h = seg_good.view(n_gene, R).cpu().numpy()
+    masks, inverse = np.unique(good_h, axis=0, return_inverse=True)
+    cmat = wls_functional(device, covariate, treatment, weights, masks, one_sample, timer)
+    mask_id = torch.as_tensor(np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32), device=device)
+    n_out = n_gene * n_stat * T
+    out_coef = torch.empty(n_out, dtype=torch.float64, device=device)
+    out_se = torch.empty(n_out, dtype=torch.float64, device=device)
+    out_asl = torch.empty(n_out, dtype=torch.float64, device=device)
+    out_ext = torch.empty(n_out, dtype=torch.int32, device=device)
+    out_nn = torch.empty(n_out, dtype=torch.int32, device=device)
+    coef_ws = torch.empty(n_out * (num_boot + 1), dtype=torch.float64, device=device) if want_coef_rows else None
+    ev = timer.start()
+    _lib.call("mm_regress_asl", device, boot0, boot1, seg_good, mask_id, cmat, n_gene, R, T, num_boot,
+              1 if approx else 0, coef_ws, out_coef, out_se, out_asl, out_ext, out_nn)
+    timer.stop("regress_asl", ev)
+    shp = (n_gene, n_stat, T)
+    return {"coef": out_coef.view(shp), "se": out_se.view(shp), "asl": out_asl.view(shp),
+            "extreme": out_ext.view(shp), "n_null": out_nn.view(shp),
+            "coef_rows": coef_ws.view(n_gene, n_stat, T, num_boot + 1) if want_coef_rows else None,
+            "n_masks": masks.shape[0]}
+
+
+def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,
+               estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None):
+    """One tile of genes through the whole test.  true_mean / true_rv: (n_genes, R) host arrays."""
+    dev = seg.device
+    R = seg.R
+    T = treatment.shape[1]
+    n_seg = n_genes * R
+    tab = unique_tables(seg, design, cell_bin, gene_lo, n_genes, estimator, timer)
+    # a-priori validity: reference hypothesis_test.py:167-171
+    with np.errstate(invalid="ignore"):
+        ok = ~(np.isnan(true_mean) | np.isnan(true_rv) | (true_mean == 0) | (true_rv < 0))
+    seg_ok = torch.as_tensor(np.ascontiguousarray(ok.reshape(-1), dtype=np.uint8), device=dev)
+    seg_skip = (seg_ok == 0).to(torch.uint8)
+    tm = torch.as_tensor(np.ascontiguousarray(true_mean.reshape(-1), dtype=np.float64), device=dev)
+    tv = torch.as_tensor(np.ascontiguousarray(true_rv.reshape(-1), dtype=np.float64), device=dev)
+    raw_mean = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
+    raw_rv = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
+    ev = timer.start()
+    _lib.call("mm_bootstrap_1d", dev, tab["entries"], seg.seg_ptr, tab["seg_lo"], n_seg, R, tab["seg_U"],
+              seg_skip, design.n_cells, design.mv_fit, estimator, num_boot, seed, raw_mean, raw_rv)
+    timer.stop("bootstrap_1d", ev)
+    if stats is not None:
+        u = tab["seg_U"].clamp(min=0) * seg_ok.to(torch.int32)
+        stats["category_draws"] = stats.get("category_draws", 0) + int(u.sum().item()) * num_boot
+        stats["unique_bytes"] = stats.get("unique_bytes", 0) + unique_bytes(tab, seg.n_cells)
+        stats["segments"] = stats.get("segments", 0) + n_seg
+    boot_mean = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
+    boot_var = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
+    seg_good = torch.empty(n_seg, dtype=torch.uint8, device=dev)
+    n_valid = torch.empty(2 * n_seg, dtype=torch.int32, device=dev)
+    ev = timer.start()
+    _lib.call("mm_fill_log", dev, raw_mean, raw_rv, seg_ok, tm, tv, None, None, tab["seg_lo"], n_seg, num_boot,
+              seed, boot_mean, boot_var, seg_good, n_valid)
+    timer.stop("fill_log", ev)
+    del raw_mean, raw_rv
+    res = regress_tile(dev, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
+                       design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer)
+    if stats is not None:
+        stats["launches"] = stats.get("launches", 0) + 7  # unique x2, bootstrap, fill, wls, regress (+memset)
+    return res
+
+
+def ht_1d_replay(device, R, replay, design_host, true_mean, true_rv, covariate, treatment, num_boot, estimator,
+                 approx, one_sample, want_coef_rows, timer=NULL_TIMER):
+    """Deterministic parity mode: host-supplied unique tables, resample counts and imputation
+    sources (``replay`` dict: tab_ptr, x, inv_sf, W, src_mean, src_rv) instead of the compression
+    and RNG kernels; the moment, imputation/log, WLS and regression kernels are the product ones.
+    ``design_host``: dict with n_cells (R,), q (R,), mv_fit (R, 3)."""
+    n_genes = true_mean.shape[0]
+    n_seg = n_genes * R
+    T = treatment.shape[1]
+    assert n_seg <= 65535, "replay mode is for small parity cases"
+    tab_ptr = np.asarray(replay["tab_ptr"], dtype=np.int64)
+    assert tab_ptr.shape[0] == n_seg + 1
+    r_of = np.arange(n_seg) % R
+    d = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)  # noqa: E731
+    x = d(replay["x"] if len(replay["x"]) else np.zeros(1), np.float64)
+    inv_sf = d(replay["inv_sf"] if len(replay["inv_sf"]) else np.zeros(1), np.float64)
+    W = d(replay["W"] if len(replay["W"]) else np.zeros(1), np.int64)
+    raw_mean = torch.empty(n_seg * num_boot, dtype=torch.float64, device=device)
+    raw_var = torch.empty(n_seg * num_boot, dtype=torch.float64, device=device)
+    raw_rv = torch.empty(n_seg * num_boot, dtype=torch.float64, device=device)
+    _lib.call("mm_bootstrap_1d_replay", device, x, inv_sf, W, d(tab_ptr, np.int64),
+              d(np.asarray(design_host["n_cells"])[r_of], np.int32), d(np.asarray(design_host["q"])[r_of], np.float64),
+              d(np.asarray(design_host["mv_fit"])[r_of], np.float64), n_seg, num_boot, estimator,
+              raw_mean, raw_var, raw_rv)
+    with np.errstate(invalid="ignore"):
+        ok = ~(np.isnan(true_mean) | np.isnan(true_rv) | (true_mean == 0) | (true_rv < 0))
+    seg_ok = d(ok.reshape(-1), np.uint8)
+    boot_mean = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=device)
+    boot_var = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=device)
+    seg_good = torch.empty(n_seg, dtype=torch.uint8, device=device)
+    n_valid = torch.empty(2 * n_seg, dtype=torch.int32, device=device)
+    src_m = d(replay["src_mean"], np.int32) if replay.get("src_mean") is not None else None
+    src_v = d(replay["src_rv"], np.int32) if replay.get("src_rv") is not None else None
+    _lib.call("mm_fill_log", device, raw_mean, raw_rv, seg_ok, d(true_mean.reshape(-1), np.float64),
+              d(true_rv.reshape(-1), np.float64), src_m, src_v, 0, n_seg, num_boot, 0, boot_mean, boot_var,
+              seg_good, n_valid)
+    res = regress_tile(device, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
+                       np.asarray(design_host["n_cells"], dtype=np.float64), one_sample, approx, want_coef_rows, timer)
+    res["raw_mean"] = raw_mean.view(n_seg, num_boot)
+    res["raw_var"] = raw_var.view(n_seg, num_boot)
+    res["raw_rv"] = raw_rv.view(n_seg, num_boot)
+    res["boot_mean"] = boot_mean.view(n_seg, num_boot + 1)
+    res["boot_var"] = boot_var.view(n_seg, num_boot + 1)
+    res["seg_good"] = seg_good
+    return res

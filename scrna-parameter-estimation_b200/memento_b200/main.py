@@ -1,0 +1,451 @@
+"""Public API: the six calls of the reference's hot path, same signatures, same
+``adata.uns['memento']`` schema (reference memento/main.py:26-520), computed on a B200.
+
+Host side: AnnData / scipy.sparse in, pandas / numpy out.  The arithmetic over cells (row sums,
+per-(gene, group) moments, compression, bootstrap, regression, ASL) runs in the CUDA kernels of
+``csrc/`` through the C ABI; the only numpy arithmetic left is over G- or Nc-length vectors
+(quantiles, the quadratic log-log fit, size-factor binning), where the reference's exact
+``np.quantile`` / ``np.polyfit`` / ``binned_statistic`` semantics are part of the contract.
+There is no CPU fallback: without a CUDA device or the built library every call raises.
+"""
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+import scipy.stats as stats
+import torch
+
+from . import _lib, engine, gev
+from .device import NULL_TIMER, CsrOnDevice, SegMatrix, StageTimer, require_cuda, to_device
+
+ESTIMATORS = {"hyper_relative": 0, "mean_only": 1}
+_UNDEFINED_IN_REFERENCE = ("hyper_absolute", "poi_absolute", "poi_relative")  # NameError there too
+
+
+# --------------------------------------------------------------------------- state
+class DeviceState:
+    """Device-resident buffers attached to ``adata.uns['memento']['_b200']``.  Buffers are never
+    mutated after creation, so copies of the AnnData share them."""
+
+    def __init__(self, device):
+        self.device = device
+        self.csr = None          # CsrOnDevice (dropped after create_groups)
+        self.seg_all = None      # SegMatrix with R == 1 (all cells)
+        self.seg = None          # grouped SegMatrix, columns == current adata.var
+        self.inv_sf_sorted = None
+        self.cell_bin = None
+        self.design = None
+        self.order = None        # host: original cell index of every sorted position
+        self.group_start = None  # host int64 [R + 1]
+        self.timer = NULL_TIMER
+        self.h2d_bytes = 0
+        self.codes = None        # host: group code of every cell (original order)
+        self.gene_index = None   # host: original column of every current gene
+        self.bin_inv_sf = None
+        self.n_bins_present = None
+        self.cell_bin_host = None
+        self.last_stats = {}
+
+    def __deepcopy__(self, memo):
+        new = DeviceState(self.device)
+        new.__dict__.update(self.__dict__)
+        return new
+
+
+class LazyGroupCells:
+    """Stand-in for the reference's per-group CSC copies (``uns['memento']['group_cells'][g]``,
+    reference util.py:8-13): has ``.shape`` immediately, builds the scipy matrix on first use."""
+
+    def __init__(self, X, cell_idx, gene_idx):
+        self._X, self._cells, self._genes = X, cell_idx, gene_idx
+        self._mat = None
+
+    @property
+    def shape(self):
+        return (len(self._cells), len(self._genes))
+
+    def materialize(self):
+        if self._mat is None:
+            self._mat = self._X[self._cells, :][:, self._genes].tocsc()
+        return self._mat
+
+    def with_genes(self, gene_idx):
+        return LazyGroupCells(self._X, self._cells, gene_idx)
+
+    def __getitem__(self, key):
+        return self.materialize()[key]
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
+def _state(adata):
+    st = adata.uns["memento"].get("_b200")
+    if st is None:
+        raise RuntimeError("call setup_memento first (no device state attached to this AnnData)")
+    return st
+
+
+def _estimator_code(estimator_type):
+    if isinstance(estimator_type, str) and estimator_type in ESTIMATORS:
+        return ESTIMATORS[estimator_type]
+    if estimator_type in _UNDEFINED_IN_REFERENCE:
+        raise NameError("estimator_type %r is not defined in the reference either (estimator.py:19-46)"
+                        % (estimator_type,))
+    raise NotImplementedError("custom estimator callables cannot run on the device; use 'hyper_relative' "
+                              "or 'mean_only'")
+
+
+def _moments_from_sums(sums, n_obs, q, estimator):
+    """sums: (5, ...) arrays [sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2].
+    reference estimator.py:179-185 / :200-204."""
+    m1 = sums[2] / n_obs
+    if estimator == 1:
+        return m1 + 1, np.ones(m1.shape) * 10
+    m2 = sums[4] / n_obs - (1 - q) * sums[3] / n_obs
+    return m1, m2 - m1 ** 2
+
+
+def _fit_mv(mean, var):
+    keep = (mean > 0) & (var > 0)                                   # reference estimator.py:89-92
+    return np.polyfit(np.log(mean[keep]), np.log(var[keep]), 2)
+
+
+def _residual_variance(mean, var, fit):
+    keep = (mean > 0) & (var > 0)                                   # reference estimator.py:105-110
+    out = np.full(mean.shape, np.nan)
+    with np.errstate(invalid="ignore"):
+        out[keep] = np.exp(np.log(var[keep]) - np.polyval(fit, np.log(mean[keep])))
+    return out
+
+
+# --------------------------------------------------------------------------- setup_memento
+def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_percent=0.1, shrinkage=0.5,
+                  num_bins=30, estimator_type="hyper_relative", device=None, profile=False, pinned=False):
+    """Compute size factors and the overall moments.  reference: main.py:26-91.
+
+    Build-only keywords: ``device`` (CUDA device), ``profile`` (collect per-kernel CUDA-event
+    times in ``uns['memento']['_b200'].timer``), ``pinned`` (stage uploads through pinned memory)."""
+    if not inplace:
+        adata = adata.copy()
+    assert adata.obs[q_column].max() < 1
+    assert type(adata.X) == sp.csr_matrix, "please make sure that adata.X is a scipy CSR matrix"
+    estimator = _estimator_code(estimator_type)
+    if "absolute" in str(estimator_type):
+        raise NameError(estimator_type)
+    dev = require_cuda(device)
+    if not (0 < num_bins <= 254):
+        raise ValueError("num_bins must be in 1..254 on the device path")
+
+    mem = adata.uns["memento"] = {}
+    mem["q_column"] = q_column
+    mem["all_q"] = adata.obs[q_column].values.mean()
+    mem["estimator_type"] = estimator_type
+    mem["filter_mean_thresh"] = filter_mean_thresh
+    mem["num_bins"] = num_bins
+    st = DeviceState(dev)
+    st.timer = StageTimer(dev) if profile else NULL_TIMER
+    mem["_b200"] = st
+
+    X = adata.X
+    n_cells, n_genes = X.shape
+    if not X.has_sorted_indices:
+        X = X.sorted_indices()
+    st.csr = CsrOnDevice(X, dev, pinned)
+    st.h2d_bytes += st.csr.h2d_bytes
+    st.seg_all = SegMatrix.from_csr(st.csr)
+
+    # naive size factor = raw UMI totals (main.py:55-59); moments over all cells (:62-66)
+    naive = st.csr.row_sums(None, st.timer)
+    sums = st.seg_all.moments(1.0 / naive, st.timer).cpu().numpy()[:, :, 0]
+    all_m, all_v = _moments_from_sums(sums, n_cells, mem["all_q"], 0)
+    all_m[sums[0] / n_cells < filter_mean_thresh] = 0                                      # :67
+    rv = _residual_variance(all_m, all_v, _fit_mv(all_m, all_v))                           # :68
+    rv_ulim = np.quantile(rv[np.isfinite(rv)], trim_percent)                               # :71
+    rv[~np.isfinite(rv)] = np.inf
+    mask = rv < rv_ulim
+    mem["least_variable_genes"] = adata.var.index[mask].tolist()
+
+    # size factor from the least variable genes (main.py:78-82 -> estimator.py:73-76)
+    mask_d = to_device(mask.astype(np.uint8), dev)
+    totals = st.csr.row_sums(mask_d, st.timer).cpu().numpy()
+    totals = totals + np.quantile(totals, shrinkage)
+    size_factor = totals / totals.mean()
+    adata.obs["memento_size_factor"] = size_factor
+
+    inv_sf = to_device(1.0 / size_factor, dev, np.float64)
+    sums = st.seg_all.moments(inv_sf, st.timer).cpu().numpy()[:, :, 0]
+    all_m, all_v = _moments_from_sums(sums, n_cells, mem["all_q"], estimator)              # :86-91
+    mem["all_1d_moments"] = [all_m, all_v]
+    # reference quirk kept: with inplace=False the copy is not returned (main.py:39-40)
+
+
+# --------------------------------------------------------------------------- create_groups
+def create_groups(adata, label_columns, label_delimiter="^", inplace=True):
+    """Creates discrete groups of the data.  reference: main.py:94-135."""
+    if not inplace:
+        adata = adata.copy()
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    label = "sg" + label_delimiter
+    for idx, col in enumerate(label_columns):
+        label = label + adata.obs[col].astype(str)
+        if idx != len(label_columns) - 1:
+            label = label + label_delimiter
+    adata.obs["memento_group"] = label
+    mem["label_columns"] = label_columns
+    mem["label_delimiter"] = label_delimiter
+    codes, uniques = pd.factorize(adata.obs["memento_group"], sort=False)   # first-appearance order (:124)
+    mem["groups"] = [str(u) for u in uniques]
+    mem["q"] = adata.obs[mem["q_column"]].values
+    R = len(mem["groups"])
+    codes = codes.astype(np.int32)
+    order = np.argsort(codes, kind="stable")
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    counts = np.bincount(codes, minlength=R)
+    st.order = order
+    st.group_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    st.codes = codes
+
+    gid_d = to_device(codes, st.device, np.int32)
+    rank_d = to_device(rank, st.device, np.int32)
+    st.seg = st.seg_all.regroup(gid_d, R, rank_d)
+    st.csr = None
+    st.gene_index = np.arange(adata.shape[1])
+    X = adata.X
+    mem["group_cells"] = {g: LazyGroupCells(X, order[st.group_start[r]:st.group_start[r + 1]], st.gene_index)
+                          for r, g in enumerate(mem["groups"])}
+    q_sum = np.bincount(codes, weights=mem["q"], minlength=R)
+    mem["group_q"] = {g: q_sum[r] / counts[r] for r, g in enumerate(mem["groups"])}
+    if not inplace:
+        return adata
+
+
+def _bin_size_factor(adata):
+    """reference: main.py:138-153 (scipy binned_statistic semantics are part of the contract)."""
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    size_factor = adata.obs["memento_size_factor"].values
+    binned = stats.binned_statistic(size_factor, size_factor, bins=mem["num_bins"], statistic="mean")
+    bin_idx = np.clip(binned[2], a_min=1, a_max=binned[0].shape[0])
+    approx_sf = binned[0][bin_idx - 1]
+    max_sf = size_factor.max()
+    is_max = size_factor == max_sf
+    approx_sf[is_max] = max_sf
+    mem["all_approx_size_factor"] = approx_sf
+    codes = st.codes
+    mem["approx_size_factor"] = {g: approx_sf[codes == r] for r, g in enumerate(mem["groups"])}
+    mem["size_factor"] = {g: size_factor[codes == r] for r, g in enumerate(mem["groups"])}
+    # device side: bin id per cell (the max cells get their own id) + 1/approx_sf per bin id
+    nb = binned[0].shape[0]
+    cell_bin = (bin_idx - 1).astype(np.int64)
+    cell_bin[is_max] = nb
+    bin_value = np.concatenate([binned[0], [max_sf]])
+    st.bin_inv_sf = 1.0 / bin_value
+    st.cell_bin_host = cell_bin
+    st.cell_bin = to_device(cell_bin[st.order].astype(np.uint8), st.device)
+    st.inv_sf_sorted = to_device(1.0 / size_factor[st.order], st.device, np.float64)
+    R = len(mem["groups"])
+    st.n_bins_present = np.array([np.unique(cell_bin[codes == r]).size for r in range(R)], dtype=np.int32)
+
+
+# --------------------------------------------------------------------------- compute_1d_moments
+def compute_1d_moments(adata, inplace=True, min_perc_group=0.7, filter_genes=True, gene_list=None):
+    """Mean, variance and residual variance in each group.  reference: main.py:171-274."""
+    assert "memento" in adata.uns
+    if not inplace:
+        adata = adata.copy()
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    if "size_factor" not in mem:
+        _bin_size_factor(adata)
+    groups = mem["groups"]
+    R = len(groups)
+    estimator = _estimator_code(mem["estimator_type"])
+    n_cells = np.diff(st.group_start).astype(np.float64)
+    group_q = np.array([mem["group_q"][g] for g in groups])
+
+    sums = st.seg.moments(st.inv_sf_sorted, st.timer).cpu().numpy()          # (5, G, R)
+    mean, var = _moments_from_sums(sums, n_cells[None, :], group_q[None, :], estimator)
+    obs_mean = sums[0] / n_cells[None, :]
+    gene_filter = (obs_mean > mem["filter_mean_thresh"]) & (var > 0)         # main.py:201-204
+    rv_filter = sums[1] >= 2                                                  # :206-207
+    mem["gene_filter"] = {g: gene_filter[:, r].copy() for r, g in enumerate(groups)}
+    overall = gene_filter.mean(axis=1) > min_perc_group                       # :210-212
+    mem["overall_gene_filter"] = overall
+    mem["gene_list"] = adata.var.index[overall].tolist()
+    if filter_genes:                                                          # :219-229
+        keep = np.flatnonzero(overall)
+        st.seg = st.seg.select_genes(keep)
+        st.gene_index = st.gene_index[keep]
+        mean, var, rv_filter = mean[keep], var[keep], rv_filter[keep]
+        mem["group_cells"] = {g: mem["group_cells"][g].with_genes(st.gene_index) for g in groups}
+        adata._inplace_subset_var(overall)
+    mem["gene_rv_filter"] = {g: rv_filter[:, r].copy() for r, g in enumerate(groups)}
+
+    # pooled mean-variance trend over the groups' (mean, var), concatenated in group order (:232-245)
+    mean_cat = np.concatenate([mean[rv_filter[:, r], r] for r in range(R)])
+    var_cat = np.concatenate([var[rv_filter[:, r], r] for r in range(R)])
+    pooled = _fit_mv(mean_cat, var_cat)
+    mem["mv_regressor"] = {"all": pooled}
+    for g in groups:
+        mem["mv_regressor"][g] = pooled.copy()
+    mem["1d_moments"] = {}
+    for r, g in enumerate(groups):                                            # :248-255
+        m, v = mean[:, r].copy(), var[:, r].copy()
+        mem["1d_moments"][g] = [m, v, _residual_variance(m, v, mem["mv_regressor"][g])]
+    if gene_list is not None:                                                 # :258-271
+        assert type(gene_list) == list
+        given = np.isin(adata.var.index.values, gene_list)
+        keep = np.flatnonzero(given)
+        st.seg = st.seg.select_genes(keep)
+        st.gene_index = st.gene_index[keep]
+        mem["group_cells"] = {g: mem["group_cells"][g].with_genes(st.gene_index) for g in groups}
+        mem["1d_moments"] = {g: [mem["1d_moments"][g][k][given] for k in range(3)] for g in groups}
+        adata._inplace_subset_var(given)
+    _refresh_design(adata)
+    if not inplace:
+        return adata
+
+
+def _refresh_design(adata):
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    groups = mem["groups"]
+    st.design = engine.GroupDesign(
+        st.device, np.diff(st.group_start), [mem["group_q"][g] for g in groups],
+        np.stack([mem["mv_regressor"][g] for g in groups]), st.n_bins_present, st.bin_inv_sf)
+
+
+# --------------------------------------------------------------------------- ht_1d_moments
+def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=True, num_boot=10000,
+                  verbose=1, num_cpus=1, seed=0, workspace_bytes=6 << 30, replay=None, **kwargs):
+    """Hypothesis test for the mean and the residual variance.  reference: main.py:341-415.
+
+    ``num_cpus`` / ``verbose`` are accepted and ignored (the GPU grid replaces the process pool).
+    Test keywords as in the reference: ``resampling='bootstrap'`` (only mode on the device path),
+    ``approx``, ``resample_rep``.  Build-only: ``seed`` (Philox key), ``workspace_bytes``,
+    ``replay`` (deterministic parity mode: host-supplied unique tables, resample counts and
+    imputation sources for every (gene, group); see engine.ht_1d_replay)."""
+    if not inplace:
+        adata = adata.copy()
+    resampling = kwargs.pop("resampling", "bootstrap")
+    approx = bool(kwargs.pop("approx", False))
+    resample_rep = bool(kwargs.pop("resample_rep", False))
+    if kwargs:
+        raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
+    if resampling != "bootstrap":
+        raise NotImplementedError("only resampling='bootstrap' is implemented on the device path")
+    if resample_rep:
+        raise NotImplementedError("resample_rep=True is not implemented on the device path yet")
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    groups = mem["groups"]
+    R, G = len(groups), adata.shape[1]
+    estimator = _estimator_code(mem["estimator_type"])
+    if st.design is None:
+        _refresh_design(adata)
+    cov = np.ascontiguousarray(covariate.values, dtype=np.float64)
+    tr_all = np.ascontiguousarray(treatment.values, dtype=np.float64)
+    T = tr_all.shape[1]
+    one_sample = bool((tr_all == 1).mean() == 1)                              # hypothesis_test.py:262
+    true_mean = np.stack([mem["1d_moments"][g][0] for g in groups], axis=1)   # (G, R)
+    true_rv = np.stack([mem["1d_moments"][g][2] for g in groups], axis=1)
+
+    genes_per_tile = engine.tile_plan(st.seg, num_boot, workspace_bytes)
+    out = {k: np.full((G, 2, T), np.nan) for k in ("coef", "se", "asl")}
+    stats_acc = {}
+    if replay is not None:
+        dh = {"n_cells": np.diff(st.group_start), "q": [mem["group_q"][g] for g in groups],
+              "mv_fit": np.stack([mem["mv_regressor"][g] for g in groups])}
+        res = engine.ht_1d_replay(st.device, R, replay, dh, true_mean, true_rv, cov, tr_all, num_boot, estimator,
+                                  approx, one_sample, want_coef_rows=not approx, timer=st.timer)
+        if not approx:
+            gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
+        for k in out:
+            out[k][:] = res[k].cpu().numpy()
+        genes_per_tile = G + 1
+        st.last_replay = res
+    for lo in range(0, G if replay is None else 0, genes_per_tile):
+        n = min(genes_per_tile, G - lo)
+        res = engine.ht_1d_tile(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
+                                cov, tr_all, num_boot, estimator, seed, approx, one_sample,
+                                want_coef_rows=not approx, timer=st.timer, stats=stats_acc)
+        if not approx:
+            gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
+        for k in out:
+            out[k][lo:lo + n] = res[k].cpu().numpy()
+    st.last_stats = stats_acc
+
+    # flat gene-major / treatment-minor outputs (main.py:399-404)
+    if treatment_for_gene is None:
+        sel = None
+        flat = {k: out[k].transpose(1, 0, 2).reshape(2, G * T) for k in out}
+    else:
+        cols = {c: i for i, c in enumerate(treatment.columns)}
+        sel = [np.array([cols[c] for c in treatment_for_gene[gname]], dtype=int) for gname in adata.var.index]
+        flat = {k: np.stack([np.concatenate([out[k][i, s, sel[i]] for i in range(G)]) for s in range(2)])
+                for k in out}
+    ht = mem["1d_ht"] = {}
+    if treatment_for_gene is not None:
+        ht["treatment_for_gene"] = treatment_for_gene
+    ht["treatment"], ht["covariate"] = treatment, covariate
+    ht["mean_coef"], ht["mean_se"], ht["mean_asl"] = flat["coef"][0], flat["se"][0], flat["asl"][0]
+    ht["var_coef"], ht["var_se"], ht["var_asl"] = flat["coef"][1], flat["se"][1], flat["asl"][1]
+    if not inplace:
+        return adata
+
+
+# --------------------------------------------------------------------------- 2D
+def compute_2d_moments(adata, gene_pairs, inplace=True):
+    """Covariance and correlation of the given gene pairs in each group.  reference: main.py:293-338."""
+    if not inplace:
+        adata = adata.copy()
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    if "size_factor" not in mem:
+        _bin_size_factor(adata)
+    groups = mem["groups"]
+    names = adata.var.index
+    pos = pd.Series(np.arange(len(names)), index=names)
+    idx1 = pos.loc[[a for a, _ in gene_pairs]].values.astype(int)
+    idx2 = pos.loc[[b for _, b in gene_pairs]].values.astype(int)
+    out = {"gene_pairs": gene_pairs, "gene_idx_1": idx1, "gene_idx_2": idx2}
+    n_cells = np.diff(st.group_start).astype(np.float64)
+    i1_d = to_device(idx1, st.device, np.int32)
+    i2_d = to_device(idx2, st.device, np.int32)
+    prod = st.seg.pair_products(i1_d, i2_d, st.inv_sf_sorted, st.timer).cpu().numpy()      # (n_pairs, R)
+    sums = st.seg.moments(st.inv_sf_sorted, st.timer).cpu().numpy()                         # (5, G, R)
+    same = idx1 == idx2
+    for r, g in enumerate(groups):
+        q = mem["group_q"][g]
+        p = prod[:, r] / n_cells[r]
+        p[same] = p[same] - (1 - q) * sums[3][idx1[same], r] / n_cells[r]                 # estimator.py:229-230
+        cov = p - (sums[2][idx1, r] / n_cells[r]) * (sums[2][idx2, r] / n_cells[r])        # :231
+        var_1 = mem["1d_moments"][g][1][idx1]
+        var_2 = mem["1d_moments"][g][1][idx2]
+        out[g] = {"cov": cov, "corr": _corr_from_cov(cov, var_1, var_2), "var_1": var_1, "var_2": var_2}
+    mem["2d_moments"] = out
+    if not inplace:
+        return adata
+
+
+def _corr_from_cov(cov, var_1, var_2):
+    """reference estimator.py:281-292 (mutates var_1 / var_2 in place, as there)."""
+    corr = np.full(cov.shape, 5.0)
+    var_1[var_1 <= 0] = np.nan
+    var_2[var_2 <= 0] = np.nan
+    denom = np.sqrt(var_1 * var_2)
+    ok = np.isfinite(denom)
+    corr[ok] = cov[ok] / denom[ok]
+    corr[corr > 1] = 1
+    corr[corr < -1] = -1
+    return corr
+
+
+def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=True, num_boot=10000,
+                  verbose=3, num_cpus=1, **kwargs):
+    """reference: main.py:418-520.  Not on the device path yet."""
+    raise NotImplementedError("ht_2d_moments is not implemented on the device path yet")

@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden outputs
+of the unmodified reference.  Run with ``pytest -m gpu`` on a B200.
+
+Tolerances (BASELINE.json north_star):
+  * point estimates: 1e-5 relative vs the reference on float32 counts (the reference itself is
+    float32-accurate there); we additionally hold 1e-9 vs the reference on float64 counts;
+  * deterministic replay of host-supplied resample counts: 1e-6 (we hold 1e-9);
+  * RNG-driven statistics: distributional agreement (KS, rank concordance).
+"""
+import numpy as np
+import pytest
+import scipy.stats as stats
+import torch
+
+from helpers import assert_close, golden_adata, load
+
+pytestmark = pytest.mark.gpu
+
+import memento_b200 as memento            # noqa: E402
+from memento_b200 import engine, synth   # noqa: E402
+from oracle import moments as o_moments  # noqa: E402
+from oracle import pipeline as o_pipe    # noqa: E402
+from oracle import resample as o_resample  # noqa: E402
+from oracle import testing as o_testing  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def st():
+    return load("stages.npz")
+
+
+@pytest.fixture(scope="module")
+def gpu_prepared(st):
+    ad = golden_adata(st)
+    memento.setup_memento(ad, "q")
+    memento.create_groups(ad, ["stim", "cell"])
+    memento.compute_1d_moments(ad, min_perc_group=0.7)
+    return ad
+
+
+@pytest.fixture(scope="module")
+def oracle_prepared(st):
+    ad = golden_adata(st)
+    o_pipe.setup_memento(ad, "q")
+    o_pipe.create_groups(ad, ["stim", "cell"])
+    o_pipe.compute_1d_moments(ad, min_perc_group=0.7)
+    return ad
+
+
+# ----------------------------------------------------------------------------- point estimates
+def test_setup_memento_vs_reference_f64(st):
+    ad = golden_adata(st)
+    memento.setup_memento(ad, "q")
+    mem = ad.uns["memento"]
+    assert_close(ad.obs["memento_size_factor"].values, st["size_factor"], 1e-10)
+    assert mem["least_variable_genes"] == st["least_variable_genes"].tolist()
+    assert_close(mem["all_1d_moments"][0], st["all_mean"], 1e-10)
+    assert_close(mem["all_1d_moments"][1], st["all_var"], 1e-9, atol=1e-15)
+
+
+def test_compute_1d_moments_vs_reference_f64(st, gpu_prepared):
+    mem = gpu_prepared.uns["memento"]
+    assert mem["groups"] == st["groups"].tolist()
+    assert_close([mem["group_q"][g] for g in mem["groups"]], st["group_q"], 1e-12)
+    assert [mem["group_cells"][g].shape[0] for g in mem["groups"]] == st["group_ncells"].tolist()
+    assert_close(mem["all_approx_size_factor"], st["approx_sf"], 1e-10)
+    assert np.array_equal(mem["overall_gene_filter"], st["overall_gene_filter"])
+    assert mem["gene_list"] == st["gene_list"].tolist()
+    assert gpu_prepared.var.index.tolist() == st["gene_list"].tolist()
+    assert_close(mem["mv_regressor"]["all"], st["mv_regressor"], 1e-8)
+    for gi, g in enumerate(mem["groups"]):
+        assert_close(mem["1d_moments"][g][0], st["m1d_mean_%d" % gi], 1e-10)
+        assert_close(mem["1d_moments"][g][1], st["m1d_var_%d" % gi], 1e-9, atol=1e-15)
+        assert_close(mem["1d_moments"][g][2], st["m1d_rv_%d" % gi], 1e-7)
+        assert np.array_equal(mem["gene_filter"][g], st["gene_filter_%d" % gi])
+        assert np.array_equal(mem["gene_rv_filter"][g], st["gene_rv_filter_%d" % gi])
+        assert mem["group_cells"][g].shape == (st["group_ncells"][gi], len(st["gene_list"]))
+
+
+def test_point_estimates_vs_reference_f32(st):
+    """The reference run on float32 counts (h5ad convention): north-star tolerance 1e-5 relative;
+    the variance is a difference of float32-accurate terms there, hence the absolute slack."""
+    f32 = load("stages_f32.npz")
+    ad = golden_adata(st)
+    ad.X = ad.X.astype(np.float32)
+    memento.setup_memento(ad, "q")
+    memento.create_groups(ad, ["stim", "cell"])
+    memento.compute_1d_moments(ad, min_perc_group=0.7)
+    mem = ad.uns["memento"]
+    assert_close(ad.obs["memento_size_factor"].values, f32["size_factor"], 1e-5)
+    assert_close(mem["all_1d_moments"][0], f32["all_mean"], 1e-5)
+    assert np.array_equal(mem["overall_gene_filter"], f32["overall_gene_filter"])
+    for gi, g in enumerate(mem["groups"]):
+        m = f32["m1d_mean_%d" % gi]
+        assert_close(mem["1d_moments"][g][0], m, 1e-5)
+        assert_close(mem["1d_moments"][g][1], f32["m1d_var_%d" % gi], 1e-5, atol=float(1e-5 * (m ** 2 + m).max()))
+
+
+def test_2d_moments_vs_reference(st, gpu_prepared):
+    ad = gpu_prepared.copy()
+    names = ad.var.index.tolist()
+    pairs = [(names[i], names[j]) for i, j in zip(st["pairs_idx1"], st["pairs_idx2"])]
+    memento.compute_2d_moments(ad, pairs)
+    mem = ad.uns["memento"]
+    assert np.array_equal(mem["2d_moments"]["gene_idx_1"], st["pairs_idx1"])
+    for gi, g in enumerate(mem["groups"]):
+        d = mem["2d_moments"][g]
+        assert_close(d["cov"], st["m2d_cov_%d" % gi], 1e-9, atol=1e-15)
+        assert_close(d["corr"], st["m2d_corr_%d" % gi], 1e-8)
+        assert_close(d["var_1"], st["m2d_var1_%d" % gi], 1e-9, atol=1e-15)
+
+
+# ----------------------------------------------------------------------------- compression
+def _canonical_oracle_table(col, sf):
+    inv_sf, _, vals, mult = o_resample.unique_table(col, sf)
+    inv_sf, vals = inv_sf.reshape(-1), vals[:, 0]
+    nz = vals > 0
+    order = np.lexsort((inv_sf[nz], vals[nz]))
+    return vals[nz][order], inv_sf[nz][order], mult[nz][order], int(mult[~nz].sum()), vals.shape[0]
+
+
+def test_unique_tables_vs_oracle(gpu_prepared, oracle_prepared):
+    dstate = gpu_prepared.uns["memento"]["_b200"]
+    omem = oracle_prepared.uns["memento"]
+    seg = dstate.seg
+    G, R = seg.G, seg.R
+    tab = engine.unique_tables(seg, dstate.design, dstate.cell_bin, 0, G, 0, want_raw=True)
+    torch.cuda.synchronize()
+    seg_ptr = seg.seg_ptr.cpu().numpy()
+    key = tab["raw_key"].cpu().numpy().view(np.uint32)
+    cnt = tab["raw_cnt"].cpu().numpy()
+    seg_U = tab["seg_U"].cpu().numpy()
+    bin_inv = dstate.bin_inv_sf
+    np.random.seed(0)
+    for gene in range(G):
+        for r, g in enumerate(omem["groups"]):
+            s = gene * R + r
+            col = omem["group_cells"][g][:, gene]
+            x_o, w_o, n_o, n_zero, U_total = _canonical_oracle_table(col, omem["approx_size_factor"][g])
+            U = seg_U[s]
+            if U_total <= 1:
+                assert U == -1, (gene, r)
+                continue
+            assert U == x_o.shape[0], (gene, r, U, x_o.shape[0])
+            k = key[seg_ptr[s]:seg_ptr[s] + U]
+            c = cnt[seg_ptr[s]:seg_ptr[s] + U]
+            x_g = (k >> 8).astype(np.float64)
+            w_g = bin_inv[k & 0xFF]
+            order = np.lexsort((w_g, x_g))
+            assert np.array_equal(x_g[order], x_o), (gene, r)
+            assert_close(w_g[order], w_o, 1e-12)
+            assert np.array_equal(c[order], n_o), (gene, r)
+            assert c.sum() + n_zero == col.shape[0]
+
+
+# ----------------------------------------------------------------------------- bootstrap, replay mode
+def test_bootstrap_replay_vs_reference(st, gpu_prepared):
+    """Host-supplied resample counts (the reference's own PCG64(5) draws) -> bootstrap mean/variance
+    must match the reference's to 1e-6 (north star); we assert 1e-9."""
+    mem = gpu_prepared.uns["memento"]
+    dev = mem["_b200"].device
+    B = 64
+    xs, ws, Ws, ptr, ncell, qs, fits = [], [], [], [0], [], [], []
+    for k, (gene, gi) in enumerate(st["table_picks"]):
+        g = mem["groups"][gi]
+        xs.append(st["tab%d_expr" % k][:, 0])
+        ws.append(st["tab%d_inv_sf" % k].reshape(-1))
+        Ws.append(np.ascontiguousarray(st["tab%d_W" % k].T).reshape(-1))   # (B, U) row-major
+        ptr.append(ptr[-1] + xs[-1].shape[0])
+        ncell.append(st["group_ncells"][gi])
+        qs.append(mem["group_q"][g])
+        fits.append(mem["mv_regressor"][g])
+    n_tab = len(xs)
+    d = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=dev)  # noqa: E731
+    out = [torch.empty(n_tab * B, dtype=torch.float64, device=dev) for _ in range(3)]
+    from memento_b200 import _lib
+    _lib.call("mm_bootstrap_1d_replay", dev, d(np.concatenate(xs), np.float64), d(np.concatenate(ws), np.float64),
+              d(np.concatenate(Ws), np.int64), d(ptr, np.int64), d(ncell, np.int32), d(qs, np.float64),
+              d(np.stack(fits), np.float64), n_tab, B, 0, out[0], out[1], out[2])
+    torch.cuda.synchronize()
+    mean = out[0].cpu().numpy().reshape(n_tab, B)
+    var = out[1].cpu().numpy().reshape(n_tab, B)
+    rv = out[2].cpu().numpy().reshape(n_tab, B)
+    for k in range(n_tab):
+        assert_close(mean[k], st["tab%d_boot_mean" % k], 1e-9, what="mean %d" % k)
+        assert_close(var[k], st["tab%d_boot_var" % k], 1e-9, atol=1e-14, what="var %d" % k)
+        want_rv = o_moments.residual_variance(st["tab%d_boot_mean" % k], st["tab%d_boot_var" % k], fits[k])
+        assert_close(rv[k], want_rv, 1e-7, what="rv %d" % k)
+
+
+def _replay_spec(oracle_ad, cov, tr, num_boot, seed):
+    """Run the oracle's per-gene driver in the reference's order with a recorder, collecting for
+    every (gene, group) the unique table, the PCG64(5) resample counts and the imputation sources."""
+    omem = oracle_ad.uns["memento"]
+    groups = omem["groups"]
+    R, G = len(groups), oracle_ad.shape[1]
+    n_cells = np.array([omem["group_cells"][g].shape[0] for g in groups])
+    x, w, W, ptr = [], [], [], [0]
+    src_m = np.full((G * R, num_boot), -1, dtype=np.int32)
+    src_v = np.full((G * R, num_boot), -1, dtype=np.int32)
+    np.random.seed(seed)
+    for gene in range(G):
+        rec = []
+        o_testing.ht_1d_gene(
+            true_mean=[omem["1d_moments"][g][0][gene] for g in groups],
+            true_res_var=[omem["1d_moments"][g][2][gene] for g in groups],
+            cells=[omem["group_cells"][g][:, gene] for g in groups],
+            approx_sf=[omem["approx_size_factor"][g] for g in groups],
+            covariate=cov.values, treatment=tr.values, n_cells=n_cells, num_boot=num_boot,
+            mv_fit=[omem["mv_regressor"][g] for g in groups], q=[omem["group_q"][g] for g in groups],
+            weighted_estimator=o_moments.hyper_1d_weighted, return_boot=True, recorder=rec)
+        by_group = {r["group"]: r for r in rec}
+        for r in range(R):
+            s = gene * R + r
+            if r in by_group:
+                t = by_group[r]
+                x.append(t["values"]); w.append(t["inv_sf"])
+                W.append(o_resample.draw_counts(t["n_cells"], t["mult"], num_boot).T.reshape(-1))
+                ptr.append(ptr[-1] + t["values"].shape[0])
+                if t["src_mean"] is not None:
+                    src_m[s] = t["src_mean"]
+                if t["src_rv"] is not None:
+                    src_v[s] = t["src_rv"]
+            else:
+                ptr.append(ptr[-1])
+    cat = lambda L, dt: np.concatenate(L).astype(dt) if L else np.zeros(0, dt)  # noqa: E731
+    # sources of -1 are never read by the kernel (entry valid); clamp for safety
+    return {"tab_ptr": np.array(ptr), "x": cat(x, np.float64), "inv_sf": cat(w, np.float64),
+            "W": cat(W, np.int64), "src_mean": np.maximum(src_m, 0), "src_rv": np.maximum(src_v, 0)}
+
+
+@pytest.mark.parametrize("variant,kw", [("approx", dict(approx=True)), ("default", dict())])
+def test_ht_1d_replay_vs_reference(gpu_prepared, oracle_prepared, variant, kw):
+    """End to end in replay mode against the golden ``ht_1d_moments`` output of the reference run
+    (np.random.seed(2024), num_cpus=1): coefficients / SE to 1e-6 (we assert 1e-8), ASL exactly for
+    the normal-approximation and counting branches."""
+    ht = load("ht1d.npz")
+    B = int(ht["num_boot"])
+    ad = gpu_prepared.copy()
+    cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+    spec = _replay_spec(oracle_prepared.copy(), cov, tr, B, 2024)
+    memento.ht_1d_moments(ad, cov, tr, num_boot=B, resampling="bootstrap", replay=spec, **kw)
+    res = ad.uns["memento"]["1d_ht"]
+    for key in ["mean_coef", "mean_se", "var_coef", "var_se"]:
+        assert_close(res[key], ht["%s_%s" % (variant, key)], 1e-8, atol=1e-12, what=(variant, key))
+    if variant == "approx":
+        for key in ["mean_asl", "var_asl"]:
+            assert_close(res[key], ht["approx_" + key], 1e-7, atol=1e-300, what=key)
+    else:
+        # counting branch is exact; the GEV-tail branch (<= 10 extreme replicates) is compared
+        # in test_gev_tail_vs_reference
+        want_m, want_v = ht["default_mean_asl"], ht["default_var_asl"]
+        ext = ad.uns["memento"]["_b200"].last_replay["extreme"].cpu().numpy()    # (G, 2, T)
+        big_m, big_v = ext[:, 0, 0] > 10, ext[:, 1, 0] > 10
+        assert_close(res["mean_asl"][big_m], want_m[big_m], 1e-12)
+        assert_close(res["var_asl"][big_v], want_v[big_v], 1e-12)
+
+
+def test_ht_1d_replay_one_sample(gpu_prepared, oracle_prepared):
+    import pandas as pd
+    ht = load("ht1d.npz")
+    B = int(ht["num_boot"])
+    ad = gpu_prepared.copy()
+    groups = ad.uns["memento"]["groups"]
+    cov, _ = synth.design_from_groups(groups, ["stim", "cell"])
+    ones = pd.DataFrame({"one": np.ones(len(groups))}, index=groups)
+    spec = _replay_spec(oracle_prepared.copy(), cov, ones, B, 77)
+    memento.ht_1d_moments(ad, cov, ones, num_boot=B, resampling="bootstrap", approx=True, replay=spec)
+    res = ad.uns["memento"]["1d_ht"]
+    for key in ["mean_coef", "mean_se", "mean_asl", "var_coef", "var_se", "var_asl"]:
+        assert_close(res[key], ht["onesample_%s" % key], 1e-8, atol=1e-12, what=key)
+
+
+# ----------------------------------------------------------------------------- bootstrap, RNG mode
+def test_rng_bootstrap_distribution_vs_oracle(gpu_prepared, oracle_prepared):
+    """Philox multinomial (conditional binomials: inversion + BTRS) against numpy's multinomial on
+    the same unique tables: two-sample KS on the bootstrapped mean and variance of several
+    (gene, group) slices, plus agreement of their first two moments within Monte Carlo error."""
+    mem = gpu_prepared.uns["memento"]
+    dstate = mem["_b200"]
+    omem = oracle_prepared.uns["memento"]
+    seg = dstate.seg
+    G, R = seg.G, seg.R
+    B = 4000
+    tab = engine.unique_tables(seg, dstate.design, dstate.cell_bin, 0, G, 0)
+    n_seg = G * R
+    raw_mean = torch.empty(n_seg * B, dtype=torch.float64, device=seg.device)
+    raw_rv = torch.empty(n_seg * B, dtype=torch.float64, device=seg.device)
+    from memento_b200 import _lib
+    _lib.call("mm_bootstrap_1d", seg.device, tab["entries"], seg.seg_ptr, 0, n_seg, R, tab["seg_U"], None,
+              dstate.design.n_cells, dstate.design.mv_fit, 0, B, 1234, raw_mean, raw_rv)
+    torch.cuda.synchronize()
+    gm = raw_mean.cpu().numpy().reshape(n_seg, B)
+    grv = raw_rv.cpu().numpy().reshape(n_seg, B)
+    sums = np.stack([mem["1d_moments"][g][0] for g in mem["groups"]], axis=1)
+    order = np.argsort(-sums.sum(axis=1))
+    picks = list(order[:6]) + list(order[len(order) // 2: len(order) // 2 + 6]) + list(order[-6:])
+    pvals = []
+    np.random.seed(5)
+    for gene in picks:
+        for r, g in enumerate(omem["groups"]):
+            col = omem["group_cells"][g][:, gene]
+            om, ov = o_resample.bootstrap_1d(col, omem["approx_size_factor"][g], omem["group_q"][g],
+                                             o_moments.hyper_1d_weighted, B)
+            if np.isnan(om).all():
+                continue
+            orv = o_moments.residual_variance(om, ov, omem["mv_regressor"][g])
+            s = gene * R + r
+            # first two moments of the bootstrapped mean: |diff| < 5 standard errors
+            se = om.std() / np.sqrt(B)
+            assert abs(gm[s].mean() - om.mean()) < 6 * se + 1e-12, (gene, r)
+            assert abs(gm[s].std() / om.std() - 1) < 0.08, (gene, r)
+            pvals.append(stats.ks_2samp(gm[s], om).pvalue)
+            a, b = grv[s][np.isfinite(grv[s])], orv[np.isfinite(orv)]
+            assert abs(a.size - b.size) < 6 * np.sqrt(B * 0.25) + 1
+            if a.size > 100 and b.size > 100:
+                pvals.append(stats.ks_2samp(a, b).pvalue)
+    pvals = np.array(pvals)
+    assert pvals.size > 40
+    assert pvals.min() > 1e-4, pvals.min()                   # no slice rejects grossly
+    assert stats.kstest(pvals, "uniform").pvalue > 1e-3      # and the KS p-values look uniform
+
+
+def test_rng_ht_1d_vs_oracle_pvalues(gpu_prepared, oracle_prepared):
+    """RNG-driven p-values: rank concordance with the oracle across genes and KS agreement of the
+    p-value distribution on the null genes (north star: 'within Monte Carlo error')."""
+    ad = gpu_prepared.copy()
+    oad = oracle_prepared.copy()
+    cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+    B = 2000
+    memento.ht_1d_moments(ad, cov, tr, num_boot=B, resampling="bootstrap", approx=True, seed=11)
+    np.random.seed(1)
+    o_pipe.ht_1d_moments(oad, cov, tr, num_boot=B, num_cpus=1, resampling="bootstrap", approx=True)
+    g, o = ad.uns["memento"]["1d_ht"], oad.uns["memento"]["1d_ht"]
+    # coefficients are RNG-free
+    assert_close(g["mean_coef"], o["mean_coef"], 1e-8, atol=1e-12)
+    assert_close(g["var_coef"], o["var_coef"], 1e-7, atol=1e-10)
+    for key in ("mean", "var"):
+        se_g, se_o = g[key + "_se"], o[key + "_se"]
+        ok = np.isfinite(se_g) & np.isfinite(se_o)
+        assert np.array_equal(np.isfinite(se_g), np.isfinite(se_o))
+        assert np.median(np.abs(se_g[ok] / se_o[ok] - 1)) < 0.04
+        pg, po = g[key + "_asl"][ok], o[key + "_asl"][ok]
+        rho = stats.spearmanr(pg, po).statistic
+        assert rho > 0.97, (key, rho)
+        lg, lo = -np.log10(np.maximum(pg, 1e-300)), -np.log10(np.maximum(po, 1e-300))
+        assert np.median(np.abs(lg - lo)) < 0.05, key
+        assert stats.ks_2samp(pg, po).pvalue > 0.01, key
