@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the memento hot path: genes tested/sec for ht_1d_moments (num_boot=10k).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "IFN-beta PBMC-shaped"): 25 000 cells x 10 000 genes synthetic
+negative-binomial counts, q = 0.07, stim vs ctrl x 8 cell types = 16 groups, covariate = cell-type
+dummies, treatment = stim, num_boot = 10 000, resampling='bootstrap'.  One step = one
+``ht_1d_moments`` call over all genes that pass the filters.
+
+  value : genes/s with the group-sorted matrix already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same call through the public Python API with HOST buffers: the matrix and per-cell
+          vectors are uploaded from pinned host memory inside the timed region and the result
+          arrays are read back
+  roofline     : the per-group moment kernel (mm_seg_moments, HBM-bound) timed live on the same matrix
+  cpu_baseline : the oracle port of the reference's CPU path on a bounded gene sample, all host cores
+
+With N > 1 (torchrun) every rank runs its own gene shard of the same shape (weak scaling, genes are
+independent units, no data-path collective); rank 0 prints one JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "scrna-parameter-estimation_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "genes tested/sec (ht_1d, num_boot=10k)"
+UNIT = "genes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=25000)
+    ap.add_argument("--genes", type=int, default=10000)
+    ap.add_argument("--types", type=int, default=8)
+    ap.add_argument("--num-boot", type=int, default=10000)
+    ap.add_argument("--approx", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="genes in the CPU sample (0 = 2 per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(a, n_groups, n_tested, extra=None):
+    c = {"workload": "configs[1] IFN-beta PBMC-shaped 1D DE: %d cells x %d genes, %d groups (stim x %d cell "
+                     "types), num_boot=%d, resampling=bootstrap, approx=%s" %
+                     (a.cells, a.genes, n_groups, a.types, a.num_boot, bool(a.approx)),
+         "cells": a.cells, "genes": a.genes, "genes_tested": n_tested, "groups": n_groups,
+         "num_boot": a.num_boot, "approx": bool(a.approx), "q": 0.07}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def make_data(a, seed, device):
+    from memento_b200 import synth
+    return synth.make_counts_fast(a.cells, a.genes, n_conditions=2, n_types=a.types, q=0.07, seed=seed,
+                                  device=device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    """The reference's CPU path (oracle port, numpy/scipy/sklearn as the reference calls them; the
+    Python reference itself cannot travel to the GPU box) on a bounded gene sample, all cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import pipeline as o_pipe
+    from memento_b200 import synth
+    dev = "cuda" if torch.cuda.is_available() else None
+    ad = make_data(a, 7, dev)
+    o_pipe.setup_memento(ad, "q")
+    o_pipe.create_groups(ad, ["stim", "cell"])
+    o_pipe.compute_1d_moments(ad, min_perc_group=0.7)
+    groups = ad.uns["memento"]["groups"]
+    cov, tr = synth.design_from_groups(groups, ["stim", "cell"])
+    cores = os.cpu_count()
+    n_sample = a.cpu_sample or max(8, 2 * cores)
+    G = ad.shape[1]
+    rng = np.random.default_rng(0)
+    kw = dict(resampling="bootstrap", approx=bool(a.approx))
+    times = []
+    for it in range(a.warmup + a.steps):
+        sub = np.sort(rng.choice(G, size=min(n_sample, G), replace=False))
+        t0 = time.perf_counter()
+        o_pipe.ht_1d_moments(ad, cov, tr, num_boot=a.num_boot, num_cpus=cores, gene_subset=sub, **kw)
+        dt = time.perf_counter() - t0
+        if it >= a.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = min(n_sample, G) / (ms / 1e3)
+    sample = "%d random genes of %d per step, all %d groups, num_boot=%d" % (min(n_sample, G), G, len(groups), a.num_boot)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_dict(a, len(groups), G),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def cpu_baseline(a, ad_host):
+    """Oracle port on the host cores, bounded sample (rank 0, N == 1 only)."""
+    from oracle import pipeline as o_pipe
+    from memento_b200 import synth
+    t0 = time.perf_counter()
+    oad = ad_host
+    o_pipe.setup_memento(oad, "q")
+    o_pipe.create_groups(oad, ["stim", "cell"])
+    o_pipe.compute_1d_moments(oad, min_perc_group=0.7)
+    t_moments = time.perf_counter() - t0
+    groups = oad.uns["memento"]["groups"]
+    cov, tr = synth.design_from_groups(groups, ["stim", "cell"])
+    cores = os.cpu_count()
+    n_sample = a.cpu_sample or max(8, 2 * cores)
+    G = oad.shape[1]
+    sub = np.sort(np.random.default_rng(0).choice(G, size=min(n_sample, G), replace=False))
+    t0 = time.perf_counter()
+    o_pipe.ht_1d_moments(oad, cov, tr, num_boot=a.num_boot, num_cpus=cores, gene_subset=sub,
+                         resampling="bootstrap", approx=bool(a.approx))
+    dt = time.perf_counter() - t0
+    return {"value": len(sub) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d random genes of %d, all %d groups, num_boot=%d (%.1f s); moment stage "
+                      "setup+groups+1d_moments on the full matrix: %.1f s" %
+                      (len(sub), G, len(groups), a.num_boot, dt, t_moments)}
+
+
+# ----------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import memento_b200 as memento
+    from memento_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ad = make_data(a, 7 + rank, dev)                       # rank r owns its own gene shard (weak scaling)
+    ad_host = ad.copy() if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
+    memento.setup_memento(ad, "q", profile=True)
+    memento.create_groups(ad, ["stim", "cell"])
+    memento.compute_1d_moments(ad, min_perc_group=0.7)
+    mem = ad.uns["memento"]
+    st = mem["_b200"]
+    groups = mem["groups"]
+    cov, tr = synth.design_from_groups(groups, ["stim", "cell"])
+    G = ad.shape[1]
+    kw = dict(num_boot=a.num_boot, resampling="bootstrap", approx=bool(a.approx))
+
+    # ---- resident-input steps
+    for _ in range(a.warmup):
+        memento.ht_1d_moments(ad, cov, tr, seed=1, **kw)
+    st.timer.collect()
+    st.timer.ms.clear(); st.timer.calls.clear()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = 0
+    for i in range(a.steps):
+        memento.ht_1d_moments(ad, cov, tr, seed=100 + i, **kw)
+        launches += st.last_stats.get("launches", 0)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    stage_ms = st.timer.collect()
+    last = dict(st.last_stats)
+    t = torch.tensor([ms_total, float(G)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, genes_total = float(tmax[0]), float(tsum[1])
+    else:
+        genes_total = float(G)
+    ms_step = ms_total / a.steps
+    value = genes_total / (ms_step / 1e3)
+
+    # ---- roofline of the HBM-bound moment kernel, timed live on the same matrix (inputs >> L2)
+    peak, peak_src = measured_peak()
+    seg = st.seg
+    for _ in range(3):
+        seg.moments(st.inv_sf_sorted)
+    torch.cuda.synchronize(dev)
+    reps = 10
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(reps):
+        seg.moments(st.inv_sf_sorted)
+    m1.record()
+    torch.cuda.synchronize(dev)
+    mom_ms = m0.elapsed_time(m1) / reps
+    mom_bytes = seg.moments_bytes()
+    mom_gbs = mom_bytes / (mom_ms * 1e-3) / 1e9
+    uniq_ms = stage_ms.get("seg_unique", 0.0) / a.steps
+    uniq_gbs = last.get("unique_bytes", 0) / (uniq_ms * 1e-3) / 1e9 if uniq_ms > 0 else None
+    boot_ms = stage_ms.get("bootstrap_1d", 0.0) / a.steps
+    roofline = {"kernel": "mm_seg_moments (per-(gene,group) sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2)",
+                "bound": "hbm", "achieved": mom_gbs, "peak": peak, "unit": "GB/s", "frac": mom_gbs / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": mom_bytes,
+                "kernel_ms": mom_ms, "nnz": seg.nnz}
+    stages = {k: v / a.steps for k, v in stage_ms.items()}
+    extra = {
+        "stage_ms_per_step": stages,
+        "seg_unique": {"bound": "hbm", "achieved": uniq_gbs, "unit": "GB/s",
+                       "frac": (uniq_gbs / peak) if uniq_gbs else None, "algorithmic_bytes": last.get("unique_bytes")},
+        "bootstrap_1d": {"bound": "issue (compute)", "category_draws_per_step": last.get("category_draws"),
+                         "draws_per_s": (last.get("category_draws", 0) / (boot_ms * 1e-3)) if boot_ms > 0 else None,
+                         "share_of_step": boot_ms / ms_step if ms_step > 0 else None},
+    }
+
+    # ---- end to end through the public API with host buffers
+    st.offload()
+    d2h = 6 * G * tr.shape[1] * 8
+    for _ in range(max(1, min(a.warmup, 2))):
+        memento.ht_1d_moments(ad, cov, tr, seed=1, **kw)
+        st.offload()
+    barrier()
+    h2d = 0
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        memento.ht_1d_moments(ad, cov, tr, seed=200 + i, **kw)
+        torch.cuda.synchronize(dev)
+        h2d = st.h2d_bytes
+        st.offload()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / a.steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": genes_total / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te[0]) * 1e3}
+
+    cpu = None
+    if ad_host is not None:
+        cpu = cpu_baseline(a, ad_host)
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": config_dict(a, len(groups), G, {
+                   "parallelism": "gene-sharded x%d (independent shards, no data-path collective)" % world,
+                   "l2": "inputs larger than L2: group-sorted matrix %.0f MB + %.0f MB of bootstrap rows per tile"
+                         % (seg.nnz * 8 / 1e6 if seg is not None else 0, 0)}),
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+               "clocks": clk}
+        out.update(extra)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -124,6 +124,17 @@ int mm_regress_asl(int device, void* stream, const double* boot0, const double* 
                    double* coef_ws, double* out_coef, double* out_se, double* out_asl,
                    int32_t* out_extreme, int32_t* out_nnull);
 
+/* GEV tail refinement of the ASL for the tests listed in `flagged` (row ids into coef_rows / asl):
+ * sorts the null (coef_rows[row][1..] - coef_rows[row][0], finite entries), fits a generalised extreme
+ * value law to each tail for tail sizes 300, 270, ..., 60 (Nelder-Mead MLE as scipy.stats.genextreme.fit
+ * does it) until a two-sided KS check at 0.05 passes, and replaces asl[row] by
+ * N_exec/n * (cdf(-|stat|) + sf(|stat|)); status[i] = 1 if replaced, 0 if the empirical bound was
+ * kept (no tail passed, a fit failed, or fewer than 300 usable replicates).  num_boot <= 16384.
+ * Replaces: memento/hypothesis_test.py:94-141 (_compute_asl, GEV branch; scipy genextreme.fit +
+ * kstest per tail, ~110 ms per fit on a CPU core). */
+int mm_gev_tail_asl(int device, void* stream, const double* coef_rows, const int32_t* flagged,
+                    int32_t n_flag, int32_t num_boot, double* asl, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

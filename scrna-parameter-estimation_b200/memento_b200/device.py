@@ -120,6 +120,22 @@ class SegMatrix:
     def n_seg(self):
         return self.G * self.R
 
+    # ------------------------------------------------------------------ host staging (end-to-end path)
+    def to_host_pinned(self):
+        """Pinned host copies of the three arrays (what an end-to-end call uploads)."""
+        return {"vals": self.vals.cpu().pin_memory(), "rows": self.rows.cpu().pin_memory(),
+                "seg_ptr": self.seg_ptr.cpu().pin_memory(), "G": self.G, "R": self.R, "n_cells": self.n_cells}
+
+    @staticmethod
+    def from_host_pinned(h, device):
+        seg = SegMatrix(h["vals"].to(device, non_blocking=True), h["rows"].to(device, non_blocking=True),
+                        h["seg_ptr"].to(device, non_blocking=True), h["G"], h["R"], h["n_cells"])
+        return seg
+
+    @staticmethod
+    def host_bytes(h):
+        return h["vals"].numel() * 4 + h["rows"].numel() * 4 + h["seg_ptr"].numel() * 8
+
     # ------------------------------------------------------------------ construction (ingest plumbing)
     @staticmethod
     def from_csr(csr, group_of_cell=None, n_groups=1, rank_of_cell=None):

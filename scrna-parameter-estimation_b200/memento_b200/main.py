@@ -44,11 +44,30 @@ class DeviceState:
         self.n_bins_present = None
         self.cell_bin_host = None
         self.last_stats = {}
+        self.host = None         # pinned host staging copies (end-to-end mode)
 
     def __deepcopy__(self, memo):
         new = DeviceState(self.device)
         new.__dict__.update(self.__dict__)
         return new
+
+    # -- end-to-end mode: keep the group-sorted matrix and the per-cell vectors in pinned HOST memory
+    #    and upload them inside every ht_* call (what a caller holding only host buffers pays).
+    def offload(self):
+        if self.host is None:   # the matrix is immutable: stage it once
+            self.host = {"seg": self.seg.to_host_pinned(), "cell_bin": self.cell_bin.cpu().pin_memory(),
+                         "inv_sf": self.inv_sf_sorted.cpu().pin_memory()}
+        self.seg = self.cell_bin = self.inv_sf_sorted = self.design = self.seg_all = None
+        self.h2d_bytes = 0
+        torch.cuda.empty_cache()
+
+    def ensure_resident(self):
+        if self.seg is None:
+            h = self.host
+            self.seg = SegMatrix.from_host_pinned(h["seg"], self.device)
+            self.cell_bin = h["cell_bin"].to(self.device, non_blocking=True)
+            self.inv_sf_sorted = h["inv_sf"].to(self.device, non_blocking=True)
+            self.h2d_bytes += SegMatrix.host_bytes(h["seg"]) + h["cell_bin"].numel() + h["inv_sf"].numel() * 8
 
 
 class LazyGroupCells:
@@ -342,6 +361,7 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         raise NotImplementedError("resample_rep=True is not implemented on the device path yet")
     mem = adata.uns["memento"]
     st = _state(adata)
+    st.ensure_resident()
     groups = mem["groups"]
     R, G = len(groups), adata.shape[1]
     estimator = _estimator_code(mem["estimator_type"])
