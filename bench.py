@@ -64,10 +64,10 @@ def config_dict(a, n_groups, n_tested, extra=None):
     return c
 
 
-def make_data(a, seed, device):
+def make_data(a, shard, device):
     from memento_b200 import synth
-    return synth.make_counts_fast(a.cells, a.genes, n_conditions=2, n_types=a.types, q=0.07, seed=seed,
-                                  device=device)
+    return synth.make_counts_fast(a.cells, a.genes, n_conditions=2, n_types=a.types, q=0.07, seed=7,
+                                  device=device, shard=shard)
 
 
 class ClockSampler:
@@ -128,7 +128,7 @@ def run_reference(a):
     from oracle import pipeline as o_pipe
     from memento_b200 import synth
     dev = "cuda" if torch.cuda.is_available() else None
-    ad = make_data(a, 7, dev)
+    ad = make_data(a, 0, dev)
     o_pipe.setup_memento(ad, "q")
     o_pipe.create_groups(ad, ["stim", "cell"])
     o_pipe.compute_1d_moments(ad, min_perc_group=0.7)
@@ -205,9 +205,15 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    ad = make_data(a, 7 + rank, dev)                       # rank r owns its own gene shard (weak scaling)
+    # rank r owns gene block r of the same cells (weak scaling: 10k genes per GPU); the UMI totals are
+    # all-reduced and the moment vectors all-gathered inside setup_memento / compute_1d_moments
+    ad = make_data(a, rank, dev)
     ad_host = ad.copy() if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
-    memento.setup_memento(ad, "q", profile=True)
+    ctx = None
+    if world > 1:
+        from memento_b200.dist import DistContext
+        ctx = DistContext(device=dev)
+    memento.setup_memento(ad, "q", profile=True, dist=ctx, gene_offset=rank * a.genes)
     memento.create_groups(ad, ["stim", "cell"])
     memento.compute_1d_moments(ad, min_perc_group=0.7)
     mem = ad.uns["memento"]
@@ -285,16 +291,17 @@ def run_ours(a):
     for _ in range(max(1, min(a.warmup, 2))):
         memento.ht_1d_moments(ad, cov, tr, seed=1, **kw)
         st.offload()
-    barrier()
     h2d = 0
-    t0 = time.perf_counter()
+    e2e_total = 0.0
     for i in range(a.steps):
-        memento.ht_1d_moments(ad, cov, tr, seed=200 + i, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        memento.ht_1d_moments(ad, cov, tr, seed=200 + i, **kw)      # uploads, computes, reads results back
         torch.cuda.synchronize(dev)
+        e2e_total += time.perf_counter() - t0
         h2d = st.h2d_bytes
-        st.offload()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / a.steps
+        st.offload()                                                # drop the device copies (untimed)
+    e2e_s = e2e_total / a.steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -309,7 +316,8 @@ def run_ours(a):
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
                "config": config_dict(a, len(groups), G, {
-                   "parallelism": "gene-sharded x%d (independent shards, no data-path collective)" % world,
+                   "parallelism": "gene-sharded x%d (10k-gene block of the same cells per GPU; all-reduce of UMI "
+                                  "totals + all-gather of moment vectors in setup only, none in the timed step)" % world,
                    "l2": "inputs larger than L2: group-sorted matrix %.0f MB + %.0f MB of bootstrap rows per tile"
                          % (seg.nnz * 8 / 1e6 if seg is not None else 0, 0)}),
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

@@ -73,14 +73,16 @@ int mm_seg_unique(int device, void* stream, const float* vals, const int32_t* ro
  * (Philox4x32-10, counter = (b, segment), key = seed), accumulate the moments and write
  *   out_mean[s*num_boot + b] = bootstrapped mean,  out_rv[...] = residual variance
  * (NaN where mean <= 0 or variance <= 0).  mv_fit[R][3] = quadratic log-log trend per group,
- * highest power first.  seg_skip (nullable): segments not to compute.
+ * highest power first.  seg_skip (nullable): segments not to compute.  gene_id (nullable,
+ * [n_seg / R]): global gene ids used in the RNG counter so that results do not depend on gene tiling
+ * or sharding.
  * Replaces: memento/bootstrap.py:74-116 (_bootstrap_1d), estimator.py:171-174 (tuple form),
  * hypothesis_test.py:186 -> estimator.py:103-111 (_residual_variance per replicate). */
 int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t* seg_ptr,
                     int64_t seg_lo, int64_t n_seg, int32_t R, const int32_t* seg_U,
                     const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
-                    int32_t estimator, int32_t num_boot, uint64_t seed, double* out_mean,
-                    double* out_rv);
+                    int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
+                    double* out_mean, double* out_rv);
 
 /* Deterministic replay: the same statistics from HOST-SUPPLIED resample counts.  Tables are in the
  * reference's order: x / inv_sf [sum U], W = per table a (num_boot x U_t) int64 block starting at
@@ -98,8 +100,8 @@ int mm_bootstrap_1d_replay(int device, void* stream, const double* x, const doub
  * Replaces: memento/hypothesis_test.py:23-33 (_fill), :167-200 of _ht_1d. */
 int mm_fill_log(int device, void* stream, const double* raw_mean, const double* raw_rv,
                 const uint8_t* seg_ok, const double* true_mean, const double* true_rv,
-                const int32_t* src_mean, const int32_t* src_rv, int64_t seg_lo, int64_t n_seg,
-                int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
+                const int32_t* src_mean, const int32_t* src_rv, const int64_t* gene_id, int32_t R,
+                int64_t n_seg, int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
                 uint8_t* seg_good, int32_t* n_valid);
 
 /* Batched small solves: for each of n_mask group-validity masks, the (T x R) linear functional C

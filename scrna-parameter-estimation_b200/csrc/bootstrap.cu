@@ -108,6 +108,7 @@ struct BootParams {
     int estimator;
     int B;
     unsigned long long seed;
+    const long long* gene_id;   // [n_seg / R] global gene ids for the RNG counter (nullable: local index)
     double* out_mean;           // [n_seg][B]
     double* out_rv;             // [n_seg][B]
 };
@@ -138,8 +139,10 @@ bootstrap_1d_kernel(BootParams P) {
     if (U < 0) { P.out_mean[o] = nan(""); P.out_rv[o] = nan(""); return; }
     const BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
     const int n_cells = P.group_ncells[r];
+    // RNG stream id: global (gene, group) so that results do not depend on tiling or gene sharding
+    const long long sid = P.gene_id ? P.gene_id[seg_rel / P.R] * P.R + r : seg;
     Philox rng;
-    rng.init(P.seed, (uint32_t)b, (uint32_t)seg, 0u, (uint32_t)(seg >> 32) ^ 0x1D1Du);
+    rng.init(P.seed, (uint32_t)b, (uint32_t)sid, 0u, (uint32_t)(sid >> 32) ^ 0x1D1Du);
     int n_rem = n_cells;
     double M1 = 0.0, M2 = 0.0;
     for (int u = 0; u < U; ++u) {
@@ -214,8 +217,8 @@ using namespace mm;
 MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t* seg_ptr,
                               int64_t seg_lo, int64_t n_seg, int32_t R, const int32_t* seg_U,
                               const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
-                              int32_t estimator, int32_t num_boot, uint64_t seed, double* out_mean,
-                              double* out_rv) {
+                              int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
+                              double* out_mean, double* out_rv) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_seg >= 0 && R > 0 && num_boot > 0, "n_seg/R/num_boot");
     MM_REQUIRE(n_seg <= 65535, "at most 65535 segments per launch (tile the genes)");
@@ -226,7 +229,7 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     P.entries = (const BootEntry*)entries; P.seg_ptr = (const long long*)seg_ptr; P.seg_lo = seg_lo;
     P.n_seg = n_seg; P.R = R; P.seg_U = seg_U; P.seg_skip = seg_skip; P.group_ncells = group_ncells;
     P.mv_fit = mv_fit; P.estimator = estimator; P.B = num_boot; P.seed = seed;
-    P.out_mean = out_mean; P.out_rv = out_rv;
+    P.gene_id = (const long long*)gene_id; P.out_mean = out_mean; P.out_rv = out_rv;
     dim3 grid((num_boot + kBootThreads - 1) / kBootThreads, (unsigned)n_seg);
     bootstrap_1d_kernel<<<grid, kBootThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_bootstrap_1d");

@@ -28,7 +28,8 @@ struct FillParams {
     const double* true_rv;      // [n_seg]
     const int* src_mean;        // replay: [n_seg][B] source replicate for invalid entries (-1 keep); nullable
     const int* src_rv;          // replay, nullable
-    long long seg_lo;           // global index of the first segment (RNG counter)
+    const long long* gene_id;   // [n_seg / R] global gene ids for the RNG counter (nullable: local index)
+    int R;
     int B;
     unsigned long long seed;
     double* boot_mean;          // [n_seg][B+1] log values, column 0 = log true value
@@ -89,13 +90,14 @@ fill_log_kernel(FillParams P) {
         return;
     }
     if (threadIdx.x == 0) { om[0] = log(P.true_mean[seg]); ov[0] = log(P.true_rv[seg]); }
+    const long long sid = P.gene_id ? P.gene_id[seg / P.R] * P.R + (seg % P.R) : seg;
     for (int b = threadIdx.x; b < B; b += kRegThreads) {
         double m = rm[b], v = rr[b];
         if (!(m > 0.0)) {
             if (P.src_mean) m = rm[P.src_mean[seg * (long long)B + b]];
             else {
                 Philox rng;
-                rng.init(P.seed, (uint32_t)b, (uint32_t)(P.seg_lo + seg), 0u, 0xF111u);
+                rng.init(P.seed, (uint32_t)b, (uint32_t)sid, (uint32_t)(sid >> 32), 0xF111u);
                 m = pick_valid(rm, B, nvm, rng);
             }
         }
@@ -103,7 +105,7 @@ fill_log_kernel(FillParams P) {
             if (P.src_rv) v = rr[P.src_rv[seg * (long long)B + b]];
             else {
                 Philox rng;
-                rng.init(P.seed, (uint32_t)b, (uint32_t)(P.seg_lo + seg), 0u, 0xF112u);
+                rng.init(P.seed, (uint32_t)b, (uint32_t)sid, (uint32_t)(sid >> 32), 0xF112u);
                 v = pick_valid(rr, B, nvr, rng);
             }
         }
@@ -386,18 +388,19 @@ using namespace mm;
 
 MM_EXPORT int mm_fill_log(int device, void* stream, const double* raw_mean, const double* raw_rv,
                           const uint8_t* seg_ok, const double* true_mean, const double* true_rv,
-                          const int32_t* src_mean, const int32_t* src_rv, int64_t seg_lo, int64_t n_seg,
-                          int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
+                          const int32_t* src_mean, const int32_t* src_rv, const int64_t* gene_id, int32_t R,
+                          int64_t n_seg, int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
                           uint8_t* seg_good, int32_t* n_valid) {
     if (int s = enter(device)) return s;
-    MM_REQUIRE(n_seg >= 0 && num_boot > 0, "n_seg/num_boot");
+    MM_REQUIRE(n_seg >= 0 && num_boot > 0 && R > 0, "n_seg/num_boot/R");
     if (n_seg == 0) return 0;
     MM_REQUIRE(raw_mean && raw_rv && seg_ok && true_mean && true_rv && boot_mean && boot_var && seg_good && n_valid,
                "null pointer");
     MM_REQUIRE(n_seg < 2147483647LL, "n_seg");
     FillParams P;
     P.raw_mean = raw_mean; P.raw_rv = raw_rv; P.seg_ok = seg_ok; P.true_mean = true_mean; P.true_rv = true_rv;
-    P.src_mean = src_mean; P.src_rv = src_rv; P.seg_lo = seg_lo; P.B = num_boot; P.seed = seed;
+    P.src_mean = src_mean; P.src_rv = src_rv; P.gene_id = (const long long*)gene_id; P.R = R; P.B = num_boot;
+    P.seed = seed;
     P.boot_mean = boot_mean; P.boot_var = boot_var; P.seg_good = seg_good; P.n_valid = n_valid;
     fill_log_kernel<<<(unsigned)n_seg, kRegThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_fill_log");

@@ -112,8 +112,9 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
 
 
 def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,
-               estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None):
-    """One tile of genes through the whole test.  true_mean / true_rv: (n_genes, R) host arrays."""
+               estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None, gene_id=None):
+    """One tile of genes through the whole test.  true_mean / true_rv: (n_genes, R) host arrays;
+    gene_id: int64 device vector of the tile's global gene ids (RNG stream ids)."""
     dev = seg.device
     R = seg.R
     T = treatment.shape[1]
@@ -130,7 +131,7 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
     raw_rv = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
     ev = timer.start()
     _lib.call("mm_bootstrap_1d", dev, tab["entries"], seg.seg_ptr, tab["seg_lo"], n_seg, R, tab["seg_U"],
-              seg_skip, design.n_cells, design.mv_fit, estimator, num_boot, seed, raw_mean, raw_rv)
+              seg_skip, design.n_cells, design.mv_fit, estimator, num_boot, seed, gene_id, raw_mean, raw_rv)
     timer.stop("bootstrap_1d", ev)
     if stats is not None:
         u = tab["seg_U"].clamp(min=0) * seg_ok.to(torch.int32)
@@ -142,7 +143,7 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
     seg_good = torch.empty(n_seg, dtype=torch.uint8, device=dev)
     n_valid = torch.empty(2 * n_seg, dtype=torch.int32, device=dev)
     ev = timer.start()
-    _lib.call("mm_fill_log", dev, raw_mean, raw_rv, seg_ok, tm, tv, None, None, tab["seg_lo"], n_seg, num_boot,
+    _lib.call("mm_fill_log", dev, raw_mean, raw_rv, seg_ok, tm, tv, None, None, gene_id, R, n_seg, num_boot,
               seed, boot_mean, boot_var, seg_good, n_valid)
     timer.stop("fill_log", ev)
     del raw_mean, raw_rv
@@ -187,7 +188,7 @@ def ht_1d_replay(device, R, replay, design_host, true_mean, true_rv, covariate, 
     src_m = d(replay["src_mean"], np.int32) if replay.get("src_mean") is not None else None
     src_v = d(replay["src_rv"], np.int32) if replay.get("src_rv") is not None else None
     _lib.call("mm_fill_log", device, raw_mean, raw_rv, seg_ok, d(true_mean.reshape(-1), np.float64),
-              d(true_rv.reshape(-1), np.float64), src_m, src_v, 0, n_seg, num_boot, 0, boot_mean, boot_var,
+              d(true_rv.reshape(-1), np.float64), src_m, src_v, None, R, n_seg, num_boot, 0, boot_mean, boot_var,
               seg_good, n_valid)
     res = regress_tile(device, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
                        np.asarray(design_host["n_cells"], dtype=np.float64), one_sample, approx, want_coef_rows, timer)

@@ -45,6 +45,8 @@ class DeviceState:
         self.cell_bin_host = None
         self.last_stats = {}
         self.host = None         # pinned host staging copies (end-to-end mode)
+        self.dist = None         # DistContext when the genes are sharded over ranks
+        self.gene_offset = 0     # global index of this rank's first gene column
 
     def __deepcopy__(self, memo):
         new = DeviceState(self.device)
@@ -59,7 +61,6 @@ class DeviceState:
                          "inv_sf": self.inv_sf_sorted.cpu().pin_memory()}
         self.seg = self.cell_bin = self.inv_sf_sorted = self.design = self.seg_all = None
         self.h2d_bytes = 0
-        torch.cuda.empty_cache()
 
     def ensure_resident(self):
         if self.seg is None:
@@ -141,11 +142,16 @@ def _residual_variance(mean, var, fit):
 
 # --------------------------------------------------------------------------- setup_memento
 def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_percent=0.1, shrinkage=0.5,
-                  num_bins=30, estimator_type="hyper_relative", device=None, profile=False, pinned=False):
+                  num_bins=30, estimator_type="hyper_relative", device=None, profile=False, pinned=False,
+                  dist=None, gene_offset=0):
     """Compute size factors and the overall moments.  reference: main.py:26-91.
 
     Build-only keywords: ``device`` (CUDA device), ``profile`` (collect per-kernel CUDA-event
-    times in ``uns['memento']['_b200'].timer``), ``pinned`` (stage uploads through pinned memory)."""
+    times in ``uns['memento']['_b200'].timer``), ``pinned`` (stage uploads through pinned memory),
+    ``dist`` (a :class:`memento_b200.dist.DistContext`: this rank holds a block of the gene columns of
+    the same cells; the UMI totals are all-reduced and the (mean, var) vectors all-gathered so that
+    size factors, trend and trim quantile are those of the full matrix; ``gene_offset`` = global index
+    of the rank's first gene column, used only to make the RNG stream ids global)."""
     if not inplace:
         adata = adata.copy()
     assert adata.obs[q_column].max() < 1
@@ -165,6 +171,8 @@ def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_p
     mem["num_bins"] = num_bins
     st = DeviceState(dev)
     st.timer = StageTimer(dev) if profile else NULL_TIMER
+    st.dist = dist
+    st.gene_offset = int(gene_offset)
     mem["_b200"] = st
 
     X = adata.X
@@ -177,18 +185,28 @@ def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_p
 
     # naive size factor = raw UMI totals (main.py:55-59); moments over all cells (:62-66)
     naive = st.csr.row_sums(None, st.timer)
+    if dist is not None:
+        naive = dist.all_reduce_sum(naive)
     sums = st.seg_all.moments(1.0 / naive, st.timer).cpu().numpy()[:, :, 0]
     all_m, all_v = _moments_from_sums(sums, n_cells, mem["all_q"], 0)
     all_m[sums[0] / n_cells < filter_mean_thresh] = 0                                      # :67
-    rv = _residual_variance(all_m, all_v, _fit_mv(all_m, all_v))                           # :68
-    rv_ulim = np.quantile(rv[np.isfinite(rv)], trim_percent)                               # :71
+    if dist is None:
+        fit = _fit_mv(all_m, all_v)
+    else:
+        fit = _fit_mv(dist.all_gather_concat(all_m)[0], dist.all_gather_concat(all_v)[0])
+    rv = _residual_variance(all_m, all_v, fit)                                             # :68
+    rv_all = rv if dist is None else dist.all_gather_concat(rv)[0]
+    rv_ulim = np.quantile(rv_all[np.isfinite(rv_all)], trim_percent)                       # :71
     rv[~np.isfinite(rv)] = np.inf
     mask = rv < rv_ulim
     mem["least_variable_genes"] = adata.var.index[mask].tolist()
 
     # size factor from the least variable genes (main.py:78-82 -> estimator.py:73-76)
     mask_d = to_device(mask.astype(np.uint8), dev)
-    totals = st.csr.row_sums(mask_d, st.timer).cpu().numpy()
+    totals = st.csr.row_sums(mask_d, st.timer)
+    if dist is not None:
+        totals = dist.all_reduce_sum(totals)
+    totals = totals.cpu().numpy()
     totals = totals + np.quantile(totals, shrinkage)
     size_factor = totals / totals.mean()
     adata.obs["memento_size_factor"] = size_factor
@@ -305,8 +323,14 @@ def compute_1d_moments(adata, inplace=True, min_perc_group=0.7, filter_genes=Tru
     mem["gene_rv_filter"] = {g: rv_filter[:, r].copy() for r, g in enumerate(groups)}
 
     # pooled mean-variance trend over the groups' (mean, var), concatenated in group order (:232-245)
-    mean_cat = np.concatenate([mean[rv_filter[:, r], r] for r in range(R)])
-    var_cat = np.concatenate([var[rv_filter[:, r], r] for r in range(R)])
+    if st.dist is None:
+        g_mean, g_var, g_rvf = mean, var, rv_filter
+    else:   # the trend is fitted on all ranks' genes, concatenated in global gene order
+        g_mean = st.dist.all_gather_concat(mean)[0]
+        g_var = st.dist.all_gather_concat(var)[0]
+        g_rvf = st.dist.all_gather_concat(rv_filter)[0]
+    mean_cat = np.concatenate([g_mean[g_rvf[:, r], r] for r in range(R)])
+    var_cat = np.concatenate([g_var[g_rvf[:, r], r] for r in range(R)])
     pooled = _fit_mv(mean_cat, var_cat)
     mem["mv_regressor"] = {"all": pooled}
     for g in groups:
@@ -388,11 +412,13 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
             out[k][:] = res[k].cpu().numpy()
         genes_per_tile = G + 1
         st.last_replay = res
+    gene_id = to_device(st.gene_index + st.gene_offset, st.device, np.int64)   # RNG stream ids (global)
     for lo in range(0, G if replay is None else 0, genes_per_tile):
         n = min(genes_per_tile, G - lo)
         res = engine.ht_1d_tile(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
                                 cov, tr_all, num_boot, estimator, seed, approx, one_sample,
-                                want_coef_rows=not approx, timer=st.timer, stats=stats_acc)
+                                want_coef_rows=not approx, timer=st.timer, stats=stats_acc,
+                                gene_id=gene_id[lo:lo + n])
         if not approx:
             gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
         for k in out:

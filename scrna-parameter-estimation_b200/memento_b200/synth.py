@@ -69,12 +69,13 @@ def design_from_groups(groups, label_columns, delimiter="^", treatment_col="stim
 
 
 def make_counts_fast(n_cells, n_genes, n_conditions=2, n_types=1, q=0.07, de_frac=0.1, log_fc=0.5, seed=7,
-                     chunk=4096, n_donors=1, device=None):
+                     chunk=4096, n_donors=1, device=None, shard=0):
     """Same model as :func:`make_counts`, with the gamma-Poisson draws done by torch (on ``device``
-    when given, e.g. the GPU for the bench's 25k x 10k matrix).  The per-gene / per-cell parameters
-    come from the same numpy stream, the counts from torch's generator seeded with ``seed``."""
+    when given, e.g. the GPU for the bench's 25k x 10k matrix).  Cell-level parameters depend on
+    ``seed`` only, gene-level parameters and the counts on (``seed``, ``shard``): different shards are
+    different gene blocks of the SAME cells (used for the gene-sharded multi-GPU runs)."""
     import torch
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng([seed, 1 + shard])
     mu = rng.lognormal(1.0, 1.4, n_genes)
     phi = rng.lognormal(-0.5, 0.5, n_genes)
     n_de = int(de_frac * n_genes)
@@ -85,13 +86,14 @@ def make_counts_fast(n_cells, n_genes, n_conditions=2, n_types=1, q=0.07, de_fra
     for t in range(1, n_types):
         sel = rng.random(n_genes) < 0.2
         type_eff[t, sel] = rng.normal(0, 0.7, sel.sum())
-    cond = rng.integers(0, n_conditions, n_cells)
-    ctype = rng.integers(0, n_types, n_cells)
-    donor = rng.integers(0, n_donors, n_cells)
-    scale = rng.lognormal(0.0, 0.3, n_cells)
+    crng = np.random.default_rng([seed, 0])
+    cond = crng.integers(0, n_conditions, n_cells)
+    ctype = crng.integers(0, n_types, n_cells)
+    donor = crng.integers(0, n_donors, n_cells)
+    scale = crng.lognormal(0.0, 0.3, n_cells)
     dev = torch.device(device) if device is not None else torch.device("cpu")
     gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
+    gen.manual_seed(seed * 1000003 + shard)
     t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)  # noqa: E731
     mu_t, shape_t = t(q * mu), t(1.0 / phi)
     ce, te, sc = t(np.exp(cond_eff)), t(np.exp(type_eff)), t(scale)
@@ -114,5 +116,5 @@ def make_counts_fast(n_cells, n_genes, n_conditions=2, n_types=1, q=0.07, de_fra
         "donor": np.array(["d%d" % d for d in donor]),
         "q": np.full(n_cells, q),
     }, index=pd.Index(["c%d" % i for i in range(n_cells)]))
-    var = pd.DataFrame(index=pd.Index(["gene%d" % i for i in range(n_genes)]))
+    var = pd.DataFrame(index=pd.Index(["gene%d" % (i + shard * n_genes) for i in range(n_genes)]))
     return AnnDataLite(X, obs, var)

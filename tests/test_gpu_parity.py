@@ -288,7 +288,7 @@ def test_rng_bootstrap_distribution_vs_oracle(gpu_prepared, oracle_prepared):
     raw_rv = torch.empty(n_seg * B, dtype=torch.float64, device=seg.device)
     from memento_b200 import _lib
     _lib.call("mm_bootstrap_1d", seg.device, tab["entries"], seg.seg_ptr, 0, n_seg, R, tab["seg_U"], None,
-              dstate.design.n_cells, dstate.design.mv_fit, 0, B, 1234, raw_mean, raw_rv)
+              dstate.design.n_cells, dstate.design.mv_fit, 0, B, 1234, None, raw_mean, raw_rv)
     torch.cuda.synchronize()
     gm = raw_mean.cpu().numpy().reshape(n_seg, B)
     grv = raw_rv.cpu().numpy().reshape(n_seg, B)
