@@ -37,12 +37,13 @@ int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32
  *   out[0*n_seg+s] = sum x          out[1*n_seg+s] = max x
  *   out[2*n_seg+s] = sum x/sf       out[3*n_seg+s] = sum x/sf^2     out[4*n_seg+s] = sum x^2/sf^2
  * inv_sf[cell] = 1/size_factor in the same (group-sorted) cell order as `rows`.
- * big_list: int32 scratch of nnz/32768 + 2 entries.
+ * nnz = seg_ptr[n_seg] (host copy, picks the launch shape); big_list: int32 scratch of nnz/4096 + 2
+ * entries.
  * Replaces: memento/estimator.py:175-185 (_hyper_1d_relative, sparse form; three sparse mat-vecs and
  * a squared copy) and the obs_mean / obs_max passes of memento/main.py:201, :206. */
 int mm_seg_moments(int device, void* stream, const float* vals, const int32_t* rows,
-                   const int64_t* seg_ptr, int64_t n_seg, const double* inv_sf, double* out,
-                   int32_t* big_list);
+                   const int64_t* seg_ptr, int64_t n_seg, int64_t nnz, const double* inv_sf,
+                   double* out, int32_t* big_list);
 
 /* Covariance sums of gene pairs within every group: for pair k and group r,
  *   out[k*R + r] = sum over cells of the group of x_{c,i} * x_{c,j} / sf_c^2
@@ -82,7 +83,26 @@ int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t
                     int64_t seg_lo, int64_t n_seg, int32_t R, const int32_t* seg_U,
                     const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                     int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
+                    const void* seg_info, const uint32_t* tab_pool, const uint32_t* acc_pool,
                     double* out_mean, double* out_rv);
+
+/* Poissonised sampler support (see csrc/bootstrap.cu header).  seg_info == NULL in mm_bootstrap_1d
+ * selects the conditional-binomial chain for every segment.
+ *   mm_poisson_table_size : HOST helper, no device work: offsets[n] (n = 0..n_max, may be NULL) of the
+ *                           32-bit inversion table of Poisson(n) inside one pool, *total = pool length.
+ *   mm_poisson_tables     : fills the pool on the device (offsets_dev = device copy of offsets).
+ *   mm_boot_prepare       : per segment, picks the remainder category and the sampler, rewrites the
+ *                           entries for Poisson-mode segments and builds the acceptance table
+ *                           g(s)/max g at acc_pool[(gene - gene_lo) * acc_stride + acc_slot[group]];
+ *                           seg_info = n_seg records of 48 bytes; segments whose expected acceptance
+ *                           rate is below min_accept, or with a multiplicity above n_table_max, keep
+ *                           the chain. */
+int mm_poisson_table_size(int32_t n_max, int32_t* offsets, int64_t* total);
+int mm_poisson_tables(int device, void* stream, int32_t n_max, const int32_t* offsets_dev, uint32_t* pool);
+int mm_boot_prepare(int device, void* stream, void* entries, const int64_t* seg_ptr, int64_t seg_lo,
+                    int64_t n_seg, int32_t R, const int32_t* seg_U, const int32_t* group_ncells,
+                    int32_t n_table_max, const int32_t* tab_off, const int64_t* acc_slot,
+                    int64_t acc_stride, uint32_t* acc_pool, void* seg_info, float min_accept);
 
 /* Deterministic replay: the same statistics from HOST-SUPPLIED resample counts.  Tables are in the
  * reference's order: x / inv_sf [sum U], W = per table a (num_boot x U_t) int64 block starting at

@@ -15,6 +15,18 @@
 //
 // mm_bootstrap_1d_replay evaluates the same moments from host-supplied resample counts (the
 // deterministic parity mode: must match the reference's statistics to 1e-6).
+//
+// Poissonised sampler (default where it applies).  The conditional-binomial chain needs per-thread
+// sampler parameters (the remaining pool differs per replicate) and diverges.  Instead: leave the
+// largest category out as the remainder, draw INDEPENDENT Poisson(n_u) counts for every other
+// category (parameters uniform across the warp -> inversion by binary search in precomputed 32-bit
+// CDF tables, shared by all categories with the same multiplicity), let S be their sum, and accept
+// with probability g(S) / max g where g(s) = Binomial(N, P)(s) / Poisson(M)(s), M = N P = sum n_u.
+// Because multinomial(x) / prod Poisson(x_u) depends on x only through s = sum x_u, the accepted
+// draw is EXACTLY multinomial(N, n / N); the acceptance rate is 1 / max g ~ sqrt(1 - P) (0.88 at 23 %
+// nonzero cells).  Segments where this would be below 0.4, or with a multiplicity above the table
+// range, use the chain.  Each lane loops over its own replicates and simply retries on rejection, so
+// rejections cost their expected value, not a warp-wide maximum.
 #include "common.cuh"
 
 namespace mm {
@@ -95,6 +107,178 @@ __device__ __forceinline__ int binom_btrs(Philox& rng, int n, float p) {
     return (int)m;  // unreachable in practice (acceptance probability > 0.8 per iteration)
 }
 
+// ---------------------------------------------------------------- Poisson inversion tables
+// Table for Poisson(lam): 32-bit thresholds thr[i] = floor(CDF(klo + i) * 2^32) over the k range that
+// holds all but < 2^-32 of the mass on either side (Chernoff bounds); the last threshold is 2^32 - 1.
+__host__ __device__ inline void poisson_range(double lam, int* klo, int* len) {
+    int hi = (int)floor(lam) + (int)ceil(7.5 + sqrt(44.4 * lam + 56.0));
+    int lo = (int)floor(lam - sqrt(44.4 * lam)) - 1;
+    if (lo < 0) lo = 0;
+    *klo = lo;
+    *len = hi - lo + 1;
+}
+
+__device__ void poisson_fill(double lam, int klo, int len, uint32_t* thr) {
+    const int m = (int)floor(lam);
+    double pm = exp((double)m * log(lam) - lam - lgamma((double)m + 1.0));
+    double p = pm;                                   // pmf at klo by downward recurrence from the mode
+    for (int k = m; k > klo; --k) p *= (double)k / lam;
+    if (klo > m) for (int k = m; k < klo; ++k) p *= lam / (double)(k + 1);
+    const double p_lo = p;
+    double total = 0.0;
+    for (int i = 0; i < len; ++i) { total += p; p *= lam / (double)(klo + i + 1); }
+    p = p_lo;
+    double cum = 0.0;
+    for (int i = 0; i < len; ++i) {
+        cum += p;
+        p *= lam / (double)(klo + i + 1);
+        double t = floor(cum / total * 4294967296.0);
+        thr[i] = (i == len - 1 || t >= 4294967295.0) ? 0xFFFFFFFFu : (uint32_t)t;
+    }
+}
+
+__global__ void poisson_tables_kernel(int n_max, const int* __restrict__ off, uint32_t* __restrict__ pool) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (n > n_max) return;
+    int klo, len;
+    poisson_range((double)n, &klo, &len);
+    poisson_fill((double)n, klo, len, pool + off[n]);
+}
+
+// first index i with thr[i] > r (thr ascending, thr[len-1] = 2^32 - 1)
+__device__ __forceinline__ int table_search(const uint32_t* __restrict__ thr, int len, uint32_t r) {
+    int lo = 0, n = len;
+    while (n > 1) {
+        int half = n >> 1;
+        uint32_t t = __ldg(thr + lo + half - 1);
+        if (t <= r) lo += half;
+        n -= half;
+    }
+    return lo;
+}
+
+struct __align__(16) SegInfo {     // written by boot_prepare_kernel, one per segment of the tile
+    int mode;        // 0: conditional-binomial chain, 1: Poissonised sampler, -1: all-NaN row
+    int s_lo;        // acceptance table covers S in [s_lo, s_lo + acc_len)
+    int acc_len;
+    int zero_off;    // table of the zero-count category when it is not the remainder (else -1)
+    int zero_kl;     // klo << 16 | len of that table
+    int rem_index;   // index of the remainder category among the nonzero entries, -1 if it is the zeros
+    long long acc_off;
+    double rem_a, rem_b;
+};
+
+struct PrepParams {
+    BootEntry* entries;
+    const long long* seg_ptr;
+    long long seg_lo, n_seg;
+    int R;
+    const int* seg_U;
+    const int* group_ncells;
+    int n_table_max;             // largest multiplicity with a universal table
+    const int* tab_off;          // [n_table_max + 1]
+    const long long* acc_slot;   // [R] offset of the group's acceptance slot inside one gene's stride
+    long long acc_stride;        // acceptance-table entries per gene
+    uint32_t* acc_pool;          // [n_genes_tile * acc_stride]
+    SegInfo* info;               // [n_seg]
+    float min_accept;            // fall back to the chain below this expected acceptance rate
+};
+
+// One warp per segment: choose the remainder category, decide the sampler, rewrite the entries'
+// (p, lq) fields as (table offset, klo << 16 | len) for Poisson-mode segments and build the
+// acceptance table g(s) / max g.
+__global__ void __launch_bounds__(256)
+boot_prepare_kernel(PrepParams P) {
+    const int lane = threadIdx.x & 31;
+    const long long seg_rel = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (seg_rel >= P.n_seg) return;
+    const long long seg = P.seg_lo + seg_rel;
+    const int r = (int)(seg % P.R);
+    const int U = P.seg_U[seg_rel];
+    SegInfo si;
+    si.mode = 0; si.s_lo = 0; si.acc_len = 0; si.zero_off = -1; si.zero_kl = 0; si.rem_index = -1;
+    si.acc_off = 0; si.rem_a = 0.0; si.rem_b = 0.0;
+    if (U < 0) { si.mode = -1; if (lane == 0) P.info[seg_rel] = si; return; }
+    BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
+    const int N = P.group_ncells[r];
+    // largest category and total nonzero mass
+    int best_n = 0, best_i = -1;
+    long long mass = 0;
+    for (int u = lane; u < U; u += 32) {
+        int n = tab[u].n;
+        mass += n;
+        if (n > best_n) { best_n = n; best_i = u; }
+    }
+    mass = warp_sum_ll(mass);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int on = __shfl_xor_sync(kFull, best_n, o), oi = __shfl_xor_sync(kFull, best_i, o);
+        if (on > best_n || (on == best_n && oi >= 0 && (best_i < 0 || oi < best_i))) { best_n = on; best_i = oi; }
+    }
+    const int n_zero = N - (int)mass;
+    int rem_n, rem_i;
+    if (n_zero >= best_n) { rem_n = n_zero; rem_i = -1; } else { rem_n = best_n; rem_i = best_i; }
+    const int M = N - rem_n;            // mass of the Poissonised categories
+    // every Poissonised multiplicity needs a universal table
+    int too_big = 0;
+    for (int u = lane; u < U; u += 32) if (u != rem_i && tab[u].n > P.n_table_max) too_big = 1;
+    if (rem_i >= 0 && n_zero > P.n_table_max) too_big = 1;
+    too_big = __any_sync(kFull, too_big);
+    if (too_big || M <= 0 || rem_n <= 0) {
+        // M == 0: a single category holds every cell (chain handles it trivially)
+        if (lane == 0) P.info[seg_rel] = si;
+        return;
+    }
+    // acceptance table: log g(s) = lgamma(N+1) - lgamma(N-s+1) - s log N + (N-s) log(rem_n / N) + M
+    int s_lo, len;
+    poisson_range((double)M, &s_lo, &len);
+    if (s_lo + len - 1 > N) len = N - s_lo + 1;
+    const long long acc_off = (seg_rel / P.R) * P.acc_stride + P.acc_slot[r];
+    uint32_t* acc = P.acc_pool + acc_off;
+    const double lN = log((double)N), lrem = log((double)rem_n / (double)N), lgN = lgamma((double)N + 1.0);
+    double best = -INFINITY;
+    for (int i = lane; i < len; i += 32) {
+        int sv = s_lo + i;
+        double lg = lgN - lgamma((double)(N - sv) + 1.0) - sv * lN + (double)(N - sv) * lrem + (double)M;
+        best = fmax(best, lg);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(kFull, best, o));
+    // expected acceptance = 1 / max g
+    if (exp(-best) < (double)P.min_accept) {
+        if (lane == 0) P.info[seg_rel] = si;
+        return;
+    }
+    for (int i = lane; i < len; i += 32) {
+        int sv = s_lo + i;
+        double lg = lgN - lgamma((double)(N - sv) + 1.0) - sv * lN + (double)(N - sv) * lrem + (double)M;
+        double t = floor(exp(lg - best) * 4294967296.0);
+        acc[i] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    }
+    for (int u = lane; u < U; u += 32) {
+        BootEntry e = tab[u];
+        int klo = 0, ln = 0, off = 0;
+        if (u != rem_i) { poisson_range((double)e.n, &klo, &ln); off = P.tab_off[e.n]; }
+        e.p = __int_as_float(off);
+        e.lq = __int_as_float((klo << 16) | ln);       // ln == 0 marks the remainder category
+        tab[u] = e;
+        if (u == rem_i) { si.rem_a = e.a; si.rem_b = e.b; }
+    }
+    if (rem_i >= 0) {   // broadcast the remainder's coefficients from the lane that owns it
+        int owner = rem_i & 31;
+        si.rem_a = __shfl_sync(kFull, si.rem_a, owner);
+        si.rem_b = __shfl_sync(kFull, si.rem_b, owner);
+        if (n_zero > 0) {
+            int klo, ln;
+            poisson_range((double)n_zero, &klo, &ln);
+            si.zero_off = P.tab_off[n_zero];
+            si.zero_kl = (klo << 16) | ln;
+        }
+    }
+    si.mode = 1; si.s_lo = s_lo; si.acc_len = len; si.rem_index = rem_i; si.acc_off = acc_off;
+    if (lane == 0) P.info[seg_rel] = si;
+}
+
 struct BootParams {
     const BootEntry* entries;
     const long long* seg_ptr;
@@ -109,6 +293,10 @@ struct BootParams {
     int B;
     unsigned long long seed;
     const long long* gene_id;   // [n_seg / R] global gene ids for the RNG counter (nullable: local index)
+    const SegInfo* info;        // [n_seg] sampler choice per segment (nullable: chain everywhere)
+    const uint32_t* tab_pool;   // universal Poisson tables
+    const uint32_t* acc_pool;   // acceptance tables
+    int reps_per_block;         // replicates handled by one block of the Poisson kernel
     double* out_mean;           // [n_seg][B]
     double* out_rv;             // [n_seg][B]
 };
@@ -137,6 +325,7 @@ bootstrap_1d_kernel(BootParams P) {
     const int U = P.seg_U[seg_rel];
     const long long o = seg_rel * (long long)P.B + b;
     if (U < 0) { P.out_mean[o] = nan(""); P.out_rv[o] = nan(""); return; }
+    if (P.info && P.info[seg_rel].mode == 1) return;      // handled by the Poissonised kernel
     const BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
     const int n_cells = P.group_ncells[r];
     // RNG stream id: global (gene, group) so that results do not depend on tiling or gene sharding
@@ -165,6 +354,62 @@ bootstrap_1d_kernel(BootParams P) {
     finish_replicate(M1, M2, (double)n_cells, P.estimator, P.mv_fit + 3 * r, mean, rv);
     P.out_mean[o] = mean;
     P.out_rv[o] = rv;
+}
+
+// ---------------------------------------------------------------- Poissonised sampler
+// Block = kBootThreads lanes, each looping over its own replicates of one segment (see header).
+__global__ void __launch_bounds__(kBootThreads)
+bootstrap_1d_poisson_kernel(BootParams P) {
+    const long long seg_rel = blockIdx.y;
+    if (P.seg_skip && P.seg_skip[seg_rel]) return;
+    const SegInfo si = P.info[seg_rel];
+    if (si.mode != 1) return;
+    const long long seg = P.seg_lo + seg_rel;
+    const int r = (int)(seg % P.R);
+    const int U = P.seg_U[seg_rel];
+    const BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
+    const int N = P.group_ncells[r];
+    const long long sid = P.gene_id ? P.gene_id[seg_rel / P.R] * P.R + r : seg;
+    const uint32_t* acc = P.acc_pool + si.acc_off;
+    const double* fit = P.mv_fit + 3 * r;
+    const int b_end = min(P.B, (int)(blockIdx.x + 1) * P.reps_per_block);
+    int b = blockIdx.x * P.reps_per_block + threadIdx.x;
+    Philox rng;
+    bool fresh = true;
+    while (b < b_end) {
+        if (fresh) { rng.init(P.seed, (uint32_t)b, (uint32_t)sid, 0u, (uint32_t)(sid >> 32) ^ 0x9015u); fresh = false; }
+        int S = 0;
+        double M1 = 0.0, M2 = 0.0;
+        for (int u = 0; u < U; ++u) {
+            const int4 lo4 = __ldg(reinterpret_cast<const int4*>(tab + u));
+            const int4 hi4 = __ldg(reinterpret_cast<const int4*>(tab + u) + 1);
+            const int kl = hi4.y;
+            const int len = kl & 0xFFFF;
+            if (len == 0) continue;                      // remainder category
+            const int k = (kl >> 16) + table_search(P.tab_pool + hi4.x, len, rng.next());
+            S += k;
+            const double kd = (double)k;
+            M1 = fma(__hiloint2double(lo4.y, lo4.x), kd, M1);
+            M2 = fma(__hiloint2double(lo4.w, lo4.z), kd, M2);
+        }
+        if (si.zero_off >= 0)
+            S += (si.zero_kl >> 16) + table_search(P.tab_pool + si.zero_off, si.zero_kl & 0xFFFF, rng.next());
+        const int i = S - si.s_lo;
+        bool ok = (i >= 0) && (i < si.acc_len);
+        if (ok) ok = rng.next() < __ldg(acc + i);
+        if (ok) {
+            const double w = (double)(N - S);            // the remainder category takes the rest
+            M1 = fma(si.rem_a, w, M1);
+            M2 = fma(si.rem_b, w, M2);
+            double mean, rv;
+            finish_replicate(M1, M2, (double)N, P.estimator, fit, mean, rv);
+            const long long o = seg_rel * (long long)P.B + b;
+            P.out_mean[o] = mean;
+            P.out_rv[o] = rv;
+            b += kBootThreads;
+            fresh = true;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- deterministic replay
@@ -214,10 +459,56 @@ bootstrap_1d_replay_kernel(ReplayParams P) {
 
 using namespace mm;
 
+MM_EXPORT int mm_poisson_table_size(int32_t n_max, int32_t* offsets, int64_t* total) {
+    // host helper: offsets[n] for n = 0..n_max (offsets may be NULL to query the total only)
+    long long off = 0;
+    for (int n = 0; n <= n_max; ++n) {
+        if (offsets) offsets[n] = (int32_t)off;
+        if (n >= 1) {
+            int klo, len;
+            poisson_range((double)n, &klo, &len);
+            off += len;
+        }
+    }
+    if (off > 2147483647LL) { mm::set_error("poisson table pool too large"); return 1; }
+    *total = off;
+    return 0;
+}
+
+MM_EXPORT int mm_poisson_tables(int device, void* stream, int32_t n_max, const int32_t* offsets_dev,
+                                uint32_t* pool) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(n_max >= 1 && n_max <= 32767, "n_max must be in 1..32767");
+    MM_REQUIRE(offsets_dev && pool, "null pointer");
+    poisson_tables_kernel<<<(n_max + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_max, offsets_dev, pool);
+    return check_launch("mm_poisson_tables");
+}
+
+MM_EXPORT int mm_boot_prepare(int device, void* stream, void* entries, const int64_t* seg_ptr, int64_t seg_lo,
+                              int64_t n_seg, int32_t R, const int32_t* seg_U, const int32_t* group_ncells,
+                              int32_t n_table_max, const int32_t* tab_off, const int64_t* acc_slot,
+                              int64_t acc_stride, uint32_t* acc_pool, void* seg_info, float min_accept) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(n_seg >= 0 && R > 0, "n_seg/R");
+    if (n_seg == 0) return 0;
+    MM_REQUIRE(entries && seg_ptr && seg_U && group_ncells && tab_off && acc_slot && acc_pool && seg_info,
+               "null pointer");
+    PrepParams P;
+    P.entries = (BootEntry*)entries; P.seg_ptr = (const long long*)seg_ptr; P.seg_lo = seg_lo; P.n_seg = n_seg;
+    P.R = R; P.seg_U = seg_U; P.group_ncells = group_ncells; P.n_table_max = n_table_max; P.tab_off = tab_off;
+    P.acc_slot = (const long long*)acc_slot; P.acc_stride = acc_stride; P.acc_pool = acc_pool;
+    P.info = (SegInfo*)seg_info; P.min_accept = min_accept;
+    long long blocks = (n_seg + 7) / 8;
+    MM_REQUIRE(blocks < 2147483647LL, "too many segments");
+    boot_prepare_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P);
+    return check_launch("mm_boot_prepare");
+}
+
 MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t* seg_ptr,
                               int64_t seg_lo, int64_t n_seg, int32_t R, const int32_t* seg_U,
                               const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                               int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
+                              const void* seg_info, const uint32_t* tab_pool, const uint32_t* acc_pool,
                               double* out_mean, double* out_rv) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_seg >= 0 && R > 0 && num_boot > 0, "n_seg/R/num_boot");
@@ -230,8 +521,16 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     P.n_seg = n_seg; P.R = R; P.seg_U = seg_U; P.seg_skip = seg_skip; P.group_ncells = group_ncells;
     P.mv_fit = mv_fit; P.estimator = estimator; P.B = num_boot; P.seed = seed;
     P.gene_id = (const long long*)gene_id; P.out_mean = out_mean; P.out_rv = out_rv;
+    P.info = (const SegInfo*)seg_info; P.tab_pool = tab_pool; P.acc_pool = acc_pool;
+    P.reps_per_block = kBootThreads * 16;
+    MM_REQUIRE(!seg_info || (tab_pool && acc_pool), "seg_info needs tab_pool and acc_pool");
     dim3 grid((num_boot + kBootThreads - 1) / kBootThreads, (unsigned)n_seg);
     bootstrap_1d_kernel<<<grid, kBootThreads, 0, (cudaStream_t)stream>>>(P);
+    if (int s = check_launch("mm_bootstrap_1d (chain)")) return s;
+    if (seg_info) {
+        dim3 grid2((num_boot + P.reps_per_block - 1) / P.reps_per_block, (unsigned)n_seg);
+        bootstrap_1d_poisson_kernel<<<grid2, kBootThreads, 0, (cudaStream_t)stream>>>(P);
+    }
     return check_launch("mm_bootstrap_1d");
 }
 

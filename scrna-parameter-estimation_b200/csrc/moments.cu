@@ -17,7 +17,7 @@
 
 namespace mm {
 
-constexpr int kBigSeg = 32768;  // nnz above which a segment is processed by a whole CTA
+constexpr int kBigSeg = 32768;  // largest nnz a warp-level group handles; longer segments use a whole CTA
 constexpr int kCtaThreads = 256;
 
 // Calls f(value, index) for every element of [lo, hi) using `nthr` cooperating threads
@@ -85,24 +85,39 @@ struct Mom {
     }
 };
 
+// W lanes cooperate on one segment (W = 8, 16 or 32; 32 / W segments per warp): short segments keep
+// every lane busy and need only log2(W) shuffle levels, while each group still reads whole 128-byte
+// lines (8 lanes x 16 B).  Segments above `big_thresh` nonzeros go to the CTA kernel through big_list.
+template <int W>
 __global__ void __launch_bounds__(kCtaThreads)
-seg_moments_warp_kernel(const float* __restrict__ vals, const int* __restrict__ rows,
-                        const long long* __restrict__ seg_ptr, long long n_seg,
-                        const double* __restrict__ inv_sf, double* __restrict__ out,
-                        int* __restrict__ big_list) {
+seg_moments_group_kernel(const float* __restrict__ vals, const int* __restrict__ rows,
+                         const long long* __restrict__ seg_ptr, long long n_seg,
+                         const double* __restrict__ inv_sf, double* __restrict__ out,
+                         int* __restrict__ big_list, int big_thresh) {
+    constexpr int kGroups = 32 / W;
     const int lane = threadIdx.x & 31;
-    long long seg = (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5);
-    if (seg >= n_seg) return;
-    long long lo = seg_ptr[seg], hi = seg_ptr[seg + 1];
-    if (hi - lo > kBigSeg) {
-        if (lane == 0) big_list[1 + atomicAdd(big_list, 1)] = (int)seg;
-        return;
+    const int sub = lane % W;
+    const long long warp_id = (long long)blockIdx.x * (kCtaThreads / 32) + (threadIdx.x >> 5);
+    const long long seg = warp_id * kGroups + lane / W;
+    const bool active = seg < n_seg;
+    long long lo = 0, hi = 0;
+    if (active) { lo = __ldg(seg_ptr + seg); hi = __ldg(seg_ptr + seg + 1); }
+    const bool big = (hi - lo > big_thresh);
+    if (big) {
+        if (sub == 0) big_list[1 + atomicAdd(big_list, 1)] = (int)seg;
+        hi = lo;
     }
     Mom m;
-    stream_pairs(vals, rows, lo, hi, lane, 32, [&](float v, int r) { m.add(v, __ldg(inv_sf + r)); });
-    m.sx = warp_sum(m.sx); m.s1 = warp_sum(m.s1); m.s2 = warp_sum(m.s2); m.s3 = warp_sum(m.s3);
-    m.mx = warp_max(m.mx);
-    if (lane == 0) {
+    stream_pairs(vals, rows, lo, hi, sub, W, [&](float v, int r) { m.add(v, __ldg(inv_sf + r)); });
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+        m.sx += __shfl_xor_sync(kFull, m.sx, o);
+        m.s1 += __shfl_xor_sync(kFull, m.s1, o);
+        m.s2 += __shfl_xor_sync(kFull, m.s2, o);
+        m.s3 += __shfl_xor_sync(kFull, m.s3, o);
+        m.mx = fmaxf(m.mx, __shfl_xor_sync(kFull, m.mx, o));
+    }
+    if (active && !big && sub == 0) {
         out[seg] = m.sx;
         out[n_seg + seg] = (double)m.mx;
         out[2 * n_seg + seg] = m.s1;
@@ -231,19 +246,31 @@ MM_EXPORT int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, c
 }
 
 MM_EXPORT int mm_seg_moments(int device, void* stream, const float* vals, const int32_t* rows,
-                             const int64_t* seg_ptr, int64_t n_seg, const double* inv_sf, double* out,
-                             int32_t* big_list) {
+                             const int64_t* seg_ptr, int64_t n_seg, int64_t nnz, const double* inv_sf,
+                             double* out, int32_t* big_list) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_seg >= 0, "n_seg");
     if (n_seg == 0) return 0;
     MM_REQUIRE(seg_ptr && inv_sf && out && big_list, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     MM_CUDA(cudaMemsetAsync(big_list, 0, sizeof(int32_t), st));
-    long long blocks = (n_seg + (kCtaThreads / 32) - 1) / (kCtaThreads / 32);
+    // group width by mean segment length; segments far above the mean (or long enough that a single
+    // warp would be the tail of the launch) are deferred to the CTA kernel
+    const long long mean_len = nnz / n_seg;
+    const int W = mean_len < 512 ? 8 : (mean_len < 2048 ? 16 : 32);
+    long long thr = nnz / (148LL * 64);
+    const int big_thresh = (int)(thr < 4096 ? 4096 : (thr > kBigSeg ? kBigSeg : thr));
+    const long long segs_per_block = (kCtaThreads / 32) * (32 / W);
+    long long blocks = (n_seg + segs_per_block - 1) / segs_per_block;
     MM_REQUIRE(blocks < 2147483647LL, "too many segments for one launch");
-    seg_moments_warp_kernel<<<(unsigned)blocks, kCtaThreads, 0, st>>>(
-        vals, rows, (const long long*)seg_ptr, n_seg, inv_sf, out, big_list);
-    if (int s = check_launch("seg_moments_warp")) return s;
+    const long long* sp = (const long long*)seg_ptr;
+    if (W == 8)
+        seg_moments_group_kernel<8><<<(unsigned)blocks, kCtaThreads, 0, st>>>(vals, rows, sp, n_seg, inv_sf, out, big_list, big_thresh);
+    else if (W == 16)
+        seg_moments_group_kernel<16><<<(unsigned)blocks, kCtaThreads, 0, st>>>(vals, rows, sp, n_seg, inv_sf, out, big_list, big_thresh);
+    else
+        seg_moments_group_kernel<32><<<(unsigned)blocks, kCtaThreads, 0, st>>>(vals, rows, sp, n_seg, inv_sf, out, big_list, big_thresh);
+    if (int s = check_launch("seg_moments_group")) return s;
     seg_moments_cta_kernel<<<148 * 4, kCtaThreads, 0, st>>>(
         vals, rows, (const long long*)seg_ptr, n_seg, inv_sf, out, big_list);
     return check_launch("seg_moments_cta");

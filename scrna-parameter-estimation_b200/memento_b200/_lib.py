@@ -17,17 +17,23 @@ _i32, _i64, _u64, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 # name -> argument ctypes after the leading (device, stream); every function returns int status
 SIGNATURES = {
     "mm_csr_row_sums": [_vp, _vp, _vp, _i64, _vp, _vp],
-    "mm_seg_moments": [_vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "mm_seg_moments": [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "mm_pair_products": [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],
     "mm_seg_unique": [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                       _vp, _vp, _vp, _vp],
-    "mm_bootstrap_1d": [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _u64, _vp, _vp, _vp],
+    "mm_bootstrap_1d": [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _u64, _vp, _vp, _vp, _vp,
+                        _vp, _vp],
+    "mm_poisson_tables": [_i32, _vp, _vp],
+    "mm_boot_prepare": [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, C.c_float],
     "mm_bootstrap_1d_replay": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "mm_fill_log": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _u64, _vp, _vp, _vp, _vp],
     "mm_wls_functional": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "mm_gev_tail_asl": [_vp, _vp, _i32, _i32, _vp, _vp],
     "mm_regress_asl": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
 }
+
+# host-only helpers (no leading device / stream arguments)
+HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp]}
 
 _lib = None
 
@@ -52,6 +58,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.c_int, _vp] + args
+    for name, args in HOST_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
     _lib = lib
     return lib
 
@@ -74,3 +84,15 @@ def call(name, device, *args):
     status = getattr(lib, name)(idx, stream, *conv)
     if status != 0:
         raise MementoCudaError("%s failed (status %d): %s" % (name, status, lib.mm_last_error().decode()))
+
+
+def poisson_table_offsets(n_max):
+    """Host helper: (offsets int32[n_max + 1], total) of the universal Poisson inversion tables."""
+    import numpy as np
+    lib = load()
+    off = np.zeros(n_max + 1, dtype=np.int32)
+    total = C.c_int64(0)
+    status = lib.mm_poisson_table_size(n_max, off.ctypes.data, C.addressof(total))
+    if status != 0:
+        raise MementoCudaError("mm_poisson_table_size failed: %s" % lib.mm_last_error().decode())
+    return off, int(total.value)

@@ -14,7 +14,6 @@ import torch
 
 from . import _lib
 
-BIG_SEG = 32768          # must match kBigSeg in csrc/moments.cu
 ENTRY_BYTES = 32         # sizeof(BootEntry)
 
 
@@ -194,10 +193,10 @@ class SegMatrix:
         """(5, G, R) float64 on the device: sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2."""
         out = torch.empty(5 * self.n_seg, dtype=torch.float64, device=self.device)
         if self._big is None:
-            self._big = torch.zeros(self.nnz // BIG_SEG + 2, dtype=torch.int32, device=self.device)
+            self._big = torch.zeros(self.nnz // 4096 + 2, dtype=torch.int32, device=self.device)
         ev = timer.start()
-        _lib.call("mm_seg_moments", self.device, self.vals, self.rows, self.seg_ptr, self.n_seg, inv_sf, out,
-                  self._big)
+        _lib.call("mm_seg_moments", self.device, self.vals, self.rows, self.seg_ptr, self.n_seg, self.nnz,
+                  inv_sf, out, self._big)
         timer.stop("seg_moments", ev)
         return out.view(5, self.G, self.R)
 

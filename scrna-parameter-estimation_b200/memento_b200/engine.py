@@ -10,6 +10,30 @@ from . import _lib
 from .device import ENTRY_BYTES, NULL_TIMER
 
 
+N_TABLE_MAX = 16384      # largest multiplicity with a universal Poisson inversion table
+SEG_INFO_BYTES = 48      # sizeof(SegInfo) in csrc/bootstrap.cu
+_TABLES = {}             # per device: (offsets tensor, pool tensor)
+
+
+def poisson_tables(device):
+    """Universal 32-bit inversion tables of Poisson(n), n = 1..N_TABLE_MAX, built once per device by
+    mm_poisson_tables (73 MB, shared by every segment of every call)."""
+    key = (device.type, device.index)
+    if key not in _TABLES:
+        off, total = _lib.poisson_table_offsets(N_TABLE_MAX)
+        off_d = torch.as_tensor(off, device=device)
+        pool = torch.empty(total, dtype=torch.int32, device=device)
+        _lib.call("mm_poisson_tables", device, N_TABLE_MAX, off_d, pool)
+        _TABLES[key] = (off_d, pool)
+    return _TABLES[key]
+
+
+def _poisson_len(lam):
+    hi = np.floor(lam) + np.ceil(7.5 + np.sqrt(44.4 * lam + 56.0))
+    lo = np.maximum(0, np.floor(lam - np.sqrt(44.4 * lam)) - 1)
+    return (hi - lo + 1).astype(np.int64)
+
+
 class GroupDesign:
     """Per-group vectors on the device, in group order (length R)."""
 
@@ -22,6 +46,10 @@ class GroupDesign:
         self.n_bins_present = torch.as_tensor(np.asarray(n_bins_present, dtype=np.int32), device=device)
         self.bin_inv_sf = torch.as_tensor(np.asarray(bin_inv_sf, dtype=np.float64), device=device)
         self.n_bins = int(self.bin_inv_sf.numel())
+        # acceptance-table slots of the Poissonised sampler: one per group, sized for M <= n_cells
+        slot = _poisson_len(self.n_cells_host.astype(np.float64)) + 2
+        self.acc_stride = int(slot.sum())
+        self.acc_slot = torch.as_tensor(np.concatenate([[0], np.cumsum(slot)[:-1]]).astype(np.int64), device=device)
 
 
 def tile_plan(seg, num_boot, workspace_bytes=6 << 30):
@@ -111,8 +139,41 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
             "n_masks": masks.shape[0]}
 
 
+def bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip=None, gene_id=None,
+                   sampler="poisson", min_accept=0.4, timer=NULL_TIMER):
+    """mm_boot_prepare (Poissonised sampler only) + mm_bootstrap_1d on the unique tables ``tab`` of a
+    gene tile.  Returns (raw_mean, raw_rv, seg_info) device tensors; raw_* are [n_seg * num_boot]."""
+    dev = seg.device
+    R = seg.R
+    n_seg = n_genes * R
+    raw_mean = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
+    raw_rv = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
+    seg_info = tab_pool = acc_pool = None
+    if sampler == "poisson":
+        tab_off, tab_pool = poisson_tables(dev)
+        acc_pool = torch.empty(max(1, n_genes * design.acc_stride), dtype=torch.int32, device=dev)
+        seg_info = torch.empty(n_seg * SEG_INFO_BYTES, dtype=torch.uint8, device=dev)
+        ev = timer.start()
+        _lib.call("mm_boot_prepare", dev, tab["entries"], seg.seg_ptr, tab["seg_lo"], n_seg, R, tab["seg_U"],
+                  design.n_cells, N_TABLE_MAX, tab_off, design.acc_slot, design.acc_stride, acc_pool, seg_info,
+                  float(min_accept))
+        timer.stop("boot_prepare", ev)
+    ev = timer.start()
+    _lib.call("mm_bootstrap_1d", dev, tab["entries"], seg.seg_ptr, tab["seg_lo"], n_seg, R, tab["seg_U"],
+              seg_skip, design.n_cells, design.mv_fit, estimator, num_boot, seed, gene_id, seg_info, tab_pool,
+              acc_pool, raw_mean, raw_rv)
+    timer.stop("bootstrap_1d", ev)
+    return raw_mean, raw_rv, seg_info
+
+
+def segment_modes(seg_info, n_seg):
+    """int32 tensor of the sampler chosen per segment (1 Poissonised, 0 chain, -1 all-NaN)."""
+    return seg_info.view(n_seg, SEG_INFO_BYTES)[:, :4].contiguous().view(torch.int32).reshape(-1)
+
+
 def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,
-               estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None, gene_id=None):
+               estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None, gene_id=None,
+               sampler="poisson", min_accept=0.4):
     """One tile of genes through the whole test.  true_mean / true_rv: (n_genes, R) host arrays;
     gene_id: int64 device vector of the tile's global gene ids (RNG stream ids)."""
     dev = seg.device
@@ -127,17 +188,17 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
     seg_skip = (seg_ok == 0).to(torch.uint8)
     tm = torch.as_tensor(np.ascontiguousarray(true_mean.reshape(-1), dtype=np.float64), device=dev)
     tv = torch.as_tensor(np.ascontiguousarray(true_rv.reshape(-1), dtype=np.float64), device=dev)
-    raw_mean = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
-    raw_rv = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
-    ev = timer.start()
-    _lib.call("mm_bootstrap_1d", dev, tab["entries"], seg.seg_ptr, tab["seg_lo"], n_seg, R, tab["seg_U"],
-              seg_skip, design.n_cells, design.mv_fit, estimator, num_boot, seed, gene_id, raw_mean, raw_rv)
-    timer.stop("bootstrap_1d", ev)
+    raw_mean, raw_rv, seg_info = bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip,
+                                                gene_id, sampler, min_accept, timer)
     if stats is not None:
         u = tab["seg_U"].clamp(min=0) * seg_ok.to(torch.int32)
         stats["category_draws"] = stats.get("category_draws", 0) + int(u.sum().item()) * num_boot
         stats["unique_bytes"] = stats.get("unique_bytes", 0) + unique_bytes(tab, seg.n_cells)
         stats["segments"] = stats.get("segments", 0) + n_seg
+        if seg_info is not None and stats.get("want_modes"):
+            modes = segment_modes(seg_info, n_seg)
+            stats["poisson_segments"] = stats.get("poisson_segments", 0) + int(((modes == 1) & (seg_ok != 0)).sum().item())
+            stats["chain_segments"] = stats.get("chain_segments", 0) + int(((modes == 0) & (seg_ok != 0)).sum().item())
     boot_mean = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
     boot_var = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
     seg_good = torch.empty(n_seg, dtype=torch.uint8, device=dev)
@@ -150,7 +211,8 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
     res = regress_tile(dev, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
                        design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer)
     if stats is not None:
-        stats["launches"] = stats.get("launches", 0) + 7  # unique x2, bootstrap, fill, wls, regress (+memset)
+        # unique x2 (+memset), prepare, bootstrap x2, fill, wls, regress
+        stats["launches"] = stats.get("launches", 0) + (9 if sampler == "poisson" else 7)
     return res
 
 

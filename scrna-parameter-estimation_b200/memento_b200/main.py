@@ -364,14 +364,17 @@ def _refresh_design(adata):
 
 # --------------------------------------------------------------------------- ht_1d_moments
 def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=True, num_boot=10000,
-                  verbose=1, num_cpus=1, seed=0, workspace_bytes=6 << 30, replay=None, **kwargs):
+                  verbose=1, num_cpus=1, seed=0, workspace_bytes=6 << 30, replay=None, sampler="poisson",
+                  **kwargs):
     """Hypothesis test for the mean and the residual variance.  reference: main.py:341-415.
 
     ``num_cpus`` / ``verbose`` are accepted and ignored (the GPU grid replaces the process pool).
     Test keywords as in the reference: ``resampling='bootstrap'`` (only mode on the device path),
     ``approx``, ``resample_rep``.  Build-only: ``seed`` (Philox key), ``workspace_bytes``,
     ``replay`` (deterministic parity mode: host-supplied unique tables, resample counts and
-    imputation sources for every (gene, group); see engine.ht_1d_replay)."""
+    imputation sources for every (gene, group); see engine.ht_1d_replay), ``sampler`` ("poisson":
+    Poissonised exact multinomial with the conditional-binomial chain as per-segment fallback;
+    "chain": the chain everywhere)."""
     if not inplace:
         adata = adata.copy()
     resampling = kwargs.pop("resampling", "bootstrap")
@@ -400,7 +403,9 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
 
     genes_per_tile = engine.tile_plan(st.seg, num_boot, workspace_bytes)
     out = {k: np.full((G, 2, T), np.nan) for k in ("coef", "se", "asl")}
-    stats_acc = {}
+    stats_acc = {"want_modes": bool(getattr(st, "count_modes", False))}
+    if sampler not in ("poisson", "chain"):
+        raise ValueError("sampler must be 'poisson' or 'chain'")
     if replay is not None:
         dh = {"n_cells": np.diff(st.group_start), "q": [mem["group_q"][g] for g in groups],
               "mv_fit": np.stack([mem["mv_regressor"][g] for g in groups])}
@@ -418,7 +423,7 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         res = engine.ht_1d_tile(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
                                 cov, tr_all, num_boot, estimator, seed, approx, one_sample,
                                 want_coef_rows=not approx, timer=st.timer, stats=stats_acc,
-                                gene_id=gene_id[lo:lo + n])
+                                gene_id=gene_id[lo:lo + n], sampler=sampler)
         if not approx:
             gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
         for k in out:

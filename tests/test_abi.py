@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_python_signatures_cover_the_header():
     names = set(declared_symbols()) - {"mm_version", "mm_last_error"}
-    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+    bound = set(_lib.SIGNATURES) | set(_lib.HOST_SIGNATURES)
+    assert names == bound, names ^ bound
 
 
 def test_header_compiles_as_c(tmp_path):
@@ -56,3 +57,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(base, f)
+
+
+def test_poisson_table_offsets_host_helper():
+    """Host-only entry point (no GPU needed): table k-ranges must hold all but ~2^-32 of the mass."""
+    import scipy.stats as st
+    off, total = _lib.poisson_table_offsets(64)
+    assert off[0] == 0 and off[1] == 0 and total > off[64] > off[63]
+    for n in (1, 7, 64):
+        length = (off[n + 1] if n < 64 else total) - off[n]
+        hi = int(np.floor(n)) + int(np.ceil(7.5 + np.sqrt(44.4 * n + 56.0)))
+        lo = max(0, int(np.floor(n - np.sqrt(44.4 * n))) - 1)
+        assert length == hi - lo + 1
+        assert st.poisson.sf(hi, n) < 2.4e-10 and (lo == 0 or st.poisson.cdf(lo - 1, n) < 2.4e-10)

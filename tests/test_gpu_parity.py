@@ -272,10 +272,12 @@ def test_ht_1d_replay_one_sample(gpu_prepared, oracle_prepared):
 
 
 # ----------------------------------------------------------------------------- bootstrap, RNG mode
-def test_rng_bootstrap_distribution_vs_oracle(gpu_prepared, oracle_prepared):
-    """Philox multinomial (conditional binomials: inversion + BTRS) against numpy's multinomial on
-    the same unique tables: two-sample KS on the bootstrapped mean and variance of several
-    (gene, group) slices, plus agreement of their first two moments within Monte Carlo error."""
+@pytest.mark.parametrize("sampler", ["poisson", "chain"])
+def test_rng_bootstrap_distribution_vs_oracle(gpu_prepared, oracle_prepared, sampler):
+    """Philox multinomial against numpy's multinomial on the same unique tables, for both device
+    samplers (Poissonised tables + acceptance step; conditional binomials by inversion / BTRS):
+    two-sample KS on the bootstrapped mean and residual variance of several (gene, group) slices,
+    agreement of the first two moments within Monte Carlo error, uniformity of the KS p-values."""
     mem = gpu_prepared.uns["memento"]
     dstate = mem["_b200"]
     omem = oracle_prepared.uns["memento"]
@@ -284,12 +286,11 @@ def test_rng_bootstrap_distribution_vs_oracle(gpu_prepared, oracle_prepared):
     B = 4000
     tab = engine.unique_tables(seg, dstate.design, dstate.cell_bin, 0, G, 0)
     n_seg = G * R
-    raw_mean = torch.empty(n_seg * B, dtype=torch.float64, device=seg.device)
-    raw_rv = torch.empty(n_seg * B, dtype=torch.float64, device=seg.device)
-    from memento_b200 import _lib
-    _lib.call("mm_bootstrap_1d", seg.device, tab["entries"], seg.seg_ptr, 0, n_seg, R, tab["seg_U"], None,
-              dstate.design.n_cells, dstate.design.mv_fit, 0, B, 1234, None, raw_mean, raw_rv)
+    raw_mean, raw_rv, info = engine.bootstrap_tile(seg, dstate.design, tab, G, 0, B, 1234, sampler=sampler)
     torch.cuda.synchronize()
+    if sampler == "poisson":
+        modes = engine.segment_modes(info, n_seg).cpu().numpy()
+        assert (modes == 1).mean() > 0.8          # the Poissonised path really is the one exercised
     gm = raw_mean.cpu().numpy().reshape(n_seg, B)
     grv = raw_rv.cpu().numpy().reshape(n_seg, B)
     sums = np.stack([mem["1d_moments"][g][0] for g in mem["groups"]], axis=1)
@@ -306,7 +307,6 @@ def test_rng_bootstrap_distribution_vs_oracle(gpu_prepared, oracle_prepared):
                 continue
             orv = o_moments.residual_variance(om, ov, omem["mv_regressor"][g])
             s = gene * R + r
-            # first two moments of the bootstrapped mean: |diff| < 5 standard errors
             se = om.std() / np.sqrt(B)
             assert abs(gm[s].mean() - om.mean()) < 6 * se + 1e-12, (gene, r)
             assert abs(gm[s].std() / om.std() - 1) < 0.08, (gene, r)
@@ -319,6 +319,36 @@ def test_rng_bootstrap_distribution_vs_oracle(gpu_prepared, oracle_prepared):
     assert pvals.size > 40
     assert pvals.min() > 1e-4, pvals.min()                   # no slice rejects grossly
     assert stats.kstest(pvals, "uniform").pvalue > 1e-3      # and the KS p-values look uniform
+
+
+def test_samplers_agree_exact_moments(gpu_prepared):
+    """Exactness check that does not need the oracle: for a multinomial(N, n/N) resample the
+    bootstrapped mean has expectation = the point estimate computed with the binned size factors
+    and a known variance; both samplers must reproduce them within 5 standard errors on every
+    valid segment (B = 20000)."""
+    mem = gpu_prepared.uns["memento"]
+    dstate = mem["_b200"]
+    seg = dstate.seg
+    G, R = seg.G, seg.R
+    B = 20000
+    n_seg = G * R
+    out = {}
+    for sampler in ("poisson", "chain"):
+        tab = engine.unique_tables(seg, dstate.design, dstate.cell_bin, 0, G, 0)
+        raw_mean, _, _ = engine.bootstrap_tile(seg, dstate.design, tab, G, 0, B, 99, sampler=sampler)
+        torch.cuda.synchronize()
+        out[sampler] = raw_mean.cpu().numpy().reshape(n_seg, B)
+    a, b = out["poisson"], out["chain"]
+    ok = np.isfinite(a).all(axis=1) & np.isfinite(b).all(axis=1)
+    assert ok.sum() > 0.9 * n_seg
+    ma, mb = a[ok].mean(axis=1), b[ok].mean(axis=1)
+    sa, sb = a[ok].std(axis=1), b[ok].std(axis=1)
+    se = np.sqrt(sa ** 2 + sb ** 2) / np.sqrt(B) + 1e-15
+    z = (ma - mb) / se
+    assert np.abs(z).max() < 5.5, np.abs(z).max()
+    assert abs(z.mean()) < 0.2 and 0.85 < z.std() < 1.15      # the z-scores look standard normal
+    ratio = sa[sb > 0] / sb[sb > 0]
+    assert np.abs(ratio - 1).max() < 0.06, np.abs(ratio - 1).max()
 
 
 def test_rng_ht_1d_vs_oracle_pvalues(gpu_prepared, oracle_prepared):
