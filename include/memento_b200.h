@@ -83,14 +83,16 @@ int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t
                     int64_t seg_lo, int64_t n_seg, int32_t R, const int32_t* seg_U,
                     const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                     int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
-                    const void* seg_info, const uint32_t* tab_pool, const uint32_t* acc_pool,
+                    const void* seg_info, const void* tab_pool, const uint32_t* acc_pool,
                     double* out_mean, double* out_rv);
 
 /* Poissonised sampler support (see csrc/bootstrap.cu header).  seg_info == NULL in mm_bootstrap_1d
  * selects the conditional-binomial chain for every segment.
  *   mm_poisson_table_size : HOST helper, no device work: offsets[n] (n = 0..n_max, may be NULL) of the
- *                           32-bit inversion table of Poisson(n) inside one pool, *total = pool length.
- *   mm_poisson_tables     : fills the pool on the device (offsets_dev = device copy of offsets).
+ *                           alias table of Poisson(n) inside one pool, *total = pool length in 8-byte
+ *                           cells {keep probability * 2^32, alias index}.
+ *   mm_poisson_tables     : fills the pool on the device (offsets_dev = device copy of offsets;
+ *                           scratch_p / scratch_a / scratch_b: `total` doubles / int32 / int32).
  *   mm_boot_prepare       : per segment, picks the remainder category and the sampler, rewrites the
  *                           entries for Poisson-mode segments and builds the acceptance table
  *                           g(s)/max g at acc_pool[(gene - gene_lo) * acc_stride + acc_slot[group]];
@@ -98,7 +100,8 @@ int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t
  *                           rate is below min_accept, or with a multiplicity above n_table_max, keep
  *                           the chain. */
 int mm_poisson_table_size(int32_t n_max, int32_t* offsets, int64_t* total);
-int mm_poisson_tables(int device, void* stream, int32_t n_max, const int32_t* offsets_dev, uint32_t* pool);
+int mm_poisson_tables(int device, void* stream, int32_t n_max, const int32_t* offsets_dev, void* pool,
+                      double* scratch_p, int32_t* scratch_a, int32_t* scratch_b);
 int mm_boot_prepare(int device, void* stream, void* entries, const int64_t* seg_ptr, int64_t seg_lo,
                     int64_t n_seg, int32_t R, const int32_t* seg_U, const int32_t* group_ncells,
                     int32_t n_table_max, const int32_t* tab_off, const int64_t* acc_slot,

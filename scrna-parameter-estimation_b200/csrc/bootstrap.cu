@@ -19,13 +19,13 @@
 // Poissonised sampler (default where it applies).  The conditional-binomial chain needs per-thread
 // sampler parameters (the remaining pool differs per replicate) and diverges.  Instead: leave the
 // largest category out as the remainder, draw INDEPENDENT Poisson(n_u) counts for every other
-// category (parameters uniform across the warp -> inversion by binary search in precomputed 32-bit
-// CDF tables, shared by all categories with the same multiplicity), let S be their sum, and accept
+// category (parameters uniform across the warp -> O(1) alias-table lookups in precomputed tables
+// shared by all categories with the same multiplicity), let S be their sum, and accept
 // with probability g(S) / max g where g(s) = Binomial(N, P)(s) / Poisson(M)(s), M = N P = sum n_u.
 // Because multinomial(x) / prod Poisson(x_u) depends on x only through s = sum x_u, the accepted
 // draw is EXACTLY multinomial(N, n / N); the acceptance rate is 1 / max g ~ sqrt(1 - P) (0.88 at 23 %
-// nonzero cells).  Segments where this would be below 0.4, or with a multiplicity above the table
-// range, use the chain.  Each lane loops over its own replicates and simply retries on rejection, so
+// nonzero cells).  Segments where this would be below min_accept (flat, dense genes), or with a
+// multiplicity above the table range, use the chain.  Each lane loops over its own replicates and simply retries on rejection, so
 // rejections cost their expected value, not a warp-wide maximum.
 #include "common.cuh"
 
@@ -107,9 +107,8 @@ __device__ __forceinline__ int binom_btrs(Philox& rng, int n, float p) {
     return (int)m;  // unreachable in practice (acceptance probability > 0.8 per iteration)
 }
 
-// ---------------------------------------------------------------- Poisson inversion tables
-// Table for Poisson(lam): 32-bit thresholds thr[i] = floor(CDF(klo + i) * 2^32) over the k range that
-// holds all but < 2^-32 of the mass on either side (Chernoff bounds); the last threshold is 2^32 - 1.
+// ---------------------------------------------------------------- Poisson tables
+// k range of the table of Poisson(lam): all but < 2^-32 of the mass on either side (Chernoff bounds).
 __host__ __device__ inline void poisson_range(double lam, int* klo, int* len) {
     int hi = (int)floor(lam) + (int)ceil(7.5 + sqrt(44.4 * lam + 56.0));
     int lo = (int)floor(lam - sqrt(44.4 * lam)) - 1;
@@ -118,43 +117,51 @@ __host__ __device__ inline void poisson_range(double lam, int* klo, int* len) {
     *len = hi - lo + 1;
 }
 
-__device__ void poisson_fill(double lam, int klo, int len, uint32_t* thr) {
+// Alias table (Walker / Vose) of Poisson(lam) restricted to k in [klo, klo + len): cell j keeps j with
+// probability prob[j] / 2^32 and otherwise yields alias[j].  One 32-bit random number r gives both the
+// cell (high word of r * len) and the fraction inside it (low word): one multiply, one 8-byte load,
+// one compare -- no search loop, no divergence.  Built by one thread per table in float64; the tails
+// outside the range (< 2^-32 each) are folded in by normalising the pmf over the range.
+__device__ void poisson_alias_fill(double lam, int klo, int len, uint2* tab, double* p, int* small, int* large) {
     const int m = (int)floor(lam);
-    double pm = exp((double)m * log(lam) - lam - lgamma((double)m + 1.0));
-    double p = pm;                                   // pmf at klo by downward recurrence from the mode
-    for (int k = m; k > klo; --k) p *= (double)k / lam;
-    if (klo > m) for (int k = m; k < klo; ++k) p *= lam / (double)(k + 1);
-    const double p_lo = p;
-    double total = 0.0;
-    for (int i = 0; i < len; ++i) { total += p; p *= lam / (double)(klo + i + 1); }
-    p = p_lo;
-    double cum = 0.0;
+    double q = exp((double)m * log(lam) - lam - lgamma((double)m + 1.0));    // pmf at the mode
+    for (int k = m; k > klo; --k) q *= (double)k / lam;                         // ... at klo
+    if (klo > m) for (int k = m; k < klo; ++k) q *= lam / (double)(k + 1);
+    double total = 0.0, w = q;
+    for (int i = 0; i < len; ++i) { p[i] = w; total += w; w *= lam / (double)(klo + i + 1); }
+    int ns = 0, nl = 0;
+    const double scale = (double)len / total;
     for (int i = 0; i < len; ++i) {
-        cum += p;
-        p *= lam / (double)(klo + i + 1);
-        double t = floor(cum / total * 4294967296.0);
-        thr[i] = (i == len - 1 || t >= 4294967295.0) ? 0xFFFFFFFFu : (uint32_t)t;
+        p[i] *= scale;
+        if (p[i] < 1.0) small[ns++] = i; else large[nl++] = i;
     }
+    while (ns > 0 && nl > 0) {
+        int sidx = small[--ns], lidx = large[--nl];
+        double t = floor(p[sidx] * 4294967296.0);
+        tab[sidx] = make_uint2(t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t, (uint32_t)lidx);
+        p[lidx] = (p[lidx] + p[sidx]) - 1.0;
+        if (p[lidx] < 1.0) small[ns++] = lidx; else large[nl++] = lidx;
+    }
+    while (nl > 0) { int i = large[--nl]; tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)i); }
+    while (ns > 0) { int i = small[--ns]; tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)i); }   // round-off leftovers
 }
 
-__global__ void poisson_tables_kernel(int n_max, const int* __restrict__ off, uint32_t* __restrict__ pool) {
+__global__ void poisson_tables_kernel(int n_max, const int* __restrict__ off, uint2* __restrict__ pool,
+                                      double* __restrict__ sp, int* __restrict__ ss, int* __restrict__ sl) {
     int n = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (n > n_max) return;
+    if (n == 1) pool[0] = make_uint2(0xFFFFFFFFu, 0u);     // null table
     int klo, len;
     poisson_range((double)n, &klo, &len);
-    poisson_fill((double)n, klo, len, pool + off[n]);
+    poisson_alias_fill((double)n, klo, len, pool + off[n], sp + off[n], ss + off[n], sl + off[n]);
 }
 
-// first index i with thr[i] > r (thr ascending, thr[len-1] = 2^32 - 1)
-__device__ __forceinline__ int table_search(const uint32_t* __restrict__ thr, int len, uint32_t r) {
-    int lo = 0, n = len;
-    while (n > 1) {
-        int half = n >> 1;
-        uint32_t t = __ldg(thr + lo + half - 1);
-        if (t <= r) lo += half;
-        n -= half;
-    }
-    return lo;
+// k - klo for one 32-bit random number
+__device__ __forceinline__ int alias_sample(const uint2* __restrict__ tab, int len, uint32_t r) {
+    const unsigned long long m = (unsigned long long)r * (unsigned)len;
+    const int j = (int)(m >> 32);
+    const uint2 e = __ldg(tab + j);
+    return ((uint32_t)m < e.x) ? j : (int)e.y;
 }
 
 struct __align__(16) SegInfo {     // written by boot_prepare_kernel, one per segment of the tile
@@ -260,7 +267,7 @@ boot_prepare_kernel(PrepParams P) {
         int klo = 0, ln = 0, off = 0;
         if (u != rem_i) { poisson_range((double)e.n, &klo, &ln); off = P.tab_off[e.n]; }
         e.p = __int_as_float(off);
-        e.lq = __int_as_float((klo << 16) | ln);       // ln == 0 marks the remainder category
+        e.lq = __int_as_float((klo << 16) | ln);       // remainder: off = klo = ln = 0 -> reads the null cell, k = 0
         tab[u] = e;
         if (u == rem_i) { si.rem_a = e.a; si.rem_b = e.b; }
     }
@@ -294,7 +301,7 @@ struct BootParams {
     unsigned long long seed;
     const long long* gene_id;   // [n_seg / R] global gene ids for the RNG counter (nullable: local index)
     const SegInfo* info;        // [n_seg] sampler choice per segment (nullable: chain everywhere)
-    const uint32_t* tab_pool;   // universal Poisson tables
+    const uint2* tab_pool;      // universal Poisson alias tables
     const uint32_t* acc_pool;   // acceptance tables
     int reps_per_block;         // replicates handled by one block of the Poisson kernel
     double* out_mean;           // [n_seg][B]
@@ -373,6 +380,9 @@ bootstrap_1d_poisson_kernel(BootParams P) {
     const uint32_t* acc = P.acc_pool + si.acc_off;
     const double* fit = P.mv_fit + 3 * r;
     const int b_end = min(P.B, (int)(blockIdx.x + 1) * P.reps_per_block);
+    __shared__ int s_next;
+    if (threadIdx.x == 0) s_next = blockIdx.x * P.reps_per_block + kBootThreads;
+    __syncthreads();
     int b = blockIdx.x * P.reps_per_block + threadIdx.x;
     Philox rng;
     bool fresh = true;
@@ -380,23 +390,33 @@ bootstrap_1d_poisson_kernel(BootParams P) {
         if (fresh) { rng.init(P.seed, (uint32_t)b, (uint32_t)sid, 0u, (uint32_t)(sid >> 32) ^ 0x9015u); fresh = false; }
         int S = 0;
         double M1 = 0.0, M2 = 0.0;
-        for (int u = 0; u < U; ++u) {
+        // four categories per Philox block; the remainder category has len == 0 and table cell {0, 0},
+        // so it contributes k = 0 without a branch
+        auto draw = [&](int u, uint32_t rnd) {
             const int4 lo4 = __ldg(reinterpret_cast<const int4*>(tab + u));
             const int4 hi4 = __ldg(reinterpret_cast<const int4*>(tab + u) + 1);
             const int kl = hi4.y;
-            const int len = kl & 0xFFFF;
-            if (len == 0) continue;                      // remainder category
-            const int k = (kl >> 16) + table_search(P.tab_pool + hi4.x, len, rng.next());
+            const int k = (kl >> 16) + alias_sample(P.tab_pool + hi4.x, kl & 0xFFFF, rnd);
             S += k;
             const double kd = (double)k;
             M1 = fma(__hiloint2double(lo4.y, lo4.x), kd, M1);
             M2 = fma(__hiloint2double(lo4.w, lo4.z), kd, M2);
+        };
+        int u = 0;
+        for (; u + 4 <= U; u += 4) {
+            const uint4 r4 = rng.block();
+            draw(u, r4.x); draw(u + 1, r4.y); draw(u + 2, r4.z); draw(u + 3, r4.w);
         }
+        uint4 r4 = rng.block();
+        if (u < U) draw(u, r4.x);
+        if (u + 1 < U) draw(u + 1, r4.y);
+        if (u + 2 < U) draw(u + 2, r4.z);
         if (si.zero_off >= 0)
-            S += (si.zero_kl >> 16) + table_search(P.tab_pool + si.zero_off, si.zero_kl & 0xFFFF, rng.next());
+            S += (si.zero_kl >> 16) + alias_sample(P.tab_pool + si.zero_off, si.zero_kl & 0xFFFF, r4.w);
+        r4 = rng.block();
         const int i = S - si.s_lo;
         bool ok = (i >= 0) && (i < si.acc_len);
-        if (ok) ok = rng.next() < __ldg(acc + i);
+        if (ok) ok = r4.x < __ldg(acc + i);
         if (ok) {
             const double w = (double)(N - S);            // the remainder category takes the rest
             M1 = fma(si.rem_a, w, M1);
@@ -406,7 +426,7 @@ bootstrap_1d_poisson_kernel(BootParams P) {
             const long long o = seg_rel * (long long)P.B + b;
             P.out_mean[o] = mean;
             P.out_rv[o] = rv;
-            b += kBootThreads;
+            b = atomicAdd(&s_next, 1);                   // results depend on (seed, b) only, not on the lane
             fresh = true;
         }
     }
@@ -460,10 +480,12 @@ bootstrap_1d_replay_kernel(ReplayParams P) {
 using namespace mm;
 
 MM_EXPORT int mm_poisson_table_size(int32_t n_max, int32_t* offsets, int64_t* total) {
-    // host helper: offsets[n] for n = 0..n_max (offsets may be NULL to query the total only)
+    // host helper: offsets[n] for n = 0..n_max (offsets may be NULL to query the total only);
+    // cell 0 of the pool is a null table (always k = 0) used for the remainder category
     long long off = 0;
     for (int n = 0; n <= n_max; ++n) {
         if (offsets) offsets[n] = (int32_t)off;
+        if (n == 0) off = 1;
         if (n >= 1) {
             int klo, len;
             poisson_range((double)n, &klo, &len);
@@ -476,11 +498,12 @@ MM_EXPORT int mm_poisson_table_size(int32_t n_max, int32_t* offsets, int64_t* to
 }
 
 MM_EXPORT int mm_poisson_tables(int device, void* stream, int32_t n_max, const int32_t* offsets_dev,
-                                uint32_t* pool) {
+                                void* pool, double* scratch_p, int32_t* scratch_a, int32_t* scratch_b) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_max >= 1 && n_max <= 32767, "n_max must be in 1..32767");
-    MM_REQUIRE(offsets_dev && pool, "null pointer");
-    poisson_tables_kernel<<<(n_max + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_max, offsets_dev, pool);
+    MM_REQUIRE(offsets_dev && pool && scratch_p && scratch_a && scratch_b, "null pointer");
+    poisson_tables_kernel<<<(n_max + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n_max, offsets_dev, (uint2*)pool,
+                                                                           scratch_p, scratch_a, scratch_b);
     return check_launch("mm_poisson_tables");
 }
 
@@ -508,7 +531,7 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
                               int64_t seg_lo, int64_t n_seg, int32_t R, const int32_t* seg_U,
                               const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                               int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
-                              const void* seg_info, const uint32_t* tab_pool, const uint32_t* acc_pool,
+                              const void* seg_info, const void* tab_pool, const uint32_t* acc_pool,
                               double* out_mean, double* out_rv) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_seg >= 0 && R > 0 && num_boot > 0, "n_seg/R/num_boot");
@@ -521,8 +544,10 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     P.n_seg = n_seg; P.R = R; P.seg_U = seg_U; P.seg_skip = seg_skip; P.group_ncells = group_ncells;
     P.mv_fit = mv_fit; P.estimator = estimator; P.B = num_boot; P.seed = seed;
     P.gene_id = (const long long*)gene_id; P.out_mean = out_mean; P.out_rv = out_rv;
-    P.info = (const SegInfo*)seg_info; P.tab_pool = tab_pool; P.acc_pool = acc_pool;
-    P.reps_per_block = kBootThreads * 16;
+    P.info = (const SegInfo*)seg_info; P.tab_pool = (const uint2*)tab_pool; P.acc_pool = acc_pool;
+    // a block covers 20 replicates per lane of one segment; lanes claim replicates from a shared counter,
+    // so rejections do not leave lanes idle at the end of the range
+    P.reps_per_block = kBootThreads * 20;
     MM_REQUIRE(!seg_info || (tab_pool && acc_pool), "seg_info needs tab_pool and acc_pool");
     dim3 grid((num_boot + kBootThreads - 1) / kBootThreads, (unsigned)n_seg);
     bootstrap_1d_kernel<<<grid, kBootThreads, 0, (cudaStream_t)stream>>>(P);

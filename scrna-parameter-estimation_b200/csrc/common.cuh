@@ -108,6 +108,12 @@ struct Philox {
         }
         return c;
     }
+    // four fresh words (does not touch the word buffer of next())
+    __device__ __forceinline__ uint4 block() {
+        uint4 o = round10(ctr, key0, key1);
+        ctr.z += 1;
+        return o;
+    }
     __device__ __forceinline__ uint32_t next() {
         if (have == 0) {
             out = round10(ctr, key0, key1);

@@ -16,14 +16,18 @@ _TABLES = {}             # per device: (offsets tensor, pool tensor)
 
 
 def poisson_tables(device):
-    """Universal 32-bit inversion tables of Poisson(n), n = 1..N_TABLE_MAX, built once per device by
-    mm_poisson_tables (73 MB, shared by every segment of every call)."""
+    """Universal alias tables of Poisson(n), n = 1..N_TABLE_MAX, built once per device by
+    mm_poisson_tables (146 MB of 8-byte cells, shared by every segment of every call)."""
     key = (device.type, device.index)
     if key not in _TABLES:
         off, total = _lib.poisson_table_offsets(N_TABLE_MAX)
         off_d = torch.as_tensor(off, device=device)
-        pool = torch.empty(total, dtype=torch.int32, device=device)
-        _lib.call("mm_poisson_tables", device, N_TABLE_MAX, off_d, pool)
+        pool = torch.empty(2 * total, dtype=torch.int32, device=device)
+        sp = torch.empty(total, dtype=torch.float64, device=device)
+        sa = torch.empty(total, dtype=torch.int32, device=device)
+        sb = torch.empty(total, dtype=torch.int32, device=device)
+        _lib.call("mm_poisson_tables", device, N_TABLE_MAX, off_d, pool, sp, sa, sb)
+        torch.cuda.synchronize(device)
         _TABLES[key] = (off_d, pool)
     return _TABLES[key]
 
@@ -140,7 +144,7 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
 
 
 def bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip=None, gene_id=None,
-                   sampler="poisson", min_accept=0.4, timer=NULL_TIMER):
+                   sampler="poisson", min_accept=0.2, timer=NULL_TIMER):
     """mm_boot_prepare (Poissonised sampler only) + mm_bootstrap_1d on the unique tables ``tab`` of a
     gene tile.  Returns (raw_mean, raw_rv, seg_info) device tensors; raw_* are [n_seg * num_boot]."""
     dev = seg.device
@@ -173,7 +177,7 @@ def segment_modes(seg_info, n_seg):
 
 def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,
                estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None, gene_id=None,
-               sampler="poisson", min_accept=0.4):
+               sampler="poisson", min_accept=0.2):
     """One tile of genes through the whole test.  true_mean / true_rv: (n_genes, R) host arrays;
     gene_id: int64 device vector of the tile's global gene ids (RNG stream ids)."""
     dev = seg.device

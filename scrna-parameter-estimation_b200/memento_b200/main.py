@@ -423,7 +423,8 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         res = engine.ht_1d_tile(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
                                 cov, tr_all, num_boot, estimator, seed, approx, one_sample,
                                 want_coef_rows=not approx, timer=st.timer, stats=stats_acc,
-                                gene_id=gene_id[lo:lo + n], sampler=sampler)
+                                gene_id=gene_id[lo:lo + n], sampler=sampler,
+                                min_accept=getattr(st, "min_accept", 0.2))
         if not approx:
             gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
         for k in out:

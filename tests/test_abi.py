@@ -63,7 +63,7 @@ def test_poisson_table_offsets_host_helper():
     """Host-only entry point (no GPU needed): table k-ranges must hold all but ~2^-32 of the mass."""
     import scipy.stats as st
     off, total = _lib.poisson_table_offsets(64)
-    assert off[0] == 0 and off[1] == 0 and total > off[64] > off[63]
+    assert off[0] == 0 and off[1] == 1 and total > off[64] > off[63]
     for n in (1, 7, 64):
         length = (off[n + 1] if n < 64 else total) - off[n]
         hi = int(np.floor(n)) + int(np.ceil(7.5 + np.sqrt(44.4 * n + 56.0)))
