@@ -15,14 +15,15 @@
 // and penalty (100 * log(DBL_MAX) per point outside the support); the KS decision uses the exact
 // critical values D_0.05(n) = scipy.stats.kstwo.isf(0.05, n) tabulated below for the nine tail sizes.
 //
-// One CTA per flagged test: the null is sorted by a shared-memory bitonic sort, then the 18
-// (side, tail size) fits run one per warp, each warp evaluating the likelihood with a shuffle reduction.
+// One 2-warp CTA per flagged test: the null is sorted by a shared-memory bitonic sort, then warp 0
+// walks the left-tail ladder and warp 1 the right-tail ladder, each evaluating the likelihood with a
+// shuffle reduction.
 #include "common.cuh"
 #include <float.h>
 
 namespace mm {
 
-constexpr int kGevThreads = 256;
+constexpr int kGevThreads = 64;    // two warps per test: left tail, right tail
 constexpr int kLadder = 9;
 __constant__ int c_tail_n[kLadder] = {300, 270, 240, 210, 180, 150, 120, 90, 60};
 // scipy.stats.kstwo.isf(0.05, n) for n in c_tail_n (scipy 1.18.1)
@@ -247,12 +248,12 @@ gev_tail_kernel(GevParams P) {
         if (tid == 0) P.status[blockIdx.x] = 0;
         return;
     }
-    // tasks t = 0..17: ladder index t / 2, side t % 2 (0 = left tail, 1 = right tail); one warp each
-    for (int round = 0; round < 3; ++round) {
-        int t = round * 8 + warp;
-        if (t < 2 * kLadder) {
-            int li = t >> 1, side = t & 1;
-            int ne = c_tail_n[li];
+    // warp 0 walks the ladder of the left tail, warp 1 that of the right tail, each until a tail size
+    // passes the KS check or a fit fails (no speculative fits)
+    {
+        const int side = warp;
+        for (int li = 0; li < kLadder; ++li) {
+            const int ne = c_tail_n[li];
             const double* x = side == 0 ? s_null : s_null + (n - ne);
             double th[3];
             int state;
@@ -267,22 +268,10 @@ gev_tail_kernel(GevParams P) {
                 } else state = 2;
             }
             if (lane == 0) { s_state[side][li] = state; s_val[side][li] = val; }
+            if (state != 2) break;
         }
-        __syncthreads();
-        // both sides decided within the evaluated prefix?
-        bool decided = true;
-        for (int side = 0; side < 2; ++side) {
-            bool dec = false;
-            for (int li = 0; li < kLadder; ++li) {
-                int s = s_state[side][li];
-                if (s == 0) break;
-                if (s == 1 || s == 3) { dec = true; break; }
-            }
-            int last = s_state[side][kLadder - 1];
-            decided = decided && (dec || last != 0);
-        }
-        if (decided) break;
     }
+    __syncthreads();
     if (tid == 0) {
         double total = 0.0;
         bool ok = true;
