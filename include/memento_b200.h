@@ -131,12 +131,30 @@ int mm_fill_log(int device, void* stream, const double* raw_mean, const double* 
  * with coef[t] = sum_r C[t,r] * y[r] equal to "residualise y and treatment on [1, covariate] with
  * weights, then weighted marginal slope".  covariate [R][n_cov], treatment [R][T], weights [R],
  * masks [n_mask][R]; scratch [n_mask][R][n_cov+T]; cmat [n_mask][T][R].  one_sample != 0: weighted
- * average over groups.
+ * average over groups.  znorm2 (nullable) [n_mask][n_cov]: squared weighted norms of the orthogonalised
+ * covariate directions left in scratch (0 = dropped as linearly dependent).
  * Replaces: memento/hypothesis_test.py:262-271 (three sklearn LinearRegression fits per gene) and
  * :218-228 (_cross_coef). */
 int mm_wls_functional(int device, void* stream, const double* covariate, const double* treatment,
                       const double* weights, const uint8_t* masks, int32_t R, int32_t n_cov,
-                      int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat);
+                      int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat,
+                      double* znorm2);
+
+/* resample_rep=True: hierarchical bootstrap over replicates.  boot0 / boot1 are residualised IN PLACE
+ * on [1, covariate]; zmat / znorm2 = scratch / znorm2 of mm_wls_functional (orthogonalised covariate
+ * directions and residualised treatment per validity mask).  Output column 0 is the observed
+ * coefficient, columns 1..num_boot-1 draw a random valid group and a random replicate per group
+ * slot (Philox, or rep_assign / iter_assign [n_gene][R][num_boot] in replay mode, indices into the
+ * gene's list of valid groups resp. 1..num_boot).  coef_ws (nullable): [n_gene][n_stat][T][num_boot].
+ * bad_flag is set when a non-finite bootstrap column is met (the caller raises).
+ * Replaces: memento/hypothesis_test.py:231-239 (_cross_coef_resampled), :273-286. */
+int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
+                         const uint8_t* seg_good, const int32_t* mask_id, const double* zmat,
+                         const double* znorm2, const double* weights, int32_t n_gene, int32_t R,
+                         int32_t n_cov, int32_t T, int32_t num_boot, int32_t approx, uint64_t seed,
+                         const int64_t* gene_id, const int32_t* rep_assign, const int32_t* iter_assign,
+                         double* coef_ws, double* out_coef, double* out_se, double* out_asl,
+                         int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag);
 
 /* Per gene: coefficient of every bootstrap column, SE (population std of columns 1..), and the ASL:
  * approx != 0 -> two-sided normal tail; else extreme count c and (c+1)/(n+1) (out_extreme carries c

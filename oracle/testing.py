@@ -133,7 +133,7 @@ def _replicate_assignment(num_rep, num_boot):
     return rep, it
 
 
-def regress(covariate, treatment, boots, n_cells, resample_rep=False, **asl_kwargs):
+def regress(covariate, treatment, boots, n_cells, resample_rep=False, record=None, **asl_kwargs):
     """Shared body of ``_regress_1d`` / ``_regress_2d``.  ``boots`` is a list of (R x (B+1))
     arrays (1D: [log mean, log res-var]; 2D: [corr]).  Returns one (coef0, se, asl) triple per
     array, or None when every bootstrap column was dropped.
@@ -153,6 +153,8 @@ def regress(covariate, treatment, boots, n_cells, resample_rep=False, **asl_kwar
         t_tilde = _residualise(covariate, treatment, n_cells)
         if resample_rep:
             rep, it = _replicate_assignment(num_rep, num_boot)
+            if record is not None:
+                record["rep_assign"], record["iter_assign"] = rep, it
             t_res = t_tilde[rep]
             w_res = n_cells[rep]
             coefs = [cross_coef_resampled(t_res, bt[(rep, it)], w_res) for bt in tildes]
@@ -201,8 +203,11 @@ def ht_1d_gene(true_mean, true_res_var, cells, approx_sf, covariate, treatment, 
         return good, boot_mean, boot_var
     if good.sum() == 0:
         return (np.nan,) * 6
+    reg_record = {} if recorder is not None else None
     res = regress(covariate[good, :], treatment[good, :], [boot_mean[good, :], boot_var[good, :]],
-                  n_cells[good], **kwargs)
+                  n_cells[good], record=reg_record, **kwargs)
+    if recorder is not None and reg_record:
+        recorder.append({"group": -1, **reg_record})
     if res is None:
         # the reference returns a 5-list here and its caller then fails to unpack 6 values
         # (hypothesis_test.py:260, main.py:403); the oracle reports all-NaN instead.

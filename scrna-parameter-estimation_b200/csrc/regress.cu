@@ -128,6 +128,8 @@ struct WlsParams {
     int one_sample;             // treatment is all ones: weighted average over groups
     double* scratch;            // [n_mask][R][Pc + T]
     double* cmat;               // [n_mask][T][R]
+    double* znorm2;             // optional [n_mask][Pc]: squared W-norms of the orthogonalised covariate
+                                // directions left in scratch (0 for dropped columns)
 };
 
 __device__ double block_sum(double v, double* sred) {
@@ -187,7 +189,9 @@ wls_functional_kernel(WlsParams P) {
         double nrm2 = block_sum(s, sred);
         double ref2 = block_sum(s0, sred);
         // numerically dependent column (e.g. an explicit intercept, or a dummy emptied by the mask)
-        if (!(nrm2 > 1e-20 * (ref2 > 0.0 ? ref2 : 1.0))) continue;
+        const bool dropped = !(nrm2 > 1e-20 * (ref2 > 0.0 ? ref2 : 1.0));
+        if (P.znorm2 && tid == 0) P.znorm2[(long long)k * Pc + c] = dropped ? 0.0 : nrm2;
+        if (dropped) continue;
         for (int c2 = c + 1; c2 < K; ++c2) {
             double d = 0.0;
             for (int r = tid; r < R; r += kRegThreads)
@@ -382,6 +386,157 @@ regress_asl_kernel(RegParams P) {
     }
 }
 
+// ------------------------------------------------------------------ hierarchical replicate bootstrap
+// resample_rep=True (reference hypothesis_test.py:231-239, :273-286): residualise the bootstrap rows
+// on [1, covariate] (in place), then for every output column j draw, for each valid group slot, a
+// random valid group and a random bootstrap replicate (column 0 = identity / observed), and take the
+// weighted marginal slope of the gathered residuals on the gathered residualised treatment.
+struct ResampParams {
+    double* boot[2];            // [n_gene][R][B+1]; overwritten by the residualised rows
+    int n_stat;
+    const unsigned char* seg_good;  // [n_gene][R]
+    const int* mask_id;         // [n_gene]
+    const double* zmat;         // wls scratch: [n_mask][R][Pc + T]
+    const double* znorm2;       // [n_mask][Pc]
+    const double* weights;      // [R]
+    int R, Pc, T, B;
+    int approx;
+    unsigned long long seed;
+    const long long* gene_id;   // [n_gene] nullable
+    const int* rep_assign;      // replay: [n_gene][R][B] compressed valid-group index, nullable
+    const int* iter_assign;     // replay: [n_gene][R][B] replicate index (1..B; column 0 ignored), nullable
+    double* coef_ws;            // optional [n_gene][n_stat][T][B]
+    double* out_coef; double* out_se; double* out_asl;   // [n_gene][n_stat][T]
+    int* out_extreme; int* out_nnull;
+    int* bad_flag;              // set to 1 if a non-finite bootstrap column is met (not supported here)
+};
+
+__global__ void __launch_bounds__(kRegThreads)
+regress_resampled_kernel(ResampParams P) {
+    extern __shared__ int s_good[];                   // R ints: list of valid groups
+    __shared__ double sred[kRegThreads / 32];
+    __shared__ int s_ngood;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int R = P.R, Pc = P.Pc, T = P.T, B = P.B, B1 = B + 1, K = Pc + T, NS = P.n_stat;
+    const unsigned char* good = P.seg_good + (long long)g * R;
+    const double* Z = P.zmat + (long long)P.mask_id[g] * R * K;
+    const double* zn = P.znorm2 + (long long)P.mask_id[g] * Pc;
+    if (tid == 0) {
+        int n = 0;
+        for (int r = 0; r < R; ++r) if (good[r]) s_good[n++] = r;
+        s_ngood = n;
+    }
+    __syncthreads();
+    const int ng = s_ngood;
+    const long long obase = (long long)g * NS * T;
+    if (ng == 0) {
+        for (int i = tid; i < NS * T; i += kRegThreads) {
+            P.out_coef[obase + i] = nan(""); P.out_se[obase + i] = nan(""); P.out_asl[obase + i] = nan("");
+            P.out_extreme[obase + i] = -1; P.out_nnull[obase + i] = 0;
+        }
+        return;
+    }
+    double wsum = 0.0;
+    for (int i = 0; i < ng; ++i) wsum += P.weights[s_good[i]];
+    // ---- phase 1: residualise every column of every statistic in place
+    for (int s = 0; s < NS; ++s) {
+        double* bt = P.boot[s] + (long long)g * R * B1;
+        for (int b = tid; b < B1; b += kRegThreads) {
+            double mu = 0.0;
+            bool finite = true;
+            for (int i = 0; i < ng; ++i) {
+                int r = s_good[i];
+                double y = bt[(long long)r * B1 + b];
+                finite = finite && isfinite(y);
+                mu += P.weights[r] * y;
+            }
+            if (!finite) *P.bad_flag = 1;
+            mu /= wsum;
+            for (int i = 0; i < ng; ++i) { int r = s_good[i]; bt[(long long)r * B1 + b] -= mu; }
+            for (int c = 0; c < Pc; ++c) {
+                if (!(zn[c] > 0.0)) continue;
+                double d = 0.0;
+                for (int i = 0; i < ng; ++i) {
+                    int r = s_good[i];
+                    d += P.weights[r] * Z[(long long)r * K + c] * bt[(long long)r * B1 + b];
+                }
+                d /= zn[c];
+                for (int i = 0; i < ng; ++i) { int r = s_good[i]; bt[(long long)r * B1 + b] -= d * Z[(long long)r * K + c]; }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: resampled slopes, one (statistic, treatment column) at a time
+    const long long sid_base = (P.gene_id ? P.gene_id[g] : (long long)g) * R;
+    auto slope = [&](const double* bt, int t, int j) {
+        double sw = 0, swa = 0, swy = 0, swaa = 0, sway = 0;
+        for (int i = 0; i < ng; ++i) {
+            int ra, bi;
+            if (j == 0) { ra = i; bi = 0; }
+            else if (P.rep_assign) {
+                ra = P.rep_assign[((long long)g * R + i) * B + j];
+                bi = P.iter_assign[((long long)g * R + i) * B + j];
+            } else {
+                Philox rng;
+                long long sid = sid_base + i;
+                rng.init(P.seed, (uint32_t)j, (uint32_t)sid, (uint32_t)(sid >> 32), 0x4E5Au);
+                uint4 r4 = rng.block();
+                ra = (int)(((unsigned long long)r4.x * (unsigned)ng) >> 32);
+                bi = 1 + (int)(((unsigned long long)r4.y * (unsigned)B) >> 32);
+            }
+            int r = s_good[ra];
+            double w = P.weights[r], a = Z[(long long)r * K + Pc + t], y = bt[(long long)r * B1 + bi];
+            sw += w; swa += w * a; swy += w * y; swaa += w * a * a; sway += w * a * y;
+        }
+        double saa = swaa - swa * swa / sw, say = sway - swa * swy / sw;
+        return say / saa;
+    };
+    for (int s = 0; s < NS; ++s) {
+        const double* bt = P.boot[s] + (long long)g * R * B1;
+        for (int t = 0; t < T; ++t) {
+            const double stat = slope(bt, t, 0);
+            const double astat = fabs(stat);
+            double sum = 0, sq = 0, vmin = INFINITY, vmax = -INFINITY;
+            int hi = 0, lo = 0;
+            for (int j = tid; j < B; j += kRegThreads) {
+                double c = (j == 0) ? stat : slope(bt, t, j);
+                if (P.coef_ws) P.coef_ws[(((long long)g * NS + s) * T + t) * B + j] = c;
+                vmin = fmin(vmin, c); vmax = fmax(vmax, c);
+                if (j > 0) { double d = c - stat; sum += d; sq = fma(d, d, sq); hi += (d > astat); lo += (d < -astat); }
+            }
+            sum = block_sum(sum, sred);
+            sq = block_sum(sq, sred);
+            int ext = (int)(block_sum((double)(hi + lo), sred) + 0.5);
+            // min / max through warp shuffles + shared memory
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, o));
+                vmax = fmax(vmax, __shfl_xor_sync(kFull, vmax, o));
+            }
+            __shared__ double s_mn[kRegThreads / 32], s_mx[kRegThreads / 32];
+            if ((tid & 31) == 0) { s_mn[tid >> 5] = vmin; s_mx[tid >> 5] = vmax; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < kRegThreads / 32; ++w) { vmin = fmin(vmin, s_mn[w]); vmax = fmax(vmax, s_mx[w]); }
+                const int n = B - 1;
+                double mu = sum / n, var = sq / n - mu * mu;
+                if (var < 0) var = 0;
+                double sd = sqrt(var), asl;
+                int extreme = -1;
+                if (!(vmin < vmax)) asl = nan("");
+                else if (P.approx) {
+                    double k2 = 1.0 / (sd * 1.4142135623730951);
+                    asl = 0.5 * erfc((astat - mu) * k2) + 0.5 * erfc((astat + mu) * k2);
+                } else { extreme = ext; asl = (double)(ext + 1) / (double)(n + 1); }
+                const long long o = obase + (long long)s * T + t;
+                P.out_coef[o] = stat; P.out_se[o] = sd; P.out_asl[o] = asl;
+                P.out_extreme[o] = extreme; P.out_nnull[o] = n;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace mm
 
 using namespace mm;
@@ -408,7 +563,8 @@ MM_EXPORT int mm_fill_log(int device, void* stream, const double* raw_mean, cons
 
 MM_EXPORT int mm_wls_functional(int device, void* stream, const double* covariate, const double* treatment,
                                 const double* weights, const uint8_t* masks, int32_t R, int32_t n_cov,
-                                int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat) {
+                                int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat,
+                                double* znorm2) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(R > 0 && n_cov >= 0 && T > 0 && n_mask >= 0, "R/n_cov/T/n_mask");
     if (n_mask == 0) return 0;
@@ -416,7 +572,7 @@ MM_EXPORT int mm_wls_functional(int device, void* stream, const double* covariat
     WlsParams P;
     P.covariate = covariate; P.treatment = treatment; P.weights = weights; P.masks = masks;
     P.R = R; P.Pc = n_cov; P.T = T; P.n_mask = n_mask; P.one_sample = one_sample;
-    P.scratch = scratch; P.cmat = cmat;
+    P.scratch = scratch; P.cmat = cmat; P.znorm2 = znorm2;
     wls_functional_kernel<<<n_mask, kRegThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_wls_functional");
 }
@@ -438,4 +594,31 @@ MM_EXPORT int mm_regress_asl(int device, void* stream, const double* boot0, cons
     P.out_nnull = out_nnull;
     regress_asl_kernel<<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_regress_asl");
+}
+
+MM_EXPORT int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
+                                   const uint8_t* seg_good, const int32_t* mask_id, const double* zmat,
+                                   const double* znorm2, const double* weights, int32_t n_gene, int32_t R,
+                                   int32_t n_cov, int32_t T, int32_t num_boot, int32_t approx, uint64_t seed,
+                                   const int64_t* gene_id, const int32_t* rep_assign, const int32_t* iter_assign,
+                                   double* coef_ws, double* out_coef, double* out_se, double* out_asl,
+                                   int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(n_gene >= 0 && R > 0 && T > 0 && num_boot > 1 && n_cov >= 0, "n_gene/R/T/num_boot/n_cov");
+    if (n_gene == 0) return 0;
+    MM_REQUIRE(boot0 && seg_good && mask_id && zmat && (znorm2 || n_cov == 0) && weights && out_coef && out_se &&
+               out_asl && out_extreme && out_nnull && bad_flag, "null pointer");
+    MM_REQUIRE((rep_assign == nullptr) == (iter_assign == nullptr), "rep_assign and iter_assign go together");
+    MM_REQUIRE((size_t)R * sizeof(int) <= 200 * 1024, "too many groups for the shared valid-group list");
+    ResampParams P;
+    P.boot[0] = boot0; P.boot[1] = boot1; P.n_stat = boot1 ? 2 : 1; P.seg_good = seg_good; P.mask_id = mask_id;
+    P.zmat = zmat; P.znorm2 = znorm2; P.weights = weights; P.R = R; P.Pc = n_cov; P.T = T; P.B = num_boot;
+    P.approx = approx; P.seed = seed; P.gene_id = (const long long*)gene_id; P.rep_assign = rep_assign;
+    P.iter_assign = iter_assign; P.coef_ws = coef_ws; P.out_coef = out_coef; P.out_se = out_se; P.out_asl = out_asl;
+    P.out_extreme = out_extreme; P.out_nnull = out_nnull; P.bad_flag = bad_flag;
+    size_t smem = (size_t)R * sizeof(int);
+    if (smem > 48 * 1024)
+        MM_CUDA(cudaFuncSetAttribute(regress_resampled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    regress_resampled_kernel<<<n_gene, kRegThreads, smem, (cudaStream_t)stream>>>(P);
+    return check_launch("mm_regress_resampled");
 }

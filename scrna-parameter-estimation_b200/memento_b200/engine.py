@@ -97,8 +97,9 @@ def unique_bytes(tab, n_cells):
     return tab["nnz"] * 8 + n_cells * 1 + (tab["n_seg"] + 1) * 8 + total_U * ENTRY_BYTES + tab["n_seg"] * 4
 
 
-def wls_functional(device, covariate, treatment, weights, masks, one_sample, timer=NULL_TIMER):
-    """masks: (n_mask, R) uint8 numpy.  Returns cmat (n_mask, T, R) on the device."""
+def wls_functional(device, covariate, treatment, weights, masks, one_sample, timer=NULL_TIMER, want_basis=False):
+    """masks: (n_mask, R) uint8 numpy.  Returns cmat (n_mask, T, R) on the device; with ``want_basis``
+    also the orthogonalised design (n_mask, R, P + T) and the squared norms (n_mask, P)."""
     R, P = covariate.shape
     T = treatment.shape[1]
     n_mask = masks.shape[0]
@@ -108,22 +109,31 @@ def wls_functional(device, covariate, treatment, weights, masks, one_sample, tim
     m_d = torch.as_tensor(np.ascontiguousarray(masks, dtype=np.uint8), device=device)
     scratch = torch.empty(max(1, n_mask * R * (P + T)), dtype=torch.float64, device=device)
     cmat = torch.empty(n_mask * T * R, dtype=torch.float64, device=device)
+    znorm2 = torch.zeros(max(1, n_mask * P), dtype=torch.float64, device=device) if want_basis else None
     ev = timer.start()
     _lib.call("mm_wls_functional", device, cov_d if P > 0 else None, tr_d, w_d, m_d, R, P, T, n_mask,
-              1 if one_sample else 0, scratch, cmat)
+              1 if one_sample else 0, scratch, cmat, znorm2)
     timer.stop("wls_functional", ev)
+    if want_basis:
+        return cmat.view(n_mask, T, R), scratch, znorm2, w_d
     return cmat.view(n_mask, T, R)
 
 
 def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, treatment, weights, one_sample,
-                 approx, want_coef_rows, timer=NULL_TIMER):
+                 approx, want_coef_rows, timer=NULL_TIMER, resample_rep=False, seed=0, gene_id=None,
+                 assignments=None):
     """Shared tail of the 1D and 2D tests for one tile.  boot*: (n_gene*R, B+1) device tensors,
     seg_good: (n_gene*R,) uint8 device.  Returns dict of host arrays (n_gene, n_stat, T) + coef rows."""
     n_gene = seg_good.numel() // R
     n_stat = 2 if boot1 is not None else 1
     good_h = seg_good.view(n_gene, R).cpu().numpy()
     masks, inverse = np.unique(good_h, axis=0, return_inverse=True)
-    cmat = wls_functional(device, covariate, treatment, weights, masks, one_sample, timer)
+    use_resampled = resample_rep and not one_sample      # reference: the one-sample branch ignores it
+    if use_resampled:
+        cmat, zmat, znorm2, w_d = wls_functional(device, covariate, treatment, weights, masks, one_sample, timer,
+                                                 want_basis=True)
+    else:
+        cmat = wls_functional(device, covariate, treatment, weights, masks, one_sample, timer)
     mask_id = torch.as_tensor(np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32), device=device)
     n_out = n_gene * n_stat * T
     out_coef = torch.empty(n_out, dtype=torch.float64, device=device)
@@ -131,15 +141,29 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
     out_asl = torch.empty(n_out, dtype=torch.float64, device=device)
     out_ext = torch.empty(n_out, dtype=torch.int32, device=device)
     out_nn = torch.empty(n_out, dtype=torch.int32, device=device)
-    coef_ws = torch.empty(n_out * (num_boot + 1), dtype=torch.float64, device=device) if want_coef_rows else None
+    n_cols = num_boot if use_resampled else num_boot + 1
+    coef_ws = torch.empty(n_out * n_cols, dtype=torch.float64, device=device) if want_coef_rows else None
     ev = timer.start()
-    _lib.call("mm_regress_asl", device, boot0, boot1, seg_good, mask_id, cmat, n_gene, R, T, num_boot,
-              1 if approx else 0, coef_ws, out_coef, out_se, out_asl, out_ext, out_nn)
+    if use_resampled:
+        bad = torch.zeros(1, dtype=torch.int32, device=device)
+        rep_a = it_a = None
+        if assignments is not None:
+            rep_a = torch.as_tensor(np.ascontiguousarray(assignments[0], dtype=np.int32), device=device)
+            it_a = torch.as_tensor(np.ascontiguousarray(assignments[1], dtype=np.int32), device=device)
+        _lib.call("mm_regress_resampled", device, boot0, boot1, seg_good, mask_id, zmat, znorm2, w_d, n_gene, R,
+                  covariate.shape[1], T, num_boot, 1 if approx else 0, seed, gene_id, rep_a, it_a, coef_ws,
+                  out_coef, out_se, out_asl, out_ext, out_nn, bad)
+        if int(bad.item()) != 0:
+            raise _lib.MementoCudaError("resample_rep: a bootstrap column is non-finite in a valid group; the "
+                                        "device path does not drop columns in this mode")
+    else:
+        _lib.call("mm_regress_asl", device, boot0, boot1, seg_good, mask_id, cmat, n_gene, R, T, num_boot,
+                  1 if approx else 0, coef_ws, out_coef, out_se, out_asl, out_ext, out_nn)
     timer.stop("regress_asl", ev)
     shp = (n_gene, n_stat, T)
     return {"coef": out_coef.view(shp), "se": out_se.view(shp), "asl": out_asl.view(shp),
             "extreme": out_ext.view(shp), "n_null": out_nn.view(shp),
-            "coef_rows": coef_ws.view(n_gene, n_stat, T, num_boot + 1) if want_coef_rows else None,
+            "coef_rows": coef_ws.view(n_gene, n_stat, T, n_cols) if want_coef_rows else None,
             "n_masks": masks.shape[0]}
 
 
@@ -177,7 +201,7 @@ def segment_modes(seg_info, n_seg):
 
 def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,
                estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None, gene_id=None,
-               sampler="poisson", min_accept=0.2):
+               sampler="poisson", min_accept=0.2, resample_rep=False):
     """One tile of genes through the whole test.  true_mean / true_rv: (n_genes, R) host arrays;
     gene_id: int64 device vector of the tile's global gene ids (RNG stream ids)."""
     dev = seg.device
@@ -213,7 +237,8 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
     timer.stop("fill_log", ev)
     del raw_mean, raw_rv
     res = regress_tile(dev, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
-                       design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer)
+                       design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer,
+                       resample_rep=resample_rep, seed=seed, gene_id=gene_id)
     if stats is not None:
         # unique x2 (+memset), prepare, bootstrap x2, fill, wls, regress
         stats["launches"] = stats.get("launches", 0) + (9 if sampler == "poisson" else 7)
@@ -221,7 +246,7 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
 
 
 def ht_1d_replay(device, R, replay, design_host, true_mean, true_rv, covariate, treatment, num_boot, estimator,
-                 approx, one_sample, want_coef_rows, timer=NULL_TIMER):
+                 approx, one_sample, want_coef_rows, timer=NULL_TIMER, resample_rep=False):
     """Deterministic parity mode: host-supplied unique tables, resample counts and imputation
     sources (``replay`` dict: tab_ptr, x, inv_sf, W, src_mean, src_rv) instead of the compression
     and RNG kernels; the moment, imputation/log, WLS and regression kernels are the product ones.
@@ -256,12 +281,14 @@ def ht_1d_replay(device, R, replay, design_host, true_mean, true_rv, covariate, 
     _lib.call("mm_fill_log", device, raw_mean, raw_rv, seg_ok, d(true_mean.reshape(-1), np.float64),
               d(true_rv.reshape(-1), np.float64), src_m, src_v, None, R, n_seg, num_boot, 0, boot_mean, boot_var,
               seg_good, n_valid)
+    res_keep = {"boot_mean": boot_mean.clone().view(n_seg, num_boot + 1), "boot_var": boot_var.clone().view(n_seg, num_boot + 1)}
+    assign = (replay["rep_assign"], replay["iter_assign"]) if (resample_rep and replay.get("rep_assign") is not None) else None
     res = regress_tile(device, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
-                       np.asarray(design_host["n_cells"], dtype=np.float64), one_sample, approx, want_coef_rows, timer)
+                       np.asarray(design_host["n_cells"], dtype=np.float64), one_sample, approx, want_coef_rows, timer,
+                       resample_rep=resample_rep, assignments=assign)
     res["raw_mean"] = raw_mean.view(n_seg, num_boot)
     res["raw_var"] = raw_var.view(n_seg, num_boot)
     res["raw_rv"] = raw_rv.view(n_seg, num_boot)
-    res["boot_mean"] = boot_mean.view(n_seg, num_boot + 1)
-    res["boot_var"] = boot_var.view(n_seg, num_boot + 1)
+    res.update(res_keep)
     res["seg_good"] = seg_good
     return res

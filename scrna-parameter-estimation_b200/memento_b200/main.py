@@ -384,8 +384,6 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
     if resampling != "bootstrap":
         raise NotImplementedError("only resampling='bootstrap' is implemented on the device path")
-    if resample_rep:
-        raise NotImplementedError("resample_rep=True is not implemented on the device path yet")
     mem = adata.uns["memento"]
     st = _state(adata)
     st.ensure_resident()
@@ -410,7 +408,8 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         dh = {"n_cells": np.diff(st.group_start), "q": [mem["group_q"][g] for g in groups],
               "mv_fit": np.stack([mem["mv_regressor"][g] for g in groups])}
         res = engine.ht_1d_replay(st.device, R, replay, dh, true_mean, true_rv, cov, tr_all, num_boot, estimator,
-                                  approx, one_sample, want_coef_rows=not approx, timer=st.timer)
+                                  approx, one_sample, want_coef_rows=not approx, timer=st.timer,
+                                  resample_rep=resample_rep)
         if not approx:
             gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
         for k in out:
@@ -424,7 +423,7 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
                                 cov, tr_all, num_boot, estimator, seed, approx, one_sample,
                                 want_coef_rows=not approx, timer=st.timer, stats=stats_acc,
                                 gene_id=gene_id[lo:lo + n], sampler=sampler,
-                                min_accept=getattr(st, "min_accept", 0.2))
+                                min_accept=getattr(st, "min_accept", 0.2), resample_rep=resample_rep)
         if not approx:
             gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
         for k in out:

@@ -188,9 +188,10 @@ def test_bootstrap_replay_vs_reference(st, gpu_prepared):
         assert_close(rv[k], want_rv, 1e-7, what="rv %d" % k)
 
 
-def _replay_spec(oracle_ad, cov, tr, num_boot, seed):
+def _replay_spec(oracle_ad, cov, tr, num_boot, seed, resample_rep=False):
     """Run the oracle's per-gene driver in the reference's order with a recorder, collecting for
-    every (gene, group) the unique table, the PCG64(5) resample counts and the imputation sources."""
+    every (gene, group) the unique table, the PCG64(5) resample counts and the imputation sources
+    (and, with resample_rep, the replicate / iteration assignments drawn in the regression)."""
     omem = oracle_ad.uns["memento"]
     groups = omem["groups"]
     R, G = len(groups), oracle_ad.shape[1]
@@ -198,6 +199,9 @@ def _replay_spec(oracle_ad, cov, tr, num_boot, seed):
     x, w, W, ptr = [], [], [], [0]
     src_m = np.full((G * R, num_boot), -1, dtype=np.int32)
     src_v = np.full((G * R, num_boot), -1, dtype=np.int32)
+    rep_a = np.zeros((G, R, num_boot), dtype=np.int32)
+    it_a = np.ones((G, R, num_boot), dtype=np.int32)
+    extra = dict(resampling="bootstrap", approx=True, resample_rep=True) if resample_rep else {}
     np.random.seed(seed)
     for gene in range(G):
         rec = []
@@ -208,8 +212,12 @@ def _replay_spec(oracle_ad, cov, tr, num_boot, seed):
             approx_sf=[omem["approx_size_factor"][g] for g in groups],
             covariate=cov.values, treatment=tr.values, n_cells=n_cells, num_boot=num_boot,
             mv_fit=[omem["mv_regressor"][g] for g in groups], q=[omem["group_q"][g] for g in groups],
-            weighted_estimator=o_moments.hyper_1d_weighted, return_boot=True, recorder=rec)
+            weighted_estimator=o_moments.hyper_1d_weighted, return_boot=not resample_rep, recorder=rec, **extra)
         by_group = {r["group"]: r for r in rec}
+        if -1 in by_group:
+            ra, ia = by_group[-1]["rep_assign"], by_group[-1]["iter_assign"]
+            rep_a[gene, :ra.shape[0]] = ra
+            it_a[gene, :ia.shape[0]] = ia
         for r in range(R):
             s = gene * R + r
             if r in by_group:
@@ -226,7 +234,8 @@ def _replay_spec(oracle_ad, cov, tr, num_boot, seed):
     cat = lambda L, dt: np.concatenate(L).astype(dt) if L else np.zeros(0, dt)  # noqa: E731
     # sources of -1 are never read by the kernel (entry valid); clamp for safety
     return {"tab_ptr": np.array(ptr), "x": cat(x, np.float64), "inv_sf": cat(w, np.float64),
-            "W": cat(W, np.int64), "src_mean": np.maximum(src_m, 0), "src_rv": np.maximum(src_v, 0)}
+            "W": cat(W, np.int64), "src_mean": np.maximum(src_m, 0), "src_rv": np.maximum(src_v, 0),
+            "rep_assign": rep_a if resample_rep else None, "iter_assign": it_a if resample_rep else None}
 
 
 @pytest.mark.parametrize("variant,kw", [("approx", dict(approx=True)), ("default", dict())])
@@ -455,3 +464,38 @@ def test_rng_ht_1d_default_kwargs_vs_oracle(gpu_prepared, oracle_prepared):
         small = po[ok] < 5e-3                      # these went through the tails in the oracle
         if small.sum() >= 3:
             assert np.median(np.abs(lg[small] - lo[small])) < 0.5, (key, lg[small], lo[small])
+
+
+# ----------------------------------------------------------------------------- resample_rep
+def test_ht_1d_replay_resample_rep_vs_reference(gpu_prepared, oracle_prepared):
+    """Hierarchical replicate bootstrap in replay mode (host-supplied resample counts, imputation
+    sources and replicate / iteration assignments) against the reference's golden output."""
+    ht = load("ht1d.npz")
+    B = int(ht["num_boot"])
+    ad = gpu_prepared.copy()
+    cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+    spec = _replay_spec(oracle_prepared.copy(), cov, tr, B, 2024, resample_rep=True)
+    memento.ht_1d_moments(ad, cov, tr, num_boot=B, resampling="bootstrap", approx=True, resample_rep=True,
+                          replay=spec)
+    res = ad.uns["memento"]["1d_ht"]
+    for key in ["mean_coef", "mean_se", "mean_asl", "var_coef", "var_se", "var_asl"]:
+        assert_close(res[key], ht["resample_rep_%s" % key], 1e-7, atol=1e-11, what=key)
+
+
+def test_rng_resample_rep_vs_oracle(gpu_prepared, oracle_prepared):
+    """RNG mode of the hierarchical bootstrap: same coefficients, SEs and p-values concordant with
+    the oracle's."""
+    ad, oad = gpu_prepared.copy(), oracle_prepared.copy()
+    cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+    B = 1500
+    kw = dict(resampling="bootstrap", approx=True, resample_rep=True)
+    memento.ht_1d_moments(ad, cov, tr, num_boot=B, seed=21, **kw)
+    np.random.seed(4)
+    o_pipe.ht_1d_moments(oad, cov, tr, num_boot=B, num_cpus=1, **kw)
+    g, o = ad.uns["memento"]["1d_ht"], oad.uns["memento"]["1d_ht"]
+    assert_close(g["mean_coef"], o["mean_coef"], 1e-8, atol=1e-12)
+    for key in ("mean", "var"):
+        ok = np.isfinite(g[key + "_se"]) & np.isfinite(o[key + "_se"])
+        assert ok.sum() > 50
+        assert np.median(np.abs(g[key + "_se"][ok] / o[key + "_se"][ok] - 1)) < 0.06
+        assert stats.spearmanr(g[key + "_asl"][ok], o[key + "_asl"][ok]).statistic > 0.95
