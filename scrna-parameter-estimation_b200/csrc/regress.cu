@@ -468,28 +468,52 @@ regress_resampled_kernel(ResampParams P) {
     __syncthreads();
     // ---- phase 2: resampled slopes, one (statistic, treatment column) at a time
     const long long sid_base = (P.gene_id ? P.gene_id[g] : (long long)g) * R;
-    auto slope = [&](const double* bt, int t, int j) {
-        double sw = 0, swa = 0, swy = 0, swaa = 0, sway = 0;
-        for (int i = 0; i < ng; ++i) {
-            int ra, bi;
-            if (j == 0) { ra = i; bi = 0; }
-            else if (P.rep_assign) {
-                ra = P.rep_assign[((long long)g * R + i) * B + j];
-                bi = P.iter_assign[((long long)g * R + i) * B + j];
-            } else {
-                Philox rng;
-                long long sid = sid_base + i;
-                rng.init(P.seed, (uint32_t)j, (uint32_t)sid, (uint32_t)(sid >> 32), 0x4E5Au);
-                uint4 r4 = rng.block();
-                ra = (int)(((unsigned long long)r4.x * (unsigned)ng) >> 32);
-                bi = 1 + (int)(((unsigned long long)r4.y * (unsigned)B) >> 32);
-            }
-            int r = s_good[ra];
-            double w = P.weights[r], a = Z[(long long)r * K + Pc + t], y = bt[(long long)r * B1 + bi];
-            sw += w; swa += w * a; swy += w * y; swaa += w * a * a; sway += w * a * y;
+    // one resampled (group, replicate) pick of slot i in output column j
+    auto pick = [&](int i, int j, int& r, int& bi) {
+        int ra;
+        if (j == 0) { ra = i; bi = 0; }
+        else if (P.rep_assign) {
+            ra = P.rep_assign[((long long)g * R + i) * B + j];
+            bi = P.iter_assign[((long long)g * R + i) * B + j];
+        } else {
+            Philox rng;
+            long long sid = sid_base + i;
+            rng.init(P.seed, (uint32_t)j, (uint32_t)sid, (uint32_t)(sid >> 32), 0x4E5Au);
+            uint4 r4 = rng.block();
+            ra = (int)(((unsigned long long)r4.x * (unsigned)ng) >> 32);
+            bi = 1 + (int)(((unsigned long long)r4.y * (unsigned)B) >> 32);
         }
-        double saa = swaa - swa * swa / sw, say = sway - swa * swy / sw;
-        return say / saa;
+        r = s_good[ra];
+    };
+    // Two passes in the operation order of the reference's numpy expressions (weighted means first,
+    // then centred sums; explicit round-to-nearest mul / add so that no FMA contraction changes the
+    // rounding): columns whose picks all share one treatment value are 0/0-like there and the
+    // closest possible agreement on them needs the same arithmetic.
+    auto slope = [&](const double* bt, int t, int j) {
+        double sw = 0, swa = 0, swy = 0, amin = INFINITY, amax = -INFINITY;
+        for (int i = 0; i < ng; ++i) {
+            int r, bi;
+            pick(i, j, r, bi);
+            double w = P.weights[r], a = Z[(long long)r * K + Pc + t], y = bt[(long long)r * B1 + bi];
+            amin = fmin(amin, a); amax = fmax(amax, a);
+            sw = __dadd_rn(sw, w);
+            swa = __dadd_rn(swa, __dmul_rn(a, w));
+            swy = __dadd_rn(swy, __dmul_rn(y, w));
+        }
+        // every pick has the same treatment value: the slope is 0/0 (the reference gets NaN there
+        // whenever its weighted mean reproduces the common value exactly, and noise otherwise)
+        if (!(amin < amax)) return nan("");
+        const double ma = swa / sw, my = swy / sw;
+        double ss = 0, num = 0;
+        for (int i = 0; i < ng; ++i) {
+            int r, bi;
+            pick(i, j, r, bi);
+            double w = P.weights[r], a = Z[(long long)r * K + Pc + t], y = bt[(long long)r * B1 + bi];
+            double ac = __dadd_rn(a, -ma);
+            ss = __dadd_rn(ss, __dmul_rn(__dmul_rn(ac, ac), w));
+            num = __dadd_rn(num, __dmul_rn(__dmul_rn(ac, w), __dadd_rn(y, -my)));
+        }
+        return num / sw / (ss / sw);
     };
     for (int s = 0; s < NS; ++s) {
         const double* bt = P.boot[s] + (long long)g * R * B1;
@@ -497,16 +521,21 @@ regress_resampled_kernel(ResampParams P) {
             const double stat = slope(bt, t, 0);
             const double astat = fabs(stat);
             double sum = 0, sq = 0, vmin = INFINITY, vmax = -INFINITY;
-            int hi = 0, lo = 0;
+            int hi = 0, lo = 0, cnt = 0;
             for (int j = tid; j < B; j += kRegThreads) {
                 double c = (j == 0) ? stat : slope(bt, t, j);
                 if (P.coef_ws) P.coef_ws[(((long long)g * NS + s) * T + t) * B + j] = c;
+                if (!isfinite(c)) continue;        // degenerate resample (reference: dropped by isfinite / nanstd)
                 vmin = fmin(vmin, c); vmax = fmax(vmax, c);
-                if (j > 0) { double d = c - stat; sum += d; sq = fma(d, d, sq); hi += (d > astat); lo += (d < -astat); }
+                if (j > 0) {
+                    double d = c - stat;
+                    sum += d; sq = fma(d, d, sq); hi += (d > astat); lo += (d < -astat); ++cnt;
+                }
             }
             sum = block_sum(sum, sred);
             sq = block_sum(sq, sred);
             int ext = (int)(block_sum((double)(hi + lo), sred) + 0.5);
+            const int n_fin = (int)(block_sum((double)cnt, sred) + 0.5);
             // min / max through warp shuffles + shared memory
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -518,7 +547,7 @@ regress_resampled_kernel(ResampParams P) {
             __syncthreads();
             if (tid == 0) {
                 for (int w = 1; w < kRegThreads / 32; ++w) { vmin = fmin(vmin, s_mn[w]); vmax = fmax(vmax, s_mx[w]); }
-                const int n = B - 1;
+                const int n = n_fin;
                 double mu = sum / n, var = sq / n - mu * mu;
                 if (var < 0) var = 0;
                 double sd = sqrt(var), asl;
