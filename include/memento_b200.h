@@ -178,6 +178,43 @@ int mm_regress_asl(int device, void* stream, const double* boot0, const double* 
 int mm_gev_tail_asl(int device, void* stream, const double* coef_rows, const int32_t* flagged,
                     int32_t n_flag, int32_t num_boot, double* asl, int32_t* status);
 
+/* ---- 2D (gene pair) bootstrap path.  item = pair * R + group; item_ptr[n_pairs * R + 1] = prefix sums
+ * of (nnz of gene 1 + nnz of gene 2 in the group) = pool offsets of the items' tables.
+ *   mm_pair_unique   : distinct (count_1, count_2, bin) triples of every item -> 64-byte entries
+ *                      {x/sf, y/sf, xy/sf^2, (x^2-(1-q)x)/sf^2, (y^2-(1-q)y)/sf^2, table ref, multiplicity};
+ *                      raw_key = x << 32 | y << 8 | bin, raw_cnt (nullable); item_U = number of triples
+ *                      with a nonzero count; scratch_* = 3 * pool entries (used above 3072 nonzeros).
+ *                      Replaces memento/bootstrap.py:40-71 on a two-column slice (:132).
+ *   mm_pair_prepare  : remainder category, alias-table references and the acceptance table of the
+ *                      Poissonised sampler per item; info = n_items records of 80 bytes (mode -2 =
+ *                      a multiplicity exceeds n_table_max: unsupported, the caller raises).
+ *   mm_pair_bootstrap: correlation replicates.  boot_corr[item][0] = true_corr[item], [1..num_boot] =
+ *                      clip(cov / sqrt(var_1 var_2), -1, 1), with the reference's sentinel rule (invalid
+ *                      variances -> 1).  item_good[item] = 0 for skipped items (NaN row).  <= 65535 items
+ *                      per call.  Replaces memento/bootstrap.py:119-157, estimator.py:214-218, :281-290,
+ *                      hypothesis_test.py:322-351.
+ *   mm_pair_bootstrap_replay : covariance, both variances and the correlation from HOST-SUPPLIED
+ *                      resample counts (tables in the reference's order; W as in mm_bootstrap_1d_replay). */
+int mm_pair_unique(int device, void* stream, const float* vals, const int32_t* rows,
+                   const int64_t* seg_ptr, int32_t R, const int32_t* idx1, const int32_t* idx2,
+                   int64_t n_pairs, const int64_t* item_ptr, const uint8_t* item_skip,
+                   const uint8_t* cell_bin, const double* bin_inv_sf, int32_t n_bins,
+                   const double* group_q, void* entries, uint64_t* raw_key, int32_t* raw_cnt,
+                   int32_t* item_U, uint64_t* scratch_key, int32_t* scratch_cnt);
+int mm_pair_prepare(int device, void* stream, void* entries, const int64_t* item_ptr, int64_t n_items,
+                    int32_t R, const int32_t* item_U, const uint8_t* item_skip,
+                    const int32_t* group_ncells, int32_t n_table_max, const int32_t* tab_off,
+                    const int64_t* acc_slot, int64_t acc_stride, uint32_t* acc_pool, void* info);
+int mm_pair_bootstrap(int device, void* stream, const void* entries, const int64_t* item_ptr,
+                      int64_t n_items, int32_t R, const void* info, const int32_t* group_ncells,
+                      const double* true_corr, const void* tab_pool, const uint32_t* acc_pool,
+                      int32_t num_boot, uint64_t seed, const int64_t* item_id, double* boot_corr,
+                      uint8_t* item_good);
+int mm_pair_bootstrap_replay(int device, void* stream, const double* x, const double* y,
+                             const double* inv_sf, const int64_t* W, const int64_t* tab_ptr,
+                             const int32_t* n_cells, const double* q, int32_t n_tab, int32_t num_boot,
+                             double* out_cov, double* out_var1, double* out_var2, double* out_corr);
+
 #ifdef __cplusplus
 }
 #endif

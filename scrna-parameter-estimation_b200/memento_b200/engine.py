@@ -292,3 +292,81 @@ def ht_1d_replay(device, R, replay, design_host, true_mean, true_rv, covariate, 
     res.update(res_keep)
     res["seg_good"] = seg_good
     return res
+
+
+# ----------------------------------------------------------------------------- 2D (gene pairs)
+PAIR_ENTRY_BYTES = 64
+PAIR_INFO_BYTES = 80
+
+
+def pair_tables(seg, design, cell_bin, idx1, idx2, skip=None, timer=NULL_TIMER, want_raw=False):
+    """mm_pair_unique on the pairs (idx1[k], idx2[k]) (numpy int arrays), all groups."""
+    dev = seg.device
+    R = seg.R
+    n_pairs = int(len(idx1))
+    n_items = n_pairs * R
+    i1 = torch.as_tensor(np.ascontiguousarray(idx1, dtype=np.int32), device=dev)
+    i2 = torch.as_tensor(np.ascontiguousarray(idx2, dtype=np.int32), device=dev)
+    ar = torch.arange(R, device=dev)
+    sa = (i1.long()[:, None] * R + ar[None, :]).reshape(-1)
+    sb = (i2.long()[:, None] * R + ar[None, :]).reshape(-1)
+    ln = (seg.seg_ptr[sa + 1] - seg.seg_ptr[sa]) + (seg.seg_ptr[sb + 1] - seg.seg_ptr[sb])
+    item_ptr = torch.zeros(n_items + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(ln, 0, out=item_ptr[1:])
+    pool = max(int(item_ptr[-1].item()), 1)
+    entries = torch.empty(pool * PAIR_ENTRY_BYTES, dtype=torch.uint8, device=dev)
+    raw_key = torch.empty(pool, dtype=torch.int64, device=dev) if want_raw else None
+    raw_cnt = torch.empty(pool, dtype=torch.int32, device=dev) if want_raw else None
+    item_U = torch.empty(n_items, dtype=torch.int32, device=dev)
+    need_scratch = bool((ln > 3072).any().item())
+    sc_n = 3 * pool if need_scratch else 1
+    sk = torch.empty(sc_n, dtype=torch.int64, device=dev)
+    sc = torch.empty(sc_n, dtype=torch.int32, device=dev)
+    skip_d = torch.as_tensor(np.ascontiguousarray(skip, dtype=np.uint8), device=dev) if skip is not None else None
+    ev = timer.start()
+    _lib.call("mm_pair_unique", dev, seg.vals, seg.rows, seg.seg_ptr, R, i1, i2, n_pairs, item_ptr, skip_d,
+              cell_bin, design.bin_inv_sf, design.n_bins, design.q, entries, raw_key, raw_cnt, item_U, sk, sc)
+    timer.stop("pair_unique", ev)
+    return {"entries": entries, "item_ptr": item_ptr, "item_U": item_U, "raw_key": raw_key, "raw_cnt": raw_cnt,
+            "skip": skip_d, "n_pairs": n_pairs, "n_items": n_items}
+
+
+def ht_2d_tile(seg, design, cell_bin, idx1, idx2, true_corr, covariate, treatment, num_boot, seed, approx,
+               one_sample, want_coef_rows, pair_id=None, timer=NULL_TIMER, stats=None, resample_rep=False):
+    """One tile of gene pairs through the 2D test.  true_corr: (n_pairs, R) host array."""
+    dev = seg.device
+    R = seg.R
+    T = treatment.shape[1]
+    n_pairs = len(idx1)
+    n_items = n_pairs * R
+    with np.errstate(invalid="ignore"):
+        skip = np.isnan(true_corr) | (np.abs(true_corr) == 1)        # reference hypothesis_test.py:325
+    tab = pair_tables(seg, design, cell_bin, idx1, idx2, skip.reshape(-1), timer)
+    tab_off, tab_pool = poisson_tables(dev)
+    acc_pool = torch.empty(max(1, n_pairs * design.acc_stride), dtype=torch.int32, device=dev)
+    info = torch.empty(n_items * PAIR_INFO_BYTES, dtype=torch.uint8, device=dev)
+    ev = timer.start()
+    _lib.call("mm_pair_prepare", dev, tab["entries"], tab["item_ptr"], n_items, R, tab["item_U"], tab["skip"],
+              design.n_cells, N_TABLE_MAX, tab_off, design.acc_slot, design.acc_stride, acc_pool, info)
+    timer.stop("pair_prepare", ev)
+    modes = info.view(n_items, PAIR_INFO_BYTES)[:, :4].contiguous().view(torch.int32).reshape(-1)
+    if bool((modes == -2).any().item()):
+        raise _lib.MementoCudaError("ht_2d: a (pair, group) has a category with more than %d cells; not supported "
+                                    "by the Poissonised 2D sampler yet" % N_TABLE_MAX)
+    tc = torch.as_tensor(np.ascontiguousarray(true_corr.reshape(-1), dtype=np.float64), device=dev)
+    boot = torch.empty(n_items * (num_boot + 1), dtype=torch.float64, device=dev)
+    good = torch.empty(n_items, dtype=torch.uint8, device=dev)
+    item_id = None
+    if pair_id is not None:
+        item_id = (pair_id[:, None] * R + torch.arange(R, device=dev)[None, :]).reshape(-1).contiguous()
+    ev = timer.start()
+    _lib.call("mm_pair_bootstrap", dev, tab["entries"], tab["item_ptr"], n_items, R, info, design.n_cells, tc,
+              tab_pool, acc_pool, num_boot, seed, item_id, boot, good)
+    timer.stop("pair_bootstrap", ev)
+    res = regress_tile(dev, boot, None, good, R, T, num_boot, covariate, treatment,
+                       design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer,
+                       resample_rep=resample_rep, seed=seed, gene_id=pair_id)
+    if stats is not None:
+        stats["launches"] = stats.get("launches", 0) + 5
+        stats["pair_items"] = stats.get("pair_items", 0) + n_items
+    return res

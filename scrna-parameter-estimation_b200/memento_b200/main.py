@@ -497,6 +497,74 @@ def _corr_from_cov(cov, var_1, var_2):
 
 
 def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=True, num_boot=10000,
-                  verbose=3, num_cpus=1, **kwargs):
-    """reference: main.py:418-520.  Not on the device path yet."""
-    raise NotImplementedError("ht_2d_moments is not implemented on the device path yet")
+                  verbose=3, num_cpus=1, seed=0, workspace_bytes=4 << 30, **kwargs):
+    """Hypothesis test for the correlation of the gene pairs of ``compute_2d_moments``.
+    reference: main.py:418-520.  One value per pair (the reference stores a (T,) array into a scalar
+    slot, main.py:509, which only works for one treatment column), unordered duplicates share the
+    result of their first occurrence, i == j pairs stay NaN."""
+    if not inplace:
+        adata = adata.copy()
+    resampling = kwargs.pop("resampling", "bootstrap")
+    approx = bool(kwargs.pop("approx", False))
+    resample_rep = bool(kwargs.pop("resample_rep", False))
+    if kwargs:
+        raise TypeError("unexpected keyword arguments: %s" % sorted(kwargs))
+    if resampling != "bootstrap":
+        raise NotImplementedError("only resampling='bootstrap' is implemented on the device path")
+    if treatment_for_gene is not None:
+        raise NotImplementedError("treatment_for_gene is broken in the reference's ht_2d_moments (main.py:492)")
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    st.ensure_resident()
+    if st.design is None:
+        _refresh_design(adata)
+    if _estimator_code(mem["estimator_type"]) != 0:
+        raise NotImplementedError("ht_2d_moments needs estimator_type='hyper_relative' (the reference has no "
+                                  "mean_only covariance estimator, estimator.py:35-46)")
+    groups = mem["groups"]
+    R = len(groups)
+    cov = np.ascontiguousarray(covariate.values, dtype=np.float64)
+    tr = np.ascontiguousarray(treatment.values, dtype=np.float64)
+    if tr.shape[1] != 1:
+        raise ValueError("ht_2d_moments supports exactly one treatment column (as the reference effectively does)")
+    one_sample = bool((tr == 1).mean() == 1)
+    idx1, idx2 = mem["2d_moments"]["gene_idx_1"], mem["2d_moments"]["gene_idx_2"]
+    n_all = idx1.shape[0]
+    # unordered de-duplication, first occurrence computes (main.py:467-482)
+    first, owner = {}, np.full(n_all, -1, dtype=np.int64)
+    for k in range(n_all):
+        a, b = int(idx1[k]), int(idx2[k])
+        if a == b:
+            continue
+        key = (a, b) if a < b else (b, a)
+        if key not in first:
+            first[key] = k
+        owner[k] = first[key]
+    uniq = np.array(sorted(set(first.values())), dtype=np.int64)
+    true_corr = np.stack([mem["2d_moments"][g]["corr"] for g in groups], axis=1)       # (n_all, R)
+    out = {k: np.full(n_all, np.nan) for k in ("coef", "se", "asl")}
+    per_item = 8 * (num_boot + 1) * (3 if not approx else 2)
+    pairs_per_tile = int(max(1, min(65535 // R, workspace_bytes // (per_item * R))))
+    stats_acc = {}
+    G = adata.shape[1]
+    for lo in range(0, uniq.shape[0], pairs_per_tile):
+        sel = uniq[lo:lo + pairs_per_tile]
+        a, b = idx1[sel].astype(np.int64), idx2[sel].astype(np.int64)
+        ga, gb = st.gene_index[a] + st.gene_offset, st.gene_index[b] + st.gene_offset
+        pid = np.minimum(ga, gb) * (1 << 31) + np.maximum(ga, gb)                        # order-free stream id
+        pair_id = to_device(pid, st.device, np.int64)
+        res = engine.ht_2d_tile(st.seg, st.design, st.cell_bin, a, b, true_corr[sel], cov, tr, num_boot, seed, approx,
+                                one_sample, want_coef_rows=not approx, pair_id=pair_id, timer=st.timer,
+                                stats=stats_acc, resample_rep=resample_rep)
+        if not approx:
+            gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
+        for k in out:
+            out[k][sel] = res[k].cpu().numpy()[:, 0, 0]
+    dup = owner >= 0
+    for k in out:
+        out[k][dup] = out[k][owner[dup]]
+    st.last_stats = stats_acc
+    mem["2d_ht"] = {"treatment": treatment, "covariate": covariate, "corr_coef": out["coef"],
+                    "corr_se": out["se"], "corr_asl": out["asl"]}
+    if not inplace:
+        return adata

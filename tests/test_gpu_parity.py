@@ -499,3 +499,89 @@ def test_rng_resample_rep_vs_oracle(gpu_prepared, oracle_prepared):
         assert ok.sum() > 50
         assert np.median(np.abs(g[key + "_se"][ok] / o[key + "_se"][ok] - 1)) < 0.1   # heavy-tailed with 4 groups
         assert stats.spearmanr(g[key + "_asl"][ok], o[key + "_asl"][ok]).statistic > 0.95
+
+
+# ----------------------------------------------------------------------------- 2D path
+def test_pair_unique_tables_vs_oracle(st, gpu_prepared, oracle_prepared):
+    """(count_1, count_2, bin) compression against the oracle's unique_table on two-column slices."""
+    dstate = gpu_prepared.uns["memento"]["_b200"]
+    omem = oracle_prepared.uns["memento"]
+    seg = dstate.seg
+    R = seg.R
+    idx1 = np.array([0, 0, 5, 7, 2, 40])
+    idx2 = np.array([3, 1, 9, 2, 7, 11])
+    tab = engine.pair_tables(seg, dstate.design, dstate.cell_bin, idx1, idx2, want_raw=True)
+    torch.cuda.synchronize()
+    ptr = tab["item_ptr"].cpu().numpy()
+    key = tab["raw_key"].cpu().numpy().view(np.uint64)
+    cnt = tab["raw_cnt"].cpu().numpy()
+    U = tab["item_U"].cpu().numpy()
+    np.random.seed(0)
+    for k in range(len(idx1)):
+        for r, g in enumerate(omem["groups"]):
+            cols = omem["group_cells"][g][:, [idx1[k], idx2[k]]]
+            inv_sf, _, vals, mult = o_resample.unique_table(cols, omem["approx_size_factor"][g])
+            nz = (vals[:, 0] > 0) | (vals[:, 1] > 0)
+            want = sorted(zip(vals[nz, 0], vals[nz, 1], np.round(inv_sf.reshape(-1)[nz], 12), mult[nz]))
+            item = k * R + r
+            kk = key[ptr[item]:ptr[item] + U[item]]
+            cc = cnt[ptr[item]:ptr[item] + U[item]]
+            got = sorted(zip((kk >> np.uint64(32)).astype(float), ((kk >> np.uint64(8)) & np.uint64(0xFFFFFF)).astype(float),
+                             np.round(dstate.bin_inv_sf[(kk & np.uint64(0xFF)).astype(int)], 12), cc))
+            assert len(got) == len(want), (k, r)
+            assert got == want, (k, r)
+            assert cc.sum() + mult[~nz].sum() == cols.shape[0]
+
+
+def test_pair_bootstrap_replay_vs_reference(st, gpu_prepared):
+    """Host-supplied resample counts for one 2D table of the golden fixture: covariance and both
+    variances must match the reference's _bootstrap_2d to 1e-6 (we assert 1e-9)."""
+    from memento_b200 import _lib
+    mem = gpu_prepared.uns["memento"]
+    dev = mem["_b200"].device
+    g = mem["groups"][1]
+    B = 64
+    expr, inv_sf, mult = st["tab2d_expr"], st["tab2d_inv_sf"].reshape(-1), st["tab2d_counts"]
+    W = o_resample.draw_counts(int(st["group_ncells"][1]), mult, B).T.reshape(-1)
+    d = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=dev)  # noqa: E731
+    outs = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(4)]
+    _lib.call("mm_pair_bootstrap_replay", dev, d(expr[:, 0], np.float64), d(expr[:, 1], np.float64), d(inv_sf, np.float64),
+              d(W, np.int64), d([0, expr.shape[0]], np.int64), d([st["group_ncells"][1]], np.int32),
+              d([mem["group_q"][g]], np.float64), 1, B, *outs)
+    torch.cuda.synchronize()
+    cov, v1, v2, corr = (o.cpu().numpy() for o in outs)
+    assert_close(cov, st["tab2d_cov"], 1e-9, atol=1e-15)
+    assert_close(v1, st["tab2d_var1"], 1e-9, atol=1e-15)
+    assert_close(v2, st["tab2d_var2"], 1e-9, atol=1e-15)
+    want = o_moments.corr_from_cov(st["tab2d_cov"].copy(), st["tab2d_var1"].copy(), st["tab2d_var2"].copy())
+    assert_close(corr, want, 1e-8)
+
+
+def test_ht_2d_vs_reference_and_oracle(st, gpu_prepared, oracle_prepared):
+    """ht_2d_moments: the observed coefficients are RNG-free and must equal the reference's golden
+    values; SE and p-values are compared with an oracle run (independent RNG) within MC error; the
+    duplicate / self-pair conventions of main.py:467-509 are checked on the golden pair list."""
+    h2 = load("ht2d.npz")
+    ad, oad = gpu_prepared.copy(), oracle_prepared.copy()
+    names = ad.var.index.tolist()
+    pairs = [(names[i], names[j]) for i, j in zip(st["pairs_idx1"], st["pairs_idx2"])]
+    memento.compute_2d_moments(ad, pairs)
+    o_pipe.compute_2d_moments(oad, pairs)
+    cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+    B = 2000
+    memento.ht_2d_moments(ad, cov, tr, num_boot=B, resampling="bootstrap", approx=True, seed=3)
+    np.random.seed(8)
+    o_pipe.ht_2d_moments(oad, cov, tr, num_boot=B, num_cpus=1, resampling="bootstrap", approx=True)
+    g, o = ad.uns["memento"]["2d_ht"], oad.uns["memento"]["2d_ht"]
+    assert_close(g["corr_coef"], h2["corr_coef"], 1e-8, atol=1e-12)          # golden (reference) values
+    assert_close(g["corr_coef"], o["corr_coef"], 1e-8, atol=1e-12)
+    ok = np.isfinite(o["corr_se"])
+    assert np.array_equal(np.isfinite(g["corr_se"]), ok)
+    assert np.abs(g["corr_se"][ok] / o["corr_se"][ok] - 1).max() < 0.12
+    assert np.abs(np.log10(g["corr_asl"][ok]) - np.log10(o["corr_asl"][ok])).max() < 0.35
+    # (names[7], names[2]) and (names[2], names[7]) are the same unordered pair; (names[5], names[5]) is skipped
+    assert g["corr_coef"][-1] == g["corr_coef"][-2] and np.isnan(g["corr_coef"][-3])
+    # default kwargs (counting + GEV tails) run as well
+    memento.ht_2d_moments(ad, cov, tr, num_boot=B, resampling="bootstrap", seed=3)
+    p = ad.uns["memento"]["2d_ht"]["corr_asl"]
+    assert np.array_equal(np.isfinite(p), ok) and (p[ok] > 0).all() and (p[ok] <= 1).all()
