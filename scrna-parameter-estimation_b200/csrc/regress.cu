@@ -203,12 +203,18 @@ wls_functional_kernel(WlsParams P) {
         }
     }
     for (int t = 0; t < T; ++t) {
-        double s = 0.0;
+        double s = 0.0, s0 = 0.0;
         for (int r = tid; r < R; r += kRegThreads) {
             double a = Z[(long long)r * K + Pc + t];
             s += P.weights[r] * a * a;
+            double v0 = P.treatment[(long long)r * T + t];
+            s0 += mask[r] ? P.weights[r] * v0 * v0 : 0.0;
         }
         double ss = block_sum(s, sred);
+        double ref2 = block_sum(s0, sred);
+        // treatment column (numerically) inside the span of [1, covariate] on the valid groups: the slope is
+        // 0/0 -- the reference returns rounding noise there, we return NaN
+        if (!(ss > 1e-20 * (ref2 > 0.0 ? ref2 : 1.0))) ss = nan("");
         for (int r = tid; r < R; r += kRegThreads)
             C[(long long)t * R + r] = mask[r] ? P.weights[r] * Z[(long long)r * K + Pc + t] / ss : 0.0;
     }

@@ -8,8 +8,8 @@
 
 Same call signatures and ``adata.uns['memento']`` schema as the reference (memento/main.py).
 """
-from .main import (compute_1d_moments, compute_2d_moments, create_groups, ht_1d_moments,  # noqa: F401
-                   ht_2d_moments, setup_memento)
+from .main import (compute_1d_moments, compute_2d_moments, create_groups, get_corr_matrix,  # noqa: F401
+                   ht_1d_moments, ht_2d_moments, setup_memento)
 from .getters import get_1d_ht_result, get_1d_moments, get_groups  # noqa: F401
 from .anndata_lite import AnnDataLite  # noqa: F401
 

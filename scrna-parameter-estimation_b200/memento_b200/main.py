@@ -483,6 +483,46 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
         return adata
 
 
+def get_corr_matrix(adata, group, block=1 << 18):
+    """All-by-all correlation matrix of one group.  reference: main.py:277-291 ->
+    estimator.py:236-270 (_hyper_corr_symmetric: sparse X^T D^2 X densified).  Here the upper triangle
+    is computed pair by pair with mm_pair_products in blocks; the dense tensor-core block kernel for
+    large gene sets is a later row of the scope table."""
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    st.ensure_resident()
+    groups = mem["groups"]
+    r = groups.index(group)
+    G = adata.shape[1]
+    n = float(st.group_start[r + 1] - st.group_start[r])
+    q = mem["group_q"][group]
+    sums = st.seg.moments(st.inv_sf_sorted, st.timer).cpu().numpy()[:, :, r]      # (5, G)
+    iu, ju = np.triu_indices(G)
+    prod = np.empty(iu.shape[0])
+    for lo in range(0, iu.shape[0], block):
+        i1 = to_device(iu[lo:lo + block], st.device, np.int32)
+        i2 = to_device(ju[lo:lo + block], st.device, np.int32)
+        prod[lo:lo + block] = st.seg.pair_products(i1, i2, st.inv_sf_sorted, st.timer)[:, r].cpu().numpy()
+    P = np.zeros((G, G))
+    P[iu, ju] = prod / n
+    P[ju, iu] = prod / n
+    d = np.arange(G)
+    P[d, d] -= (1 - q) * sums[3] / n                                              # estimator.py:256
+    mean = sums[2] / n
+    cov = P - np.outer(mean, mean)
+    var = mem["1d_moments"][group][1]
+    with np.errstate(invalid="ignore"):
+        denom = np.sqrt(np.outer(var, var))                                        # :263 (original var)
+    ok = np.isfinite(denom)
+    corr = np.full(cov.shape, 5.0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        corr[ok] = cov[ok] / denom[ok]
+    near = (corr < 1.05) & (corr > -1.05)
+    corr[near] = np.clip(corr[near], -1, 1)
+    corr[(corr > 1) | (corr < -1)] = np.nan
+    return corr
+
+
 def _corr_from_cov(cov, var_1, var_2):
     """reference estimator.py:281-292 (mutates var_1 / var_2 in place, as there)."""
     corr = np.full(cov.shape, 5.0)
