@@ -38,12 +38,17 @@ int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32
  *   out[2*n_seg+s] = sum x/sf       out[3*n_seg+s] = sum x/sf^2     out[4*n_seg+s] = sum x^2/sf^2
  * inv_sf[cell] = 1/size_factor in the same (group-sorted) cell order as `rows`.
  * nnz = seg_ptr[n_seg] (host copy, picks the launch shape); big_list: int32 scratch of nnz/4096 + 2
- * entries.
+ * entries.  group_start (nullable, device int64[R+1]) / R / max_group_cells: first renumbered row of each
+ * group; when the largest group's 1/size_factor window fits in shared memory (<= 96 KB) it is staged
+ * there instead of being gathered through L1.  chunk_seg (nullable, device int32[ceil(nnz / 4096)]):
+ * index of the segment containing nonzero 4096 * i; when given (and segments average >= 48 nonzeros)
+ * the flat streaming kernel is used: one contiguous pass over the nonzero arrays.
  * Replaces: memento/estimator.py:175-185 (_hyper_1d_relative, sparse form; three sparse mat-vecs and
  * a squared copy) and the obs_mean / obs_max passes of memento/main.py:201, :206. */
 int mm_seg_moments(int device, void* stream, const float* vals, const int32_t* rows,
                    const int64_t* seg_ptr, int64_t n_seg, int64_t nnz, const double* inv_sf,
-                   double* out, int32_t* big_list);
+                   double* out, int32_t* big_list, const int64_t* group_start, int32_t R,
+                   int64_t max_group_cells, const int32_t* chunk_seg);
 
 /* Covariance sums of gene pairs within every group: for pair k and group r,
  *   out[k*R + r] = sum over cells of the group of x_{c,i} * x_{c,j} / sf_c^2

@@ -108,12 +108,18 @@ class CsrOnDevice:
 class SegMatrix:
     """Group-sorted CSC (see module docstring).  Immutable once built."""
 
-    def __init__(self, vals, rows, seg_ptr, n_genes, n_groups, n_cells):
+    def __init__(self, vals, rows, seg_ptr, n_genes, n_groups, n_cells, group_start=None):
         self.vals, self.rows, self.seg_ptr = vals, rows, seg_ptr
         self.G, self.R, self.n_cells = int(n_genes), int(n_groups), int(n_cells)
         self.device = vals.device
         self.nnz = int(vals.numel())
         self._big = None
+        # first renumbered row of each group (host numpy int64 [R + 1]); one group = all cells when absent
+        gs = np.asarray([0, self.n_cells], dtype=np.int64) if group_start is None else np.asarray(group_start, dtype=np.int64)
+        self.group_start_host = gs
+        self.group_start = torch.as_tensor(gs, device=self.device)
+        self.max_group_cells = int(np.diff(gs).max()) if gs.size > 1 else 0
+        self._chunk_seg = None
 
     @property
     def n_seg(self):
@@ -123,12 +129,13 @@ class SegMatrix:
     def to_host_pinned(self):
         """Pinned host copies of the three arrays (what an end-to-end call uploads)."""
         return {"vals": self.vals.cpu().pin_memory(), "rows": self.rows.cpu().pin_memory(),
-                "seg_ptr": self.seg_ptr.cpu().pin_memory(), "G": self.G, "R": self.R, "n_cells": self.n_cells}
+                "seg_ptr": self.seg_ptr.cpu().pin_memory(), "G": self.G, "R": self.R, "n_cells": self.n_cells,
+                "group_start": self.group_start_host}
 
     @staticmethod
     def from_host_pinned(h, device):
         seg = SegMatrix(h["vals"].to(device, non_blocking=True), h["rows"].to(device, non_blocking=True),
-                        h["seg_ptr"].to(device, non_blocking=True), h["G"], h["R"], h["n_cells"])
+                        h["seg_ptr"].to(device, non_blocking=True), h["G"], h["R"], h["n_cells"], h["group_start"])
         return seg
 
     @staticmethod
@@ -160,8 +167,12 @@ class SegMatrix:
         seg_len = torch.bincount(key, minlength=n_genes * n_groups)
         seg_ptr = torch.zeros(n_genes * n_groups + 1, dtype=torch.int64, device=dev)
         torch.cumsum(seg_len, 0, out=seg_ptr[1:])
+        gs = None
+        if group_of_cell is not None:
+            cnt = torch.bincount(group_of_cell.long(), minlength=n_groups).cpu().numpy()
+            gs = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
         return SegMatrix(vals[order].contiguous(), new_rows[order].to(torch.int32).contiguous(), seg_ptr,
-                         n_genes, n_groups, n_cells)
+                         n_genes, n_groups, n_cells, gs)
 
     def regroup(self, group_of_cell, n_groups, rank_of_cell):
         """From an ungrouped (R == 1) matrix to a grouped one."""
@@ -186,17 +197,28 @@ class SegMatrix:
         seg_of = torch.repeat_interleave(torch.arange(seg_ids.numel(), device=dev), ln, output_size=total)
         src = lo[seg_of] + (torch.arange(total, device=dev) - new_ptr[seg_of])
         return SegMatrix(self.vals[src].contiguous(), self.rows[src].contiguous(), new_ptr, gi.numel(), R,
-                         self.n_cells)
+                         self.n_cells, self.group_start_host)
 
     # ------------------------------------------------------------------ kernels
+    FLAT_WARP_ELEMS = 4096   # must match kFlatWarpElems in csrc/moments.cu
+
+    def chunk_seg(self):
+        """Segment containing nonzero FLAT_WARP_ELEMS * i, for the flat streaming moment kernel."""
+        if self._chunk_seg is None:
+            starts = torch.arange(0, max(self.nnz, 1), self.FLAT_WARP_ELEMS, device=self.device, dtype=torch.int64)
+            idx = torch.searchsorted(self.seg_ptr, starts, right=True) - 1
+            self._chunk_seg = idx.clamp_(0, max(self.n_seg - 1, 0)).to(torch.int32)
+        return self._chunk_seg
+
     def moments(self, inv_sf, timer=NULL_TIMER):
         """(5, G, R) float64 on the device: sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2."""
         out = torch.empty(5 * self.n_seg, dtype=torch.float64, device=self.device)
         if self._big is None:
             self._big = torch.zeros(self.nnz // 4096 + 2, dtype=torch.int32, device=self.device)
+        chunk_seg = self.chunk_seg()
         ev = timer.start()
         _lib.call("mm_seg_moments", self.device, self.vals, self.rows, self.seg_ptr, self.n_seg, self.nnz,
-                  inv_sf, out, self._big)
+                  inv_sf, out, self._big, self.group_start, self.R, self.max_group_cells, chunk_seg)
         timer.stop("seg_moments", ev)
         return out.view(5, self.G, self.R)
 
