@@ -15,7 +15,9 @@
 // and penalty (100 * log(DBL_MAX) per point outside the support); the KS decision uses the exact
 // critical values D_0.05(n) = scipy.stats.kstwo.isf(0.05, n) tabulated below for the nine tail sizes.
 //
-// One 2-warp CTA per flagged test: the null is sorted by a shared-memory bitonic sort, then warp 0
+// One 2-warp CTA per flagged test: the <= 1024 most extreme values of each side are isolated by a few
+// counting passes over the null (thresholds around mean -+ 1.5 sd, adjusted until 300..1024 values
+// fall beyond them), sorted in shared memory (16 KB per test, so many tests share an SM), then warp 0
 // walks the left-tail ladder and warp 1 the right-tail ladder, each evaluating the likelihood with a
 // shuffle reduction.
 #include "common.cuh"
@@ -205,56 +207,107 @@ __device__ double gev_ks(const double* x, int n, const double th[3], int lane) {
     return d;
 }
 
+constexpr int kCand = 1024;     // candidate slots per tail (the 300 most extreme values are selected from them)
+
+// bitonic sort (ascending) of kCand doubles in shared memory by the whole block
+__device__ void sort_cand(double* a, int tid) {
+    for (int k = 2; k <= kCand; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < kCand; i += kGevThreads) {
+                int l = i ^ j;
+                if (l > i) {
+                    double x = a[i], y = a[l];
+                    bool up = ((i & k) == 0);
+                    if ((x > y) == up) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
 __global__ void __launch_bounds__(kGevThreads)
 gev_tail_kernel(GevParams P) {
-    extern __shared__ __align__(16) double s_null[];     // sort_cap doubles
-    __shared__ int s_n;
+    __shared__ double s_lo[kCand];          // ascending; the c_lo smallest-side candidates first, +inf padding after
+    __shared__ double s_hi[kCand];          // ascending; -inf padding first, the c_hi largest-side candidates last
+    __shared__ double s_red[2][kGevThreads / 32];
+    __shared__ int s_cnt[3];
     __shared__ int s_state[2][kLadder];    // 0 pending, 1 pass, 2 ks-fail, 3 fit error
     __shared__ double s_val[2][kLadder];
     const int row = P.flagged[blockIdx.x];
     const double* cr = P.coef_rows + (long long)row * (P.B + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double stat = cr[0], astat = fabs(stat);
-    if (tid == 0) s_n = 0;
     if (tid < 2 * kLadder) { s_state[tid / kLadder][tid % kLadder] = 0; }
-    __syncthreads();
+    // ---- size, mean and spread of the null (finite entries of coef[1:] - coef[0])
+    double sum = 0.0, sq = 0.0;
     int cnt = 0;
-    for (int i = tid; i < P.sort_cap; i += kGevThreads) {
-        double v = INFINITY;
-        if (i < P.B) {
-            double d = cr[i + 1] - stat;
-            if (isfinite(d)) { v = d; ++cnt; }
-        }
-        s_null[i] = v;
+    for (int i = tid; i < P.B; i += kGevThreads) {
+        double d = cr[i + 1] - stat;
+        if (isfinite(d)) { sum += d; sq = fma(d, d, sq); ++cnt; }
     }
-    cnt = warp_sum_int(cnt);
-    if (lane == 0) atomicAdd(&s_n, cnt);
+    sum = warp_sum(sum); sq = warp_sum(sq); cnt = warp_sum_int(cnt);
+    if (tid < 3) s_cnt[tid] = 0;
+    if (lane == 0) { s_red[0][warp] = sum; s_red[1][warp] = sq; }
     __syncthreads();
-    for (int k = 2; k <= P.sort_cap; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < P.sort_cap; i += kGevThreads) {
-                int l = i ^ j;
-                if (l > i) {
-                    double a = s_null[i], b = s_null[l];
-                    bool up = ((i & k) == 0);
-                    if ((a > b) == up) { s_null[i] = b; s_null[l] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    const int n = s_n;
+    if (lane == 0) atomicAdd(&s_cnt[0], cnt);
+    __syncthreads();
+    const int n = s_cnt[0];
+    double tsum = 0.0, tsq = 0.0;
+    for (int w = 0; w < kGevThreads / 32; ++w) { tsum += s_red[0][w]; tsq += s_red[1][w]; }
     if (n < c_tail_n[0]) {     // fewer than 300 usable replicates: keep the empirical bound
         if (tid == 0) P.status[blockIdx.x] = 0;
         return;
     }
+    const double mu = tsum / n;
+    double var = tsq / n - mu * mu;
+    const double sd = sqrt(var > 0.0 ? var : 0.0);
+    // ---- thresholds that isolate between 300 and kCand values on each side (a few counting passes)
+    double t_lo = mu - 1.5 * sd, t_hi = mu + 1.5 * sd;
+    bool ok_lo = false, ok_hi = false;
+    for (int it = 0; it < 24 && !(ok_lo && ok_hi); ++it) {
+        int c_lo = 0, c_hi = 0;
+        for (int i = tid; i < P.B; i += kGevThreads) {
+            double d = cr[i + 1] - stat;
+            if (isfinite(d)) { c_lo += (d <= t_lo); c_hi += (d >= t_hi); }
+        }
+        c_lo = warp_sum_int(c_lo); c_hi = warp_sum_int(c_hi);
+        __syncthreads();
+        if (tid < 3) s_cnt[tid] = 0;
+        __syncthreads();
+        if (lane == 0) { atomicAdd(&s_cnt[1], c_lo); atomicAdd(&s_cnt[2], c_hi); }
+        __syncthreads();
+        c_lo = s_cnt[1]; c_hi = s_cnt[2];
+        ok_lo = c_lo >= c_tail_n[0] && c_lo <= kCand;
+        ok_hi = c_hi >= c_tail_n[0] && c_hi <= kCand;
+        const double step = sd * (it < 8 ? 0.2 : (it < 16 ? 0.05 : 0.0125));
+        if (!ok_lo) t_lo += (c_lo < c_tail_n[0]) ? step : -0.5 * step;
+        if (!ok_hi) t_hi -= (c_hi < c_tail_n[0]) ? step : -0.5 * step;
+    }
+    if (!(ok_lo && ok_hi)) {   // heavy ties around the cut: keep the empirical bound
+        if (tid == 0) P.status[blockIdx.x] = 0;
+        return;
+    }
+    // ---- gather the candidates and sort them
+    for (int i = tid; i < kCand; i += kGevThreads) { s_lo[i] = INFINITY; s_hi[i] = -INFINITY; }
+    __syncthreads();
+    if (tid < 3) s_cnt[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < P.B; i += kGevThreads) {
+        double d = cr[i + 1] - stat;
+        if (!isfinite(d)) continue;
+        if (d <= t_lo) s_lo[atomicAdd(&s_cnt[1], 1)] = d;
+        if (d >= t_hi) s_hi[atomicAdd(&s_cnt[2], 1)] = d;
+    }
+    __syncthreads();
+    sort_cand(s_lo, tid);
+    sort_cand(s_hi, tid);
     // warp 0 walks the ladder of the left tail, warp 1 that of the right tail, each until a tail size
     // passes the KS check or a fit fails (no speculative fits)
     {
         const int side = warp;
         for (int li = 0; li < kLadder; ++li) {
             const int ne = c_tail_n[li];
-            const double* x = side == 0 ? s_null : s_null + (n - ne);
+            const double* x = side == 0 ? s_lo : s_hi + (kCand - ne);
             double th[3];
             int state;
             double val = 0.0;
@@ -299,14 +352,9 @@ MM_EXPORT int mm_gev_tail_asl(int device, void* stream, const double* coef_rows,
     MM_REQUIRE(n_flag >= 0 && num_boot > 0, "n_flag/num_boot");
     if (n_flag == 0) return 0;
     MM_REQUIRE(coef_rows && flagged && asl && status, "null pointer");
-    int cap = 1;
-    while (cap < num_boot) cap <<= 1;
-    MM_REQUIRE(cap <= 16384, "GEV tail stage supports num_boot <= 16384");
     GevParams P;
-    P.coef_rows = coef_rows; P.flagged = flagged; P.n_flag = n_flag; P.B = num_boot; P.sort_cap = cap;
+    P.coef_rows = coef_rows; P.flagged = flagged; P.n_flag = n_flag; P.B = num_boot; P.sort_cap = 0;
     P.asl = asl; P.status = status;
-    size_t smem = (size_t)cap * sizeof(double);
-    MM_CUDA(cudaFuncSetAttribute(gev_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gev_tail_kernel<<<n_flag, kGevThreads, smem, (cudaStream_t)stream>>>(P);
+    gev_tail_kernel<<<n_flag, kGevThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_gev_tail_asl");
 }
