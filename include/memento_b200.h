@@ -37,18 +37,20 @@ int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32
  *   out[0*n_seg+s] = sum x          out[1*n_seg+s] = max x
  *   out[2*n_seg+s] = sum x/sf       out[3*n_seg+s] = sum x/sf^2     out[4*n_seg+s] = sum x^2/sf^2
  * inv_sf[cell] = 1/size_factor in the same (group-sorted) cell order as `rows`.
- * nnz = seg_ptr[n_seg] (host copy, picks the launch shape); big_list: int32 scratch of nnz/4096 + 2
- * entries.  group_start (nullable, device int64[R+1]) / R / max_group_cells: first renumbered row of each
- * group; when the largest group's 1/size_factor window fits in shared memory (<= 96 KB) it is staged
- * there instead of being gathered through L1.  chunk_seg (nullable, device int32[ceil(nnz / 4096)]):
- * index of the segment containing nonzero 4096 * i; when given (and segments average >= 48 nonzeros)
- * the flat streaming kernel is used: one contiguous pass over the nonzero arrays.
+ * nnz = seg_ptr[n_seg] (host copy, picks the launch shape).
+ * n_cells = length of inv_sf.  chunk_seg (device int32[ceil(nnz / 512)]): index of the segment containing
+ * nonzero 512 * i (the last segment whose start is <= 512 * i); edge: float64 scratch of
+ * 10 * ceil(nnz / 512) entries.  With both (and 16-byte aligned vals / rows / inv_sf) the matrix is read as
+ * ONE contiguous stream and the result is deterministic: segments averaging >= 64 nonzeros use the
+ * register-streaming span kernel (1/size_factor table in shared memory when n_cells * 8 fits), shorter ones
+ * the TMA-staged tile kernel (4096-nonzero tiles bulk-copied into a shared-memory ring).  When either is
+ * NULL the segments are reduced one by one from global memory and big_list (int32 scratch of
+ * nnz / 4096 + 2 entries, otherwise unused and nullable) collects the segments that need a whole CTA.
  * Replaces: memento/estimator.py:175-185 (_hyper_1d_relative, sparse form; three sparse mat-vecs and
  * a squared copy) and the obs_mean / obs_max passes of memento/main.py:201, :206. */
 int mm_seg_moments(int device, void* stream, const float* vals, const int32_t* rows,
                    const int64_t* seg_ptr, int64_t n_seg, int64_t nnz, const double* inv_sf,
-                   double* out, int32_t* big_list, const int64_t* group_start, int32_t R,
-                   int64_t max_group_cells, const int32_t* chunk_seg);
+                   int64_t n_cells, double* out, int32_t* big_list, const int32_t* chunk_seg, double* edge);
 
 /* Covariance sums of gene pairs within every group: for pair k and group r,
  *   out[k*R + r] = sum over cells of the group of x_{c,i} * x_{c,j} / sf_c^2
@@ -177,7 +179,7 @@ int mm_regress_asl(int device, void* stream, const double* boot0, const double* 
  * value law to each tail for tail sizes 300, 270, ..., 60 (Nelder-Mead MLE as scipy.stats.genextreme.fit
  * does it) until a two-sided KS check at 0.05 passes, and replaces asl[row] by
  * N_exec/n * (cdf(-|stat|) + sf(|stat|)); status[i] = 1 if replaced, 0 if the empirical bound was
- * kept (no tail passed, a fit failed, or fewer than 300 usable replicates).  num_boot <= 16384.
+ * kept (no tail passed, a fit failed, or fewer than 300 usable replicates).
  * Replaces: memento/hypothesis_test.py:94-141 (_compute_asl, GEV branch; scipy genextreme.fit +
  * kstest per tail, ~110 ms per fit on a CPU core). */
 int mm_gev_tail_asl(int device, void* stream, const double* coef_rows, const int32_t* flagged,

@@ -17,7 +17,7 @@ _i32, _i64, _u64, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 # name -> argument ctypes after the leading (device, stream); every function returns int status
 SIGNATURES = {
     "mm_csr_row_sums": [_vp, _vp, _vp, _i64, _vp, _vp],
-    "mm_seg_moments": [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _vp],
+    "mm_seg_moments": [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
     "mm_pair_products": [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],
     "mm_seg_unique": [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                       _vp, _vp, _vp, _vp],

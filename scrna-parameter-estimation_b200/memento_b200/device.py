@@ -200,12 +200,12 @@ class SegMatrix:
                          self.n_cells, self.group_start_host)
 
     # ------------------------------------------------------------------ kernels
-    FLAT_WARP_ELEMS = 4096   # must match kFlatWarpElems in csrc/moments.cu
+    CHUNK = 512   # must match kSpanElems in csrc/moments.cu
 
     def chunk_seg(self):
-        """Segment containing nonzero FLAT_WARP_ELEMS * i, for the flat streaming moment kernel."""
+        """Segment containing nonzero CHUNK * i (the span index of the streaming moment kernels)."""
         if self._chunk_seg is None:
-            starts = torch.arange(0, max(self.nnz, 1), self.FLAT_WARP_ELEMS, device=self.device, dtype=torch.int64)
+            starts = torch.arange(0, max(self.nnz, 1), self.CHUNK, device=self.device, dtype=torch.int64)
             idx = torch.searchsorted(self.seg_ptr, starts, right=True) - 1
             self._chunk_seg = idx.clamp_(0, max(self.n_seg - 1, 0)).to(torch.int32)
         return self._chunk_seg
@@ -213,12 +213,14 @@ class SegMatrix:
     def moments(self, inv_sf, timer=NULL_TIMER):
         """(5, G, R) float64 on the device: sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2."""
         out = torch.empty(5 * self.n_seg, dtype=torch.float64, device=self.device)
-        if self._big is None:
+        if self._big is None:      # scratch: big-segment list (fallback kernel) and per-tile edge partials
+            n_chunks = (self.nnz + self.CHUNK - 1) // self.CHUNK
             self._big = torch.zeros(self.nnz // 4096 + 2, dtype=torch.int32, device=self.device)
+            self._edge = torch.empty(10 * max(n_chunks, 1), dtype=torch.float64, device=self.device)
         chunk_seg = self.chunk_seg()
         ev = timer.start()
         _lib.call("mm_seg_moments", self.device, self.vals, self.rows, self.seg_ptr, self.n_seg, self.nnz,
-                  inv_sf, out, self._big, self.group_start, self.R, self.max_group_cells, chunk_seg)
+                  inv_sf, int(inv_sf.numel()), out, self._big, chunk_seg, self._edge)
         timer.stop("seg_moments", ev)
         return out.view(5, self.G, self.R)
 
