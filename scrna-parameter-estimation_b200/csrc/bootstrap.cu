@@ -118,7 +118,7 @@ __host__ __device__ inline void poisson_range(double lam, int* klo, int* len) {
 }
 
 // Alias table (Walker / Vose) of Poisson(lam) restricted to k in [klo, klo + len): cell j keeps j with
-// probability prob[j] / 2^32 and otherwise yields alias[j].  One 32-bit random number r gives both the
+// probability prob[j] / 2^32 and otherwise yields klo + alias[j] (cells store absolute counts).  One 32-bit random number r gives both the
 // cell (high word of r * len) and the fraction inside it (low word): one multiply, one 8-byte load,
 // one compare -- no search loop, no divergence.  Built by one thread per table in float64; the tails
 // outside the range (< 2^-32 each) are folded in by normalising the pmf over the range.
@@ -138,12 +138,12 @@ __device__ void poisson_alias_fill(double lam, int klo, int len, uint2* tab, dou
     while (ns > 0 && nl > 0) {
         int sidx = small[--ns], lidx = large[--nl];
         double t = floor(p[sidx] * 4294967296.0);
-        tab[sidx] = make_uint2(t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t, (uint32_t)lidx);
+        tab[sidx] = make_uint2(t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t, (uint32_t)(klo + lidx));
         p[lidx] = (p[lidx] + p[sidx]) - 1.0;
         if (p[lidx] < 1.0) small[ns++] = lidx; else large[nl++] = lidx;
     }
-    while (nl > 0) { int i = large[--nl]; tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)i); }
-    while (ns > 0) { int i = small[--ns]; tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)i); }   // round-off leftovers
+    while (nl > 0) { int i = large[--nl]; tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)(klo + i)); }
+    while (ns > 0) { int i = small[--ns]; tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)(klo + i)); }   // round-off leftovers
 }
 
 __global__ void poisson_tables_kernel(int n_max, const int* __restrict__ off, uint2* __restrict__ pool,
@@ -154,14 +154,6 @@ __global__ void poisson_tables_kernel(int n_max, const int* __restrict__ off, ui
     int klo, len;
     poisson_range((double)n, &klo, &len);
     poisson_alias_fill((double)n, klo, len, pool + off[n], sp + off[n], ss + off[n], sl + off[n]);
-}
-
-// k - klo for one 32-bit random number
-__device__ __forceinline__ int alias_sample(const uint2* __restrict__ tab, int len, uint32_t r) {
-    const unsigned long long m = (unsigned long long)r * (unsigned)len;
-    const int j = (int)(m >> 32);
-    const uint2 e = __ldg(tab + j);
-    return ((uint32_t)m < e.x) ? j : (int)e.y;
 }
 
 struct __align__(16) SegInfo {     // written by boot_prepare_kernel, one per segment of the tile
@@ -267,7 +259,8 @@ boot_prepare_kernel(PrepParams P) {
         int klo = 0, ln = 0, off = 0;
         if (u != rem_i) { poisson_range((double)e.n, &klo, &ln); off = P.tab_off[e.n]; }
         e.p = __int_as_float(off);
-        e.lq = __int_as_float((klo << 16) | ln);       // remainder: off = klo = ln = 0 -> reads the null cell, k = 0
+        e.lq = __int_as_float(ln);                     // remainder: off = ln = 0 -> reads the null cell {2^32 - 1, 0}, k = 0
+        e.mode = klo - off;                            // kept cell index -> count (the sampler field of the chain is not needed here)
         tab[u] = e;
         if (u == rem_i) { si.rem_a = e.a; si.rem_b = e.b; }
     }
@@ -395,8 +388,7 @@ bootstrap_1d_poisson_kernel(BootParams P) {
         auto draw = [&](int u, uint32_t rnd) {
             const int4 lo4 = __ldg(reinterpret_cast<const int4*>(tab + u));
             const int4 hi4 = __ldg(reinterpret_cast<const int4*>(tab + u) + 1);
-            const int kl = hi4.y;
-            const int k = (kl >> 16) + alias_sample(P.tab_pool + hi4.x, kl & 0xFFFF, rnd);
+            const int k = alias_draw(P.tab_pool, (unsigned)hi4.x, (unsigned)hi4.y, hi4.w, rnd);
             S += k;
             const double kd = (double)k;
             M1 = fma(__hiloint2double(lo4.y, lo4.x), kd, M1);
@@ -412,7 +404,8 @@ bootstrap_1d_poisson_kernel(BootParams P) {
         if (u + 1 < U) draw(u + 1, r4.y);
         if (u + 2 < U) draw(u + 2, r4.z);
         if (si.zero_off >= 0)
-            S += (si.zero_kl >> 16) + alias_sample(P.tab_pool + si.zero_off, si.zero_kl & 0xFFFF, r4.w);
+            S += alias_draw(P.tab_pool, (unsigned)si.zero_off, (unsigned)(si.zero_kl & 0xFFFF),
+                            (si.zero_kl >> 16) - si.zero_off, r4.w);
         r4 = rng.block();
         const int i = S - si.s_lo;
         bool ok = (i >= 0) && (i < si.acc_len);

@@ -169,4 +169,17 @@ struct Philox {
     __device__ __forceinline__ float uniform() { return ((next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 };
 
+// ---------------------------------------------------------------- alias-table draw (Poissonised samplers)
+// Cell `off + j` of the pool keeps j with probability prob / 2^32 and otherwise yields its alias; cells store
+// ABSOLUTE counts in .y (klo of the table + alias index).  One 32-bit random number gives the cell (high
+// word of r * len, folded with the offset into one IMAD.HI) and the fraction inside it (low word); the cell
+// address is a single IMAD.WIDE.U32, so the draw costs two ALU-pipe instructions (compare + select) -- the
+// ALU pipe is what bounds the bootstrap kernels.  c = klo - off turns a kept cell index into its count.
+__device__ __forceinline__ int alias_draw(const uint2* __restrict__ pool, unsigned off, unsigned len, int c, uint32_t r) {
+    const unsigned idx = __umulhi(r, len) + off;
+    const unsigned frac = r * len;
+    const uint2 e = __ldg(pool + idx);
+    return frac < e.x ? (int)idx + c : (int)e.y;
+}
+
 }  // namespace mm

@@ -316,13 +316,6 @@ struct PairBootParams {
     unsigned char* item_good;   // [n_items]
 };
 
-__device__ __forceinline__ int alias_sample2(const uint2* __restrict__ tab, int len, uint32_t r) {
-    const unsigned long long m = (unsigned long long)r * (unsigned)len;
-    const int j = (int)(m >> 32);
-    const uint2 e = __ldg(tab + j);
-    return ((uint32_t)m < e.x) ? j : (int)e.y;
-}
-
 __global__ void __launch_bounds__(kPairThreads)
 pair_bootstrap_kernel(PairBootParams P) {
     const long long item = blockIdx.y;
@@ -361,7 +354,7 @@ pair_bootstrap_kernel(PairBootParams P) {
         double acc5[5] = {0, 0, 0, 0, 0};
         auto draw = [&](int u, uint32_t rnd) {
             const PairEntry e = tab[u];
-            const int k = (e.kl >> 16) + alias_sample2(P.tab_pool + e.off, e.kl & 0xFFFF, rnd);
+            const int k = alias_draw(P.tab_pool, (unsigned)e.off, (unsigned)(e.kl & 0xFFFF), (e.kl >> 16) - e.off, rnd);
             S += k;
             const double kd = (double)k;
             acc5[0] = fma(e.c1, kd, acc5[0]); acc5[1] = fma(e.c2, kd, acc5[1]); acc5[2] = fma(e.cx, kd, acc5[2]);
@@ -377,7 +370,8 @@ pair_bootstrap_kernel(PairBootParams P) {
         if (u + 1 < pi.U) draw(u + 1, r4.y);
         if (u + 2 < pi.U) draw(u + 2, r4.z);
         if (pi.zero_off >= 0)
-            S += (pi.zero_kl >> 16) + alias_sample2(P.tab_pool + pi.zero_off, pi.zero_kl & 0xFFFF, r4.w);
+            S += alias_draw(P.tab_pool, (unsigned)pi.zero_off, (unsigned)(pi.zero_kl & 0xFFFF),
+                            (pi.zero_kl >> 16) - pi.zero_off, r4.w);
         r4 = rng.block();
         const int i = S - pi.s_lo;
         bool ok = (i >= 0) && (i < pi.acc_len);

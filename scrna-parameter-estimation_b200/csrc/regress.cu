@@ -18,6 +18,7 @@ namespace mm {
 
 constexpr int kRegThreads = 256;
 constexpr int kMaxT = 4;   // treatment columns handled per pass
+constexpr int kRegCmax = 1024;   // entries of the regression functional staged in shared memory
 
 // ------------------------------------------------------------------ fill + log
 struct FillParams {
@@ -237,18 +238,34 @@ struct RegParams {
     int* out_nnull;             // [n_gene][n_stat][T] null size
 };
 
+// TT = treatment columns per pass (1, 2 or TT): the per-thread statistics are TT-sized register arrays, so
+// the common single-treatment test runs at 4x the occupancy of the general one.  The loop over the groups
+// loads four groups x both statistics before the FMAs, so every thread keeps 8 independent HBM reads in
+// flight (one replicate column per thread: the reads of a warp are contiguous 256-byte rows).
+template <int TT>
 __global__ void __launch_bounds__(kRegThreads)
 regress_asl_kernel(RegParams P) {
-    __shared__ double s_stat[2][kMaxT];
-    __shared__ double s_red[kRegThreads / 32][2 * kMaxT][2];
-    __shared__ int s_cnt[kRegThreads / 32][2 * kMaxT][2];
-    __shared__ double s_mm[kRegThreads / 32][2 * kMaxT][2];
+    __shared__ double s_stat[2][TT];
+    __shared__ double s_red[kRegThreads / 32][2 * TT][2];
+    __shared__ int s_cnt[kRegThreads / 32][2 * TT][2];
+    __shared__ double s_mm[kRegThreads / 32][2 * TT][2];
     __shared__ int s_nvalid[kRegThreads / 32];
     const int g = blockIdx.x;
     const int R = P.R, T = P.T, B1 = P.B + 1, NS = P.n_stat;
     const unsigned char* good = P.seg_good + (long long)g * R;
     const double* C = P.cmat + (long long)P.mask_id[g] * T * R;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // regression functional of this gene's mask: shared memory when it fits, global (L1) otherwise
+    __shared__ double s_Cbuf[kRegCmax];
+    __shared__ unsigned char s_good[kRegCmax];
+    const double* s_C = C;
+    if (T * R <= kRegCmax) {
+        for (int i = tid; i < T * R; i += kRegThreads) s_Cbuf[i] = C[i];
+        for (int i = tid; i < R; i += kRegThreads) s_good[i] = good[i];
+        s_C = s_Cbuf;
+        good = s_good;
+        __syncthreads();
+    }
 
     int n_good = 0;
     for (int r = 0; r < R; ++r) n_good += good[r];
@@ -261,8 +278,8 @@ regress_asl_kernel(RegParams P) {
         return;
     }
 
-    for (int t0 = 0; t0 < T; t0 += kMaxT) {
-        const int tn = min(kMaxT, T - t0);
+    for (int t0 = 0; t0 < T; t0 += TT) {
+        const int tn = min(TT, T - t0);
         // observed statistic = column 0
         if (tid < NS * tn) {
             int s = tid / tn, t = tid % tn;
@@ -274,33 +291,44 @@ regress_asl_kernel(RegParams P) {
         }
         __syncthreads();
 
-        double sum[2][kMaxT], sq[2][kMaxT], mn[2][kMaxT], mx[2][kMaxT];
-        int hi[2][kMaxT], lo[2][kMaxT];
+        double sum[2][TT], sq[2][TT], mn[2][TT], mx[2][TT];
+        int hi[2][TT], lo[2][TT];
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int t = 0; t < kMaxT; ++t) {
+            for (int t = 0; t < TT; ++t) {
                 sum[s][t] = 0; sq[s][t] = 0; hi[s][t] = 0; lo[s][t] = 0;
                 mn[s][t] = INFINITY; mx[s][t] = -INFINITY;
             }
         int nvalid = 0;
         for (int b = tid; b < B1; b += kRegThreads) {
-            double acc[2][kMaxT];
+            double acc[2][TT];
 #pragma unroll
             for (int s = 0; s < 2; ++s)
 #pragma unroll
-                for (int t = 0; t < kMaxT; ++t) acc[s][t] = 0.0;
+                for (int t = 0; t < TT; ++t) acc[s][t] = 0.0;
             bool finite = true;
-            for (int r = 0; r < R; ++r) {
-                if (!good[r]) continue;
+            for (int r0 = 0; r0 < R; r0 += 4) {
+                double v[4][2];
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    if (s < NS) {
-                        double v = P.boot[s][((long long)g * R + r) * B1 + b];
-                        finite = finite && isfinite(v);
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + j;
+                    const bool use = r < R && good[r];
 #pragma unroll
-                        for (int t = 0; t < kMaxT; ++t)
-                            if (t < tn) acc[s][t] = fma(C[(long long)(t0 + t) * R + r], v, acc[s][t]);
+                    for (int s = 0; s < 2; ++s)
+                        v[j][s] = (use && s < NS) ? __ldg(P.boot[s] + ((long long)g * R + r) * B1 + b) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + j;
+                    if (r < R && good[r]) {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            finite = finite && isfinite(v[j][s]);
+#pragma unroll
+                            for (int t = 0; t < TT; ++t)
+                                if (t < tn) acc[s][t] = fma(s_C[(t0 + t) * R + r], v[j][s], acc[s][t]);
+                        }
                     }
                 }
             }
@@ -309,7 +337,7 @@ regress_asl_kernel(RegParams P) {
             for (int s = 0; s < 2; ++s) {
                 if (s < NS) {
 #pragma unroll
-                    for (int t = 0; t < kMaxT; ++t) {
+                    for (int t = 0; t < TT; ++t) {
                         if (t < tn) {
                             double c = finite ? acc[s][t] : nan("");
                             if (P.coef_ws)
@@ -338,7 +366,7 @@ regress_asl_kernel(RegParams P) {
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int t = 0; t < kMaxT; ++t) {
+            for (int t = 0; t < TT; ++t) {
                 if (s < NS && t < tn) {
                     double a = warp_sum(sum[s][t]), b2 = warp_sum(sq[s][t]);
                     int h = warp_sum_int(hi[s][t]), l = warp_sum_int(lo[s][t]);
@@ -349,15 +377,15 @@ regress_asl_kernel(RegParams P) {
                         vmax = fmax(vmax, __shfl_xor_sync(kFull, vmax, o));
                     }
                     if (lane == 0) {
-                        s_red[warp][s * kMaxT + t][0] = a; s_red[warp][s * kMaxT + t][1] = b2;
-                        s_cnt[warp][s * kMaxT + t][0] = h; s_cnt[warp][s * kMaxT + t][1] = l;
-                        s_mm[warp][s * kMaxT + t][0] = vmin; s_mm[warp][s * kMaxT + t][1] = vmax;
+                        s_red[warp][s * TT + t][0] = a; s_red[warp][s * TT + t][1] = b2;
+                        s_cnt[warp][s * TT + t][0] = h; s_cnt[warp][s * TT + t][1] = l;
+                        s_mm[warp][s * TT + t][0] = vmin; s_mm[warp][s * TT + t][1] = vmax;
                     }
                 }
             }
         __syncthreads();
         if (tid < NS * tn) {
-            int s = tid / tn, t = tid % tn, j = s * kMaxT + t;
+            int s = tid / tn, t = tid % tn, j = s * TT + t;
             double a = 0, b2 = 0, vmin = INFINITY, vmax = -INFINITY;
             int h = 0, l = 0, n = 0;
             for (int w = 0; w < kRegThreads / 32; ++w) {
@@ -627,7 +655,9 @@ MM_EXPORT int mm_regress_asl(int device, void* stream, const double* boot0, cons
     P.cmat = cmat; P.R = R; P.T = T; P.B = num_boot; P.approx = approx; P.coef_ws = coef_ws;
     P.out_coef = out_coef; P.out_se = out_se; P.out_asl = out_asl; P.out_extreme = out_extreme;
     P.out_nnull = out_nnull;
-    regress_asl_kernel<<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    if (T == 1) regress_asl_kernel<1><<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    else if (T == 2) regress_asl_kernel<2><<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    else regress_asl_kernel<kMaxT><<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_regress_asl");
 }
 
