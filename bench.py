@@ -37,6 +37,27 @@ METRIC = "genes tested/sec (ht_1d, num_boot=10k)"
 UNIT = "genes/s"
 
 
+def ncu_traffic(nnz):
+    """DRAM bytes per mm_seg_moments launch from the committed `ncu --set full` capture of the same matrix
+    (profiles/r01_seg_moments_stream.json: dram__bytes_read.sum + dram__bytes_write.sum of the span kernel and
+    the edge fix-up kernel).  None when the capture is absent or was taken on another matrix."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_seg_moments_stream.json")
+    if not os.path.exists(path) or nnz != 58873218:
+        return None, None
+    tot = 0.0
+    for l in json.load(open(path))["launches"]:
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = l.get(k)
+            if m:
+                tot += m["value"] * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m["unit"]]
+    return tot, "profiles/r01_seg_moments_stream.json (ncu --set full, same matrix, stream + edge kernels)"
+
+
+def engine_tile_genes(seg, num_boot):
+    from memento_b200 import engine
+    return engine.tile_plan(seg, num_boot)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,10 +293,11 @@ def run_ours(a):
     uniq_ms = stage_ms.get("seg_unique", 0.0) / a.steps
     uniq_gbs = last.get("unique_bytes", 0) / (uniq_ms * 1e-3) / 1e9 if uniq_ms > 0 else None
     boot_ms = stage_ms.get("bootstrap_1d", 0.0) / a.steps
+    traffic, traffic_src = ncu_traffic(seg.nnz)
     roofline = {"kernel": "mm_seg_moments (per-(gene,group) sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2)",
                 "bound": "hbm", "achieved": mom_gbs, "peak": peak, "unit": "GB/s", "frac": mom_gbs / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": mom_bytes,
-                "kernel_ms": mom_ms, "nnz": seg.nnz}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes": mom_bytes, "kernel_ms": mom_ms, "nnz": seg.nnz}
     stages = {k: v / a.steps for k, v in stage_ms.items()}
     extra = {
         "stage_ms_per_step": stages,
@@ -319,8 +341,10 @@ def run_ours(a):
                "config": config_dict(a, len(groups), G, {
                    "parallelism": "gene-sharded x%d (10k-gene block of the same cells per GPU; all-reduce of UMI "
                                   "totals + all-gather of moment vectors in setup only, none in the timed step)" % world,
-                   "l2": "inputs larger than L2: group-sorted matrix %.0f MB + %.0f MB of bootstrap rows per tile"
-                         % (seg.nnz * 8 / 1e6 if seg is not None else 0, 0)}),
+                   "l2": "inputs larger than L2: group-sorted matrix %.0f MB streamed per step, plus ~%.1f GB of "
+                         "bootstrap rows written and re-read per gene tile"
+                         % (seg.nnz * 8 / 1e6 if seg is not None else 0,
+                            min(G, engine_tile_genes(seg, a.num_boot)) * seg.R * (a.num_boot + 1) * 32 / 1e9)}),
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clk}
         out.update(extra)

@@ -52,6 +52,26 @@ int mm_seg_moments(int device, void* stream, const float* vals, const int32_t* r
                    const int64_t* seg_ptr, int64_t n_seg, int64_t nnz, const double* inv_sf,
                    int64_t n_cells, double* out, int32_t* big_list, const int32_t* chunk_seg, double* edge);
 
+/* Dense gene block on the tensor cores, step 1: the fp16 operand panels of one group.  For every listed gene i
+ * (gene_idx[i], n_genes of them) and every cell c of group `group` (renumbered rows row0 .. row0 + n_cells - 1),
+ *   z = (x_ci / sf_c - center[i]) * inv_scale[i]      (float64),   z_hi = fp16(z),   z_lo = fp16((z - z_hi) * 2^11)
+ * written K-major as z_hi[i * k_pad + (c - row0)], zero-padded to k_pad (a multiple of 64, >= n_cells).
+ * center = the group mean of x / sf, inv_scale = a power of two that makes z O(1). */
+int mm_block_panels(int device, void* stream, const float* vals, const int32_t* rows, const int64_t* seg_ptr,
+                    int32_t R, int32_t group, int64_t row0, int32_t n_cells, const double* inv_sf,
+                    const int32_t* gene_idx, int32_t n_genes, const double* center, const double* inv_scale,
+                    int32_t k_pad, void* z_hi, void* z_lo);
+
+/* Dense gene block, step 2: out[a * ldo + b] = scale_a[a] * scale_b[b] * sum_k z_a[k] z_b[k] for a < m, b < n, with
+ * z = z_hi + 2^-11 z_lo, as three fp16 tcgen05.mma products (hi hi, hi lo, lo hi) accumulated in fp32 in tensor
+ * memory: TMA-loaded 128-byte-swizzled 128 x 64 tiles, 128 x 128 output tile per CTA, float64 epilogue.
+ * With the panels of mm_block_panels this is n times the plug-in covariance of every gene pair of the block.
+ * Replaces: memento/estimator.py:226-231 (_hyper_cov_relative on an A x B block of pairs) and :254-259
+ * (_hyper_corr_symmetric: sparse X^T D^2 X densified to G x G). */
+int mm_block_gemm(int device, void* stream, const void* a_hi, const void* a_lo, int32_t m, const void* b_hi,
+                  const void* b_lo, int32_t n, int32_t k_pad, const double* scale_a, const double* scale_b,
+                  double* out, int64_t ldo);
+
 /* Covariance sums of gene pairs within every group: for pair k and group r,
  *   out[k*R + r] = sum over cells of the group of x_{c,i} * x_{c,j} / sf_c^2
  * by a merge join of the two sorted row-id lists.

@@ -1,0 +1,309 @@
+// Dense gene-block covariance on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces, for gene_pairs = A x B (a dense block: C3 of BASELINE.json, 1.5k TFs x 10k targets, and the
+// all-by-all get_corr_matrix), reference estimator.py:220-233 (_hyper_cov_relative, which materialises the
+// two Nc x n_pairs sparse operands) and estimator.py:236-270 (_hyper_corr_symmetric, a sparse-sparse product
+// densified to G x G): per group,
+//     S'[a][b] = sum_c (x_ca / sf_c - m_a) (x_cb / sf_c - m_b) = n * (sum_c x_ca x_cb / sf_c^2 / n - m_a m_b)
+// i.e. n times the plug-in covariance, as ONE GEMM Z_A Z_B^T over the cells of the group.
+//
+// Numerics (float64 results from fp16 tensor-core inputs).  The operands are CENTRED with the float64
+// group means (so the GEMM result is the covariance itself, not a difference of two large numbers) and
+// scaled by a power of two per (gene, group) so that they are O(1); each float64 value z is split into
+// z = hi + 2^-11 lo with hi = fp16(z), lo = fp16((z - hi) 2^11).  Three tensor-core products
+//     acc0 += hi_A hi_B^T,      acc1 += hi_A lo_B^T + lo_A hi_B^T
+// (products of fp16 numbers are exact in the fp32 accumulators) give S' = (acc0 + 2^-11 acc1) 2^(e_a + e_b)
+// with a relative error of ~2^-22 from the dropped lo lo term plus the fp32 accumulation error, both
+// relative to sum |z_a z_b| <= n sqrt(var_a var_b): correlations are good to ~1e-6 absolute.
+//
+// Kernel structure (one 128 x 128 output tile per CTA, cta_group::1, UMMA 128 x 128 x 16, kind::f16):
+//   warp 0   TMA producer: per 64-cell k-block four 16 KB tiles (hi/lo of A and B, K-major, 128-byte
+//            swizzle) into a kGemmStages ring, mbarrier complete_tx;
+//   warp 1   allocates all 512 TMEM columns (two buffers of two fp32 accumulators) and, from one lane,
+//            issues the 12 tcgen05.mma of a k-block; tcgen05.commit frees the ring slot / hands a finished
+//            256-cell chunk to the epilogue;
+//   warps 2-9 epilogue: tcgen05.ld of a chunk's accumulators (each warp its own 32-lane quarter and 64 of the
+//            128 columns), float64 accumulation over the chunks in registers (the tensor core's fp32
+//            accumulation truncates, see block_gemm_kernel), rescale, 128-bit stores of the float64 block.
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+
+namespace mm {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;     // tile: 128 x 128 outputs, 64 cells (128 bytes of fp16) per k-block
+constexpr int kUmmaK = 16;
+constexpr int kGemmStages = 3;
+constexpr int kOperandBytes = kBM * kBK * 2;      // 16 KB
+constexpr int kStageBytes = 4 * kOperandBytes;    // hi_A, lo_A, hi_B, lo_B
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = (2 + kEpiWarps) * 32;
+constexpr int kTmemCols = 512;                  // two buffers x (hi hi | hi lo + lo hi) x 128 fp32 columns
+constexpr int kChunkBlocks = 4;                 // k-blocks (of 64 cells) accumulated in fp32 before float64 takes over
+constexpr double kLoScale = 2048.0;               // 2^11
+
+// ------------------------------------------------------------------ panels
+// One CTA per listed gene: row = the cells of group `group` (renumbered rows [row0, row0 + n_cells)), padded
+// with zeros to k_pad.  Cells where the gene is zero hold the constant -center * inv_scale.
+__global__ void __launch_bounds__(128)
+block_panels_kernel(const float* __restrict__ vals, const int* __restrict__ rows, const long long* __restrict__ seg_ptr,
+                    int R, int group, long long row0, int n_cells, const double* __restrict__ inv_sf,
+                    const int* __restrict__ gene_idx, const double* __restrict__ center,
+                    const double* __restrict__ inv_scale, int k_pad, __half* __restrict__ z_hi,
+                    __half* __restrict__ z_lo) {
+    const int i = blockIdx.x;
+    const double c = center[i], is = inv_scale[i];
+    __half* hi = z_hi + (long long)i * k_pad;
+    __half* lo = z_lo + (long long)i * k_pad;
+    const double z0 = -c * is;
+    const __half h0 = __double2half(z0);
+    const __half l0 = __double2half((z0 - (double)__half2float(h0)) * kLoScale);
+    const __half zero = __float2half(0.f);
+    for (int k = threadIdx.x; k < k_pad; k += 128) {
+        hi[k] = k < n_cells ? h0 : zero;
+        lo[k] = k < n_cells ? l0 : zero;
+    }
+    __syncthreads();
+    const long long s = (long long)gene_idx[i] * R + group;
+    const long long a = seg_ptr[s], b = seg_ptr[s + 1];
+    for (long long e = a + threadIdx.x; e < b; e += 128) {
+        const int r = rows[e];
+        const double z = ((double)vals[e] * __ldg(inv_sf + r) - c) * is;
+        const __half h = __double2half(z);
+        const int k = (int)(r - row0);
+        hi[k] = h;
+        lo[k] = __double2half((z - (double)__half2float(h)) * kLoScale);
+    }
+}
+
+// ------------------------------------------------------------------ tcgen05 helpers
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    // K-major operand tile, 128-byte swizzle: 8-row groups 1024 bytes apart; descriptor version 1 (sm_100)
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// out[m][n] = scale_a[m] * scale_b[n] * sum over chunks of (acc0 + 2^-11 acc1), m < M, n < N.
+// The tensor core adds into its fp32 accumulator with truncation: on a sum of same-sign terms the error grows
+// like 1.4e-8 per accumulated cell (measured: 1.3e-4 at K = 12 000).  So a TMEM accumulator only ever sees
+// kChunkBlocks k-blocks (256 cells, error <= ~4e-6 of the chunk); the epilogue warps add the chunks up in
+// float64 registers while the MMA warp already fills the other accumulator pair (TMEM is double buffered:
+// 2 x (128 + 128) columns = all 512).
+__global__ void __launch_bounds__(kGemmThreads, 1)
+block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  int k_blocks, int M, int N, const double* __restrict__ scale_a, const double* __restrict__ scale_b,
+                  double* __restrict__ out, long long ldo, int vec_ok) {
+    extern __shared__ unsigned char smem_raw[];
+    // 128-byte-swizzled operand tiles need a 1024-byte aligned base (the launch adds 1 KB of slack)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.y, n_blk = blockIdx.x;
+    const int n_chunks = (k_blocks + kChunkBlocks - 1) / kChunkBlocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpiWarps); }
+        mbar_init_fence();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int s = kb % kGemmStages;
+                if (kb >= kGemmStages) mbar_wait(&empty_bar[s], ((kb / kGemmStages) & 1) ^ 1);
+                unsigned char* st = smem + (size_t)s * kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_2d(st, &map_a_hi, &full_bar[s], kb * kBK, m_blk * kBM);
+                tma_load_2d(st + kOperandBytes, &map_a_lo, &full_bar[s], kb * kBK, m_blk * kBM);
+                tma_load_2d(st + 2 * kOperandBytes, &map_b_hi, &full_bar[s], kb * kBK, n_blk * kBN);
+                tma_load_2d(st + 3 * kOperandBytes, &map_b_lo, &full_bar[s], kb * kBK, n_blk * kBN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = F16, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int buf = c & 1;
+                if (c >= 2) mbar_wait(&tmem_empty[buf], ((c >> 1) & 1) ^ 1);      // the epilogue has drained this pair
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc0 = tmem_base + buf * (2 * kBN), acc1 = acc0 + kBN;
+                const int kb_end = min(k_blocks, (c + 1) * kChunkBlocks);
+                for (int kb = c * kChunkBlocks; kb < kb_end; ++kb) {
+                    const int s = kb % kGemmStages;
+                    mbar_wait(&full_bar[s], (kb / kGemmStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t koff = k * kUmmaK * 2;       // bytes inside the 128-byte swizzled row
+                        const uint64_t a_hi = umma_desc(base + koff), a_lo = umma_desc(base + kOperandBytes + koff);
+                        const uint64_t b_hi = umma_desc(base + 2 * kOperandBytes + koff), b_lo = umma_desc(base + 3 * kOperandBytes + koff);
+                        const uint32_t acc = (kb > c * kChunkBlocks || k > 0) ? 1u : 0u;
+                        umma_f16(acc0, a_hi, b_hi, idesc, acc);               // acc0 (+)= hi hi
+                        umma_f16(acc1, a_hi, b_lo, idesc, acc);               // acc1 (+)= hi lo
+                        umma_f16(acc1, a_lo, b_hi, idesc, 1u);                // acc1 += lo hi
+                    }
+                    umma_commit(&empty_bar[s]);        // the ring slot is free once these MMAs have read it
+                }
+                umma_commit(&tmem_full[buf]);          // this accumulator pair is complete
+            }
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32 (w % 4), 32 (w % 4) + 32); two warps share a lane quarter and
+        // take 64 of the 128 columns each
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int m = m_blk * kBM + q * 32 + lane;
+        double acc[kBN / 2];
+#pragma unroll
+        for (int j = 0; j < kBN / 2; ++j) acc[j] = 0.0;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int buf = c & 1;
+            mbar_wait(&tmem_full[buf], (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * kBN) + half * (kBN / 2);
+#pragma unroll
+            for (int c0 = 0; c0 < kBN / 2; c0 += 16) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(trow + c0, r0);
+                tmem_ld16(trow + kBN + c0, r1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j)     // hi hi + 2^-11 (hi lo + lo hi) in fp32 (24 bits are enough for one chunk), then float64
+                    acc[c0 + j] += (double)fmaf(__uint_as_float(r1[j]), (float)(1.0 / kLoScale), __uint_as_float(r0[j]));
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        if (m < M) {
+            const double sa = scale_a[m];
+            double* orow = out + (long long)m * ldo;
+            const int n0 = n_blk * kBN + half * (kBN / 2);
+#pragma unroll
+            for (int j = 0; j < kBN / 2; j += 2) {
+                const int n = n0 + j;
+                if (n + 1 < N && vec_ok) {
+                    *reinterpret_cast<double2*>(orow + n) =
+                        make_double2(acc[j] * sa * __ldg(scale_b + n), acc[j + 1] * sa * __ldg(scale_b + n + 1));
+                } else {
+                    if (n < N) orow[n] = acc[j] * sa * __ldg(scale_b + n);
+                    if (n + 1 < N) orow[n + 1] = acc[j + 1] * sa * __ldg(scale_b + n + 1);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host: tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+
+// fp16 matrix [rows][k_pad], k contiguous; box = 64 x 128 with the 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int k_pad) {
+    auto fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return 2; }
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return 2; }
+    return 0;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+MM_EXPORT int mm_block_panels(int device, void* stream, const float* vals, const int32_t* rows, const int64_t* seg_ptr,
+                              int32_t R, int32_t group, int64_t row0, int32_t n_cells, const double* inv_sf,
+                              const int32_t* gene_idx, int32_t n_genes, const double* center, const double* inv_scale,
+                              int32_t k_pad, void* z_hi, void* z_lo) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(n_genes >= 0 && R > 0 && group >= 0 && group < R, "n_genes/R/group");
+    MM_REQUIRE(k_pad >= n_cells && k_pad % kBK == 0, "k_pad must be a multiple of 64 and >= n_cells");
+    if (n_genes == 0) return 0;
+    MM_REQUIRE(vals && rows && seg_ptr && inv_sf && gene_idx && center && inv_scale && z_hi && z_lo, "null pointer");
+    block_panels_kernel<<<n_genes, 128, 0, (cudaStream_t)stream>>>(vals, rows, (const long long*)seg_ptr, R, group, row0,
+                                                                  n_cells, inv_sf, gene_idx, center, inv_scale, k_pad,
+                                                                  (__half*)z_hi, (__half*)z_lo);
+    return check_launch("mm_block_panels");
+}
+
+MM_EXPORT int mm_block_gemm(int device, void* stream, const void* a_hi, const void* a_lo, int32_t m, const void* b_hi,
+                            const void* b_lo, int32_t n, int32_t k_pad, const double* scale_a, const double* scale_b,
+                            double* out, int64_t ldo) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(m >= 0 && n >= 0 && k_pad > 0 && k_pad % kBK == 0 && ldo >= n, "m/n/k_pad/ldo");
+    if (m == 0 || n == 0) return 0;
+    MM_REQUIRE(a_hi && a_lo && b_hi && b_lo && scale_a && scale_b && out, "null pointer");
+    MM_REQUIRE((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) & 15) == 0,
+               "operand panels must be 16-byte aligned");
+    const int vec_ok = (((uintptr_t)out & 15) == 0 && (ldo & 1) == 0) ? 1 : 0;     // 128-bit stores of the block
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    if (int s = make_map(&ma_hi, a_hi, m, k_pad)) return s;
+    if (int s = make_map(&ma_lo, a_lo, m, k_pad)) return s;
+    if (int s = make_map(&mb_hi, b_hi, n, k_pad)) return s;
+    if (int s = make_map(&mb_lo, b_lo, n, k_pad)) return s;
+    const size_t smem = (size_t)kGemmStages * kStageBytes + 1024;     // + slack for the 1024-byte alignment
+    MM_CUDA(cudaFuncSetAttribute(block_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n + kBN - 1) / kBN, (m + kBM - 1) / kBM);
+    block_gemm_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k_pad / kBK, m, n,
+                                                                         scale_a, scale_b, out, ldo, vec_ok);
+    return check_launch("mm_block_gemm");
+}

@@ -228,6 +228,60 @@ class SegMatrix:
         """Algorithmic bytes of one mm_seg_moments launch."""
         return self.nnz * 8 + (self.n_seg + 1) * 8 + self.n_cells * 8 + 5 * self.n_seg * 8
 
+    # ------------------------------------------------------------------ dense gene block (tensor cores)
+    BLOCK_K = 64   # must match kBK in csrc/block.cu
+
+    def block_cross(self, idx_a, idx_b, inv_sf, sums, groups=None, timer=NULL_TIMER):
+        """Centred cross products of a dense gene block on the tensor cores (csrc/block.cu):
+        out[r, a, b] = sum over the cells c of group r of (x_ca / sf_c - m_a)(x_cb / sf_c - m_b), i.e. n_r times the
+        plug-in covariance (reference estimator.py:226-231 / :254-259).  ``idx_a`` / ``idx_b``: gene indices
+        (numpy int arrays); ``sums``: the (5, G, R) device tensor of ``moments``; ``groups``: group indices
+        (default all).  Returns a float64 device tensor (len(groups), |A|, |B|)."""
+        dev = self.device
+        groups = list(range(self.R)) if groups is None else list(groups)
+        ia = torch.as_tensor(np.ascontiguousarray(idx_a, dtype=np.int32), device=dev)
+        same = idx_b is idx_a or (len(idx_a) == len(idx_b) and np.array_equal(idx_a, idx_b))
+        ib = ia if same else torch.as_tensor(np.ascontiguousarray(idx_b, dtype=np.int32), device=dev)
+        na, nb = int(ia.numel()), int(ib.numel())
+        out = torch.empty((len(groups), na, nb), dtype=torch.float64, device=dev)
+        gs = self.group_start_host
+        k_max = max(int(gs[r + 1] - gs[r]) for r in groups)
+        k_cap = max(self.BLOCK_K, (k_max + self.BLOCK_K - 1) // self.BLOCK_K * self.BLOCK_K)
+        pa = torch.empty((2, na, k_cap), dtype=torch.float16, device=dev)
+        pb = pa if same else torch.empty((2, nb, k_cap), dtype=torch.float16, device=dev)
+
+        def scaling(idx, r, n):
+            # centre = group mean of x / sf; scale = power of two nearest to the centred root mean square
+            m = sums[2][idx.long(), r] / n
+            second = sums[4][idx.long(), r] / n - m * m
+            e = torch.where(second > 0, torch.round(0.5 * torch.log2(second.clamp(min=1e-300))), torch.zeros_like(second))
+            e = e.clamp(-200, 200)
+            return m.contiguous(), torch.exp2(-e).contiguous(), torch.exp2(e).contiguous()
+
+        ev = timer.start()
+        for j, r in enumerate(groups):
+            n = int(gs[r + 1] - gs[r])
+            k_pad = max(self.BLOCK_K, (n + self.BLOCK_K - 1) // self.BLOCK_K * self.BLOCK_K)
+            ca, inv_a, sc_a = scaling(ia, r, float(n))
+            za = pa.view(-1)[:2 * na * k_pad].view(2, na, k_pad)
+            _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
+                      ia, na, ca, inv_a, k_pad, za[0], za[1])
+            if same:
+                zb, sc_b = za, sc_a
+            else:
+                cb, inv_b, sc_b = scaling(ib, r, float(n))
+                zb = pb.view(-1)[:2 * nb * k_pad].view(2, nb, k_pad)
+                _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
+                          ib, nb, cb, inv_b, k_pad, zb[0], zb[1])
+            _lib.call("mm_block_gemm", dev, za[0], za[1], na, zb[0], zb[1], nb, k_pad, sc_a, sc_b, out[j], nb)
+        timer.stop("block_cross", ev)
+        return out
+
+    @staticmethod
+    def block_flops(n_a, n_b, n_cells_per_group):
+        """Tensor-core flops of block_cross: three fp16 products per (a, b, cell)."""
+        return 3 * 2.0 * n_a * n_b * float(sum((int(n) + 63) // 64 * 64 for n in n_cells_per_group))
+
     def pair_products(self, idx1, idx2, inv_sf, timer=NULL_TIMER):
         n = int(idx1.numel())
         out = torch.empty(n * self.R, dtype=torch.float64, device=self.device)

@@ -465,16 +465,30 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
     idx2 = pos.loc[[b for _, b in gene_pairs]].values.astype(int)
     out = {"gene_pairs": gene_pairs, "gene_idx_1": idx1, "gene_idx_2": idx2}
     n_cells = np.diff(st.group_start).astype(np.float64)
-    i1_d = to_device(idx1, st.device, np.int32)
-    i2_d = to_device(idx2, st.device, np.int32)
-    prod = st.seg.pair_products(i1_d, i2_d, st.inv_sf_sorted, st.timer).cpu().numpy()      # (n_pairs, R)
-    sums = st.seg.moments(st.inv_sf_sorted, st.timer).cpu().numpy()                         # (5, G, R)
+    sums_d = st.seg.moments(st.inv_sf_sorted, st.timer)                                     # (5, G, R) on the device
+    sums = sums_d.cpu().numpy()
     same = idx1 == idx2
+    block = _as_dense_block(idx1, idx2)
+    if block is not None:
+        # gene_pairs is a full A x B block: one tensor-core GEMM per group instead of a merge join per pair
+        genes_a, genes_b, pos = block
+        cross = st.seg.block_cross(genes_a, genes_b, st.inv_sf_sorted, sums_d, timer=st.timer)    # (R, |A|, |B|)
+        cross = cross.reshape(len(groups), -1)
+        pos_d = None if pos is None else to_device(pos, st.device, np.int64)
+    else:
+        i1_d = to_device(idx1, st.device, np.int32)
+        i2_d = to_device(idx2, st.device, np.int32)
+        prod = st.seg.pair_products(i1_d, i2_d, st.inv_sf_sorted, st.timer).cpu().numpy()  # (n_pairs, R)
     for r, g in enumerate(groups):
         q = mem["group_q"][g]
-        p = prod[:, r] / n_cells[r]
-        p[same] = p[same] - (1 - q) * sums[3][idx1[same], r] / n_cells[r]                 # estimator.py:229-230
-        cov = p - (sums[2][idx1, r] / n_cells[r]) * (sums[2][idx2, r] / n_cells[r])        # :231
+        if block is not None:
+            c = cross[r] if pos_d is None else cross[r][pos_d]
+            cov = c.cpu().numpy() / n_cells[r]                                             # centred: :226-231 in one step
+            cov[same] = cov[same] - (1 - q) * sums[3][idx1[same], r] / n_cells[r]         # estimator.py:229-230
+        else:
+            p = prod[:, r] / n_cells[r]
+            p[same] = p[same] - (1 - q) * sums[3][idx1[same], r] / n_cells[r]             # estimator.py:229-230
+            cov = p - (sums[2][idx1, r] / n_cells[r]) * (sums[2][idx2, r] / n_cells[r])    # :231
         var_1 = mem["1d_moments"][g][1][idx1]
         var_2 = mem["1d_moments"][g][1][idx2]
         out[g] = {"cov": cov, "corr": _corr_from_cov(cov, var_1, var_2), "var_1": var_1, "var_2": var_2}
@@ -483,11 +497,32 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
         return adata
 
 
+DENSE_BLOCK_MIN_PAIRS = 4096     # below this the per-pair merge join is cheaper than building the panels
+
+
+def _as_dense_block(idx1, idx2):
+    """If the pairs are exactly the product A x B of two gene lists (in any order), return (A, B, pos) with
+    pos[k] = position of pair k in the row-major A x B block (None when the pairs already are in that
+    order, i.e. itertools.product(A, B)); otherwise None."""
+    n = idx1.shape[0]
+    if n < DENSE_BLOCK_MIN_PAIRS:
+        return None
+    genes_a, pa = np.unique(idx1, return_inverse=True)
+    genes_b, pb = np.unique(idx2, return_inverse=True)
+    if genes_a.size * genes_b.size != n:
+        return None
+    pos = pa.astype(np.int64) * genes_b.size + pb
+    if np.unique(pos).size != n:
+        return None
+    if np.array_equal(pos, np.arange(n)):
+        pos = None
+    return genes_a.astype(np.int64), genes_b.astype(np.int64), pos
+
+
 def get_corr_matrix(adata, group, block=1 << 18):
     """All-by-all correlation matrix of one group.  reference: main.py:277-291 ->
-    estimator.py:236-270 (_hyper_corr_symmetric: sparse X^T D^2 X densified).  Here the upper triangle
-    is computed pair by pair with mm_pair_products in blocks; the dense tensor-core block kernel for
-    large gene sets is a later row of the scope table."""
+    estimator.py:236-270 (_hyper_corr_symmetric: sparse X^T D^2 X densified).  One tensor-core GEMM over
+    the cells of the group (mm_block_panels + mm_block_gemm); tiny gene sets use mm_pair_products."""
     mem = adata.uns["memento"]
     st = _state(adata)
     st.ensure_resident()
@@ -496,20 +531,26 @@ def get_corr_matrix(adata, group, block=1 << 18):
     G = adata.shape[1]
     n = float(st.group_start[r + 1] - st.group_start[r])
     q = mem["group_q"][group]
-    sums = st.seg.moments(st.inv_sf_sorted, st.timer).cpu().numpy()[:, :, r]      # (5, G)
-    iu, ju = np.triu_indices(G)
-    prod = np.empty(iu.shape[0])
-    for lo in range(0, iu.shape[0], block):
-        i1 = to_device(iu[lo:lo + block], st.device, np.int32)
-        i2 = to_device(ju[lo:lo + block], st.device, np.int32)
-        prod[lo:lo + block] = st.seg.pair_products(i1, i2, st.inv_sf_sorted, st.timer)[:, r].cpu().numpy()
-    P = np.zeros((G, G))
-    P[iu, ju] = prod / n
-    P[ju, iu] = prod / n
+    sums_d = st.seg.moments(st.inv_sf_sorted, st.timer)
+    sums = sums_d.cpu().numpy()[:, :, r]                                          # (5, G)
     d = np.arange(G)
-    P[d, d] -= (1 - q) * sums[3] / n                                              # estimator.py:256
-    mean = sums[2] / n
-    cov = P - np.outer(mean, mean)
+    if G * G >= DENSE_BLOCK_MIN_PAIRS:
+        # centred X^T D^2 X of the group as one tensor-core GEMM (csrc/block.cu)
+        cov = st.seg.block_cross(d, d, st.inv_sf_sorted, sums_d, groups=[r], timer=st.timer)[0].cpu().numpy() / n
+        cov[d, d] -= (1 - q) * sums[3] / n                                        # estimator.py:256
+    else:
+        iu, ju = np.triu_indices(G)
+        prod = np.empty(iu.shape[0])
+        for lo in range(0, iu.shape[0], block):
+            i1 = to_device(iu[lo:lo + block], st.device, np.int32)
+            i2 = to_device(ju[lo:lo + block], st.device, np.int32)
+            prod[lo:lo + block] = st.seg.pair_products(i1, i2, st.inv_sf_sorted, st.timer)[:, r].cpu().numpy()
+        P = np.zeros((G, G))
+        P[iu, ju] = prod / n
+        P[ju, iu] = prod / n
+        P[d, d] -= (1 - q) * sums[3] / n                                          # estimator.py:256
+        mean = sums[2] / n
+        cov = P - np.outer(mean, mean)
     var = mem["1d_moments"][group][1]
     with np.errstate(invalid="ignore"):
         denom = np.sqrt(np.outer(var, var))                                        # :263 (original var)

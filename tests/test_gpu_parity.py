@@ -594,5 +594,29 @@ def test_ht_2d_vs_reference_and_oracle(st, gpu_prepared, oracle_prepared):
 def test_get_corr_matrix_vs_reference(st, gpu_prepared):
     """All-by-all correlation of one group against the reference's _hyper_corr_symmetric."""
     mem = gpu_prepared.uns["memento"]
+    from memento_b200 import main as mm_main
+    # tensor-core block path (fp16 hi/lo operands, chunked fp32 accumulation): the covariance is good to 5e-6 of
+    # sqrt(plain_var_i plain_var_j); the estimator's variances subtract the sampling noise, so a correlation
+    # carries that error amplified by plain / corrected standard deviations
     cm = memento.get_corr_matrix(gpu_prepared, mem["groups"][1])
+    ref = st["corr_matrix_g1"]
+    dst = mem["_b200"]
+    sums = dst.seg.moments(dst.inv_sf_sorted).cpu().numpy()[:, :, 1]
+    n = float(dst.group_start[2] - dst.group_start[1])
+    plain = sums[4] / n - (sums[2] / n) ** 2
+    var = mem["1d_moments"][mem["groups"][1]][1]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        amp = np.sqrt(np.outer(plain, plain) / np.outer(var, var))
+    both = np.isfinite(ref) & np.isfinite(cm) & np.isfinite(amp)
+    assert (np.abs(cm[both] - ref[both]) <= 5e-6 * amp[both] + 1e-12).all()
+    # NaN entries (variance <= 0, or a raw value beyond the 1.05 cut-off of estimator.py:265-268) agree, except
+    # where the raw value sits on the cut-off itself
+    assert (np.isnan(cm) != np.isnan(ref)).mean() < 1e-3
+    # per-pair float64 path
+    old = mm_main.DENSE_BLOCK_MIN_PAIRS
+    mm_main.DENSE_BLOCK_MIN_PAIRS = 1 << 62
+    try:
+        cm = memento.get_corr_matrix(gpu_prepared, mem["groups"][1])
+    finally:
+        mm_main.DENSE_BLOCK_MIN_PAIRS = old
     assert_close(cm, st["corr_matrix_g1"], 1e-8, atol=1e-11)
