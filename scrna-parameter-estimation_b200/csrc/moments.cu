@@ -539,7 +539,7 @@ __device__ __forceinline__ double warp_sum4(double sx, double s1, double s2, dou
     return keep;      // lanes 0-7: sum sx, 8-15: sum s1, 16-23: sum s2, 24-31: sum s3
 }
 
-template <bool kSmemTable, int kStreamThreads, bool kPrefetch>
+template <bool kSmemTable, int kStreamThreads, bool kPrefetch, int kC>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict__ rows,
                           const long long* __restrict__ seg_ptr, long long n_seg, long long nnz,
@@ -554,16 +554,19 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
-    const long long n_spans = (nnz + kSpanElems - 1) / kSpanElems;
+    // A warp owns chunks of kC consecutive spans and carries its accumulators from span to span, so only the
+    // two ends of a chunk can leave partial sums for the edge kernel.
+    constexpr int kChunkElems = kC * kSpanElems;
+    const long long n_spans = (nnz + kChunkElems - 1) / kChunkElems;            // chunks ("span" below = chunk index)
     const long long warps_total = (long long)gridDim.x * (kStreamThreads / 32);
-    // Boundary metadata is fetched one span ahead (it is a chain of two dependent loads: the first segment
-    // of the span from chunk_seg, then the segment starts from seg_ptr), so it never stalls the reduction.
-    auto first_seg = [&](long long sp) -> int { return (sp <= 0 || sp >= n_spans) ? 0 : __ldg(chunk_seg + sp); };
-    auto last_seg = [&](long long sp) -> int { return sp + 1 < n_spans ? __ldg(chunk_seg + sp + 1) : (int)(n_seg - 1); };
-    // lane k: clamped span-relative start of piece base + k of span sp (pieces = segments s0 .. s0 + np - 1)
+    // Boundary metadata is fetched one chunk ahead (it is a chain of two dependent loads: the first segment
+    // of the chunk from chunk_seg, then the segment starts from seg_ptr), so it never stalls the reduction.
+    auto first_seg = [&](long long sp) -> int { return (sp <= 0 || sp >= n_spans) ? 0 : __ldg(chunk_seg + sp * kC); };
+    auto last_seg = [&](long long sp) -> int { return sp + 1 < n_spans ? __ldg(chunk_seg + (sp + 1) * kC) : (int)(n_seg - 1); };
+    // lane k: clamped chunk-relative start of piece base + k of chunk sp (pieces = segments s0 .. s0 + np - 1)
     auto window = [&](long long sp, int s0, int np, int base) -> int {
-        const long long t0 = sp * kSpanElems;
-        const int nn = (int)((nnz - t0 < kSpanElems) ? (nnz - t0) : kSpanElems);
+        const long long t0 = sp * kChunkElems;
+        const int nn = (int)((nnz - t0 < kChunkElems) ? (nnz - t0) : kChunkElems);
         const int k = base + lane;
         long long p = (sp < n_spans && k <= np) ? __ldg(seg_ptr + (long long)s0 + k) - t0 : (long long)nn + 1;
         return p < 0 ? -1 : (p > nn ? nn + 1 : (int)p);
@@ -573,32 +576,8 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
     int bl = window(span, s0, s1 - s0 + 1, 0);
     int s0_nx = first_seg(span + warps_total), s1_nx = last_seg(span + warps_total);
     for (; span < n_spans; span += warps_total) {
-        const long long t_lo = span * kSpanElems;
-        const int n = (int)((nnz - t_lo < kSpanElems) ? (nnz - t_lo) : kSpanElems);
-        // ---- the warp's next span goes to L2 now (one 128-byte line per lane and array): a register-free
-        // second buffer, so that the loads below are L2 hits instead of HBM round trips
-        if (kPrefetch) {
-            const long long p_lo = (span + warps_total) * kSpanElems + 32 * lane;
-            if (p_lo + 32 <= nnz) { prefetch_l2(vals + p_lo); prefetch_l2(rows + p_lo); }
-        }
-        // ---- all streaming loads of the span: lane owns elements 128 q + 4 lane + {0..3}, q = 0..3
-        float4 v[4];
-        int4 r[4];
-        if (n == kSpanElems) {
-            const float4* v4 = reinterpret_cast<const float4*>(vals + t_lo) + lane;
-            const int4* r4 = reinterpret_cast<const int4*>(rows + t_lo) + lane;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { v[q] = ld_stream4(v4 + 32 * q); r[q] = ld_stream4(r4 + 32 * q); }
-        } else {     // ragged end of the arrays
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int e = 128 * q + 4 * lane;
-                v[q].x = e < n ? vals[t_lo + e] : 0.f;         r[q].x = e < n ? rows[t_lo + e] : 0;
-                v[q].y = e + 1 < n ? vals[t_lo + e + 1] : 0.f; r[q].y = e + 1 < n ? rows[t_lo + e + 1] : 0;
-                v[q].z = e + 2 < n ? vals[t_lo + e + 2] : 0.f; r[q].z = e + 2 < n ? rows[t_lo + e + 2] : 0;
-                v[q].w = e + 3 < n ? vals[t_lo + e + 3] : 0.f; r[q].w = e + 3 < n ? rows[t_lo + e + 3] : 0;
-            }
-        }
+        const long long t_lo = span * kChunkElems;
+        const int n = (int)((nnz - t_lo < kChunkElems) ? (nnz - t_lo) : kChunkElems);
         // ---- metadata of the next spans (in flight during this span's reduction)
         const int bl_nx = window(span + warps_total, s0_nx, s1_nx - s0_nx + 1, 0);
         const int s0_nn = first_seg(span + 2 * warps_total), s1_nn = last_seg(span + 2 * warps_total);
@@ -634,9 +613,37 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
             advance();
         }
         int from = 0;
+#pragma unroll 1
+        for (int j = 0; j < kC; ++j) {
+        const int sp_lo = j * kSpanElems;                    // first element of this span inside the chunk
+        if (sp_lo >= n) break;
+        // ---- the next span (of this chunk, or the first of the warp's next chunk) goes to L2 now (one 128-byte
+        // line per lane and array): a register-free second buffer, so that its loads are L2 hits
+        if (kPrefetch) {
+            const long long p_lo = (j + 1 < kC ? t_lo + sp_lo + kSpanElems : (span + warps_total) * kChunkElems) + 32 * lane;
+            if (p_lo + 32 <= nnz) { prefetch_l2(vals + p_lo); prefetch_l2(rows + p_lo); }
+        }
+        // ---- all streaming loads of the span: lane owns elements 128 q + 4 lane + {0..3}, q = 0..3
+        float4 v[4];
+        int4 r[4];
+        if (n - sp_lo >= kSpanElems) {
+            const float4* v4 = reinterpret_cast<const float4*>(vals + t_lo + sp_lo) + lane;
+            const int4* r4 = reinterpret_cast<const int4*>(rows + t_lo + sp_lo) + lane;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { v[q] = ld_stream4(v4 + 32 * q); r[q] = ld_stream4(r4 + 32 * q); }
+        } else {     // ragged end of the arrays
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = sp_lo + 128 * q + 4 * lane;
+                v[q].x = e < n ? vals[t_lo + e] : 0.f;         r[q].x = e < n ? rows[t_lo + e] : 0;
+                v[q].y = e + 1 < n ? vals[t_lo + e + 1] : 0.f; r[q].y = e + 1 < n ? rows[t_lo + e + 1] : 0;
+                v[q].z = e + 2 < n ? vals[t_lo + e + 2] : 0.f; r[q].z = e + 2 < n ? rows[t_lo + e + 2] : 0;
+                v[q].w = e + 3 < n ? vals[t_lo + e + 3] : 0.f; r[q].w = e + 3 < n ? rows[t_lo + e + 3] : 0;
+            }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int row_lo = 128 * q, row_hi = 128 * q + 128;
+            const int row_lo = sp_lo + 128 * q, row_hi = row_lo + 128;
             const int e0 = row_lo + 4 * lane;
             double w0, w1, w2, w3;
             if constexpr (kSmemTable) { w0 = s_w[r[q].x]; w1 = s_w[r[q].y]; w2 = s_w[r[q].z]; w3 = s_w[r[q].w]; }
@@ -665,7 +672,8 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
                 if (cur >= np || from >= n || from >= row_hi) break;
             }
         }
-        // the last piece continues after the span
+        }
+        // the last piece continues after the chunk
         if (cur < np && from < n) emit(true);
         s0 = s0_nx; s1 = s1_nx; bl = bl_nx;
         s0_nx = s0_nn; s1_nx = s1_nn;
@@ -841,25 +849,25 @@ static int launch_tile(cudaStream_t st, int n_sm, int regime, const float* vals,
     return check_launch("seg_moments_edge");
 }
 
-template <int kThreads, bool kPrefetch>
+template <int kThreads, bool kPrefetch, int kC>
 static int launch_stream(cudaStream_t st, int n_sm, const float* vals, const int32_t* rows, const long long* sp,
                          long long n_seg, long long nnz, const int32_t* chunk_seg, const double* inv_sf,
                          long long n_cells, double* out, double* edge, bool smem_table) {
-    const long long n_spans = (nnz + kSpanElems - 1) / kSpanElems;
+    const long long n_spans = (nnz + kC * kSpanElems - 1) / (kC * kSpanElems);      // chunks of kC spans
     long long grid = n_sm;
     const long long need = (n_spans + kThreads / 32 - 1) / (kThreads / 32);
     if (grid > need) grid = need;
     if (smem_table) {
         const size_t smem = (size_t)n_cells * sizeof(double);
-        MM_CUDA(cudaFuncSetAttribute(seg_moments_stream_kernel<true, kThreads, kPrefetch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        seg_moments_stream_kernel<true, kThreads, kPrefetch><<<(unsigned)grid, kThreads, smem, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
+        MM_CUDA(cudaFuncSetAttribute(seg_moments_stream_kernel<true, kThreads, kPrefetch, kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        seg_moments_stream_kernel<true, kThreads, kPrefetch, kC><<<(unsigned)grid, kThreads, smem, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
                                                                                         inv_sf, (int)n_cells, out, edge);
     } else {
-        seg_moments_stream_kernel<false, kThreads, kPrefetch><<<(unsigned)grid, kThreads, 0, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
+        seg_moments_stream_kernel<false, kThreads, kPrefetch, kC><<<(unsigned)grid, kThreads, 0, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
                                                                                       inv_sf, (int)n_cells, out, edge);
     }
     if (int s = check_launch("seg_moments_stream")) return s;
-    seg_moments_edge_kernel<kSpanElems><<<(unsigned)((n_spans + 255) / 256), 256, 0, st>>>(sp, n_seg, nnz, chunk_seg, edge, out);
+    seg_moments_edge_kernel<kC * kSpanElems><<<(unsigned)((n_spans + 255) / 256), 256, 0, st>>>(sp, n_seg, nnz, chunk_seg, edge, out);
     return check_launch("seg_moments_edge");
 }
 
@@ -897,8 +905,10 @@ MM_EXPORT int mm_seg_moments(int device, void* stream, const float* vals, const 
             bool pf = true;
             if (const char* ov = getenv("MM_MOMENTS_THREADS")) threads = atoi(ov);      // tuning hooks
             if (const char* ov = getenv("MM_MOMENTS_PREFETCH")) pf = atoi(ov) != 0;
-#define MM_STREAM(T, PF) launch_stream<T, PF>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table)
-            if (threads == 1024) return pf ? MM_STREAM(1024, true) : MM_STREAM(1024, false);
+            int chunk_spans = 4;
+            if (const char* ov = getenv("MM_MOMENTS_CHUNK")) chunk_spans = atoi(ov) == 1 ? 1 : 4;
+#define MM_STREAM(T, PF) (chunk_spans == 1 ? launch_stream<T, PF, 1>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
+                                           : launch_stream<T, PF, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table))
             if (threads == 768) return pf ? MM_STREAM(768, true) : MM_STREAM(768, false);
             if (threads == 512) return pf ? MM_STREAM(512, true) : MM_STREAM(512, false);
             return pf ? MM_STREAM(640, true) : MM_STREAM(640, false);

@@ -59,6 +59,7 @@ CASES = {
     "exact_tile_edges": [4096, 4096, 0, 0, 8192, 1, 4095, 0],
     "exact_span_edges": [512, 512, 0, 1024, 1, 511, 0, 0, 513, 511, 0, 512 * 3, 0],
     "window_of_31": [0] * 30 + [2] + [0] * 31 + [3, 0] + [1] * 70 + [0] * 33 + [600],
+    "exact_chunk_edges": [2048, 2048, 0, 4096, 1, 2047, 0, 0, 2049, 2047, 512, 1536, 0],
     "multi_tile_segments": [10, 20000, 3, 0, 12289, 4093, 5, 0, 0, 30000, 2],
     "ragged_end": [4096 * 2 + 1],
     "ragged_end3": [5000, 4096 * 3 - 5000 + 3],
@@ -95,6 +96,13 @@ def test_seg_moments_tile_regimes(regime, monkeypatch):
     monkeypatch.setenv("MM_MOMENTS_REGIME", regime)
     for name in ("mixed", "exact_tile_edges", "multi_tile_segments", "many_small"):
         _run(CASES[name], seed=6)
+
+
+@pytest.mark.parametrize("name", ["exact_span_edges", "window_of_31", "multi_tile_segments", "ragged_end3", "mixed"])
+def test_seg_moments_stream_single_span_chunks(name, monkeypatch):
+    monkeypatch.setenv("MM_MOMENTS_KERNEL", "stream")
+    monkeypatch.setenv("MM_MOMENTS_CHUNK", "1")
+    _run(CASES[name], seed=8)
 
 
 def test_seg_moments_table_too_large_for_smem(monkeypatch):
