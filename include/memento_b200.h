@@ -187,12 +187,15 @@ int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
  * approx != 0 -> two-sided normal tail; else extreme count c and (c+1)/(n+1) (out_extreme carries c
  * for the GEV tail stage).  boot1 may be NULL (one statistic).  coef_ws (nullable) receives the
  * coefficient rows [n_gene][n_stat][T][num_boot+1].  Outputs [n_gene][n_stat][T].
+ * n_split >= 1: CTAs per gene; with n_split > 1 the replicate columns of a gene are split between them
+ * (for tiles with few genes and thousands of groups) and split_ws (float64 scratch of
+ * n_gene * n_split * n_stat * T * 8) carries their partial statistics to a deterministic combine step.
  * Replaces: memento/hypothesis_test.py:242-300 (_regress_1d), :367-414 (_regress_2d), :57-92. */
 int mm_regress_asl(int device, void* stream, const double* boot0, const double* boot1,
                    const uint8_t* seg_good, const int32_t* mask_id, const double* cmat,
                    int32_t n_gene, int32_t R, int32_t T, int32_t num_boot, int32_t approx,
                    double* coef_ws, double* out_coef, double* out_se, double* out_asl,
-                   int32_t* out_extreme, int32_t* out_nnull);
+                   int32_t* out_extreme, int32_t* out_nnull, int32_t n_split, double* split_ws);
 
 /* GEV tail refinement of the ASL for the tests listed in `flagged` (row ids into coef_rows / asl):
  * sorts the null (coef_rows[row][1..] - coef_rows[row][0], finite entries), fits a generalised extreme

@@ -236,12 +236,39 @@ struct RegParams {
     double* out_asl;
     int* out_extreme;           // [n_gene][n_stat][T] extreme count (-1 when not applicable)
     int* out_nnull;             // [n_gene][n_stat][T] null size
+    int n_split;                // CTAs per gene (replicate columns are split between them)
+    double* split_ws;           // [n_gene][n_split][n_stat][T][8] partial statistics when n_split > 1
 };
 
 // TT = treatment columns per pass (1, 2 or TT): the per-thread statistics are TT-sized register arrays, so
 // the common single-treatment test runs at 4x the occupancy of the general one.  The loop over the groups
 // loads four groups x both statistics before the FMAs, so every thread keeps 8 independent HBM reads in
 // flight (one replicate column per thread: the reads of a warp are contiguous 256-byte rows).
+// ASL / SE of one (gene, statistic, treatment column) from the statistics of its null (reference
+// hypothesis_test.py:57-92, 297-298)
+__device__ __forceinline__ void regress_finish(const RegParams& P, long long o, double stat, double a, double b2, int h,
+                                               int l, double vmin, double vmax, int n) {
+    double mu = a / n, var = b2 / n - mu * mu;
+    if (var < 0) var = 0;
+    double sd = sqrt(var);
+    double asl;
+    int extreme = -1;
+    if (!(vmin < vmax)) {
+        asl = nan("");   // all coefficients identical (reference :62-64)
+    } else if (P.approx) {
+        double astat = fabs(stat), k = 1.0 / (sd * 1.4142135623730951);
+        asl = 0.5 * erfc((astat - mu) * k) + 0.5 * erfc((astat + mu) * k);   // :79-83
+    } else {
+        extreme = h + l;
+        asl = (double)(extreme + 1) / (double)(n + 1);                        // :92 (and the GEV fallback)
+    }
+    P.out_coef[o] = stat;
+    P.out_se[o] = (n > 0) ? sd : nan("");
+    P.out_asl[o] = asl;
+    P.out_extreme[o] = extreme;
+    P.out_nnull[o] = n;
+}
+
 template <int TT>
 __global__ void __launch_bounds__(kRegThreads)
 regress_asl_kernel(RegParams P) {
@@ -271,7 +298,7 @@ regress_asl_kernel(RegParams P) {
     for (int r = 0; r < R; ++r) n_good += good[r];
     const long long obase = (long long)g * NS * T;
     if (n_good == 0) {   // reference hypothesis_test.py:203-204
-        for (int i = tid; i < NS * T; i += kRegThreads) {
+        for (int i = tid; i < NS * T && blockIdx.y == 0; i += kRegThreads) {
             P.out_coef[obase + i] = nan(""); P.out_se[obase + i] = nan(""); P.out_asl[obase + i] = nan("");
             P.out_extreme[obase + i] = -1; P.out_nnull[obase + i] = 0;
         }
@@ -301,7 +328,11 @@ regress_asl_kernel(RegParams P) {
                 mn[s][t] = INFINITY; mx[s][t] = -INFINITY;
             }
         int nvalid = 0;
-        for (int b = tid; b < B1; b += kRegThreads) {
+        // with few genes and many groups per gene (thousands of guides / donors) one CTA per gene would leave the GPU
+        // empty: the replicate columns are then split over gridDim.y CTAs and combined by regress_asl_finish_kernel
+        const int per = (B1 + P.n_split - 1) / P.n_split;
+        const int b_lo = blockIdx.y * per, b_hi = min(B1, b_lo + per);
+        for (int b = b_lo + tid; b < b_hi; b += kRegThreads) {
             double acc[2][TT];
 #pragma unroll
             for (int s = 0; s < 2; ++s)
@@ -396,25 +427,12 @@ regress_asl_kernel(RegParams P) {
             }
             const double stat = s_stat[s][t];
             const long long o = obase + (long long)s * T + t0 + t;
-            double mu = a / n, var = b2 / n - mu * mu;
-            if (var < 0) var = 0;
-            double sd = sqrt(var);
-            double asl;
-            int extreme = -1;
-            if (!(vmin < vmax)) {
-                asl = nan("");   // all coefficients identical (reference :62-64)
-            } else if (P.approx) {
-                double astat = fabs(stat), k = 1.0 / (sd * 1.4142135623730951);
-                asl = 0.5 * erfc((astat - mu) * k) + 0.5 * erfc((astat + mu) * k);   // :79-83
+            if (P.n_split > 1) {
+                double* w = P.split_ws + ((((long long)g * P.n_split + blockIdx.y) * NS + s) * T + t0 + t) * 8;
+                w[0] = a; w[1] = b2; w[2] = (double)h; w[3] = (double)l; w[4] = vmin; w[5] = vmax; w[6] = (double)n; w[7] = stat;
             } else {
-                extreme = h + l;
-                asl = (double)(extreme + 1) / (double)(n + 1);                        // :92 (and the GEV fallback)
+                regress_finish(P, o, stat, a, b2, h, l, vmin, vmax, n);
             }
-            P.out_coef[o] = stat;
-            P.out_se[o] = (n > 0) ? sd : nan("");
-            P.out_asl[o] = asl;
-            P.out_extreme[o] = extreme;
-            P.out_nnull[o] = n;
         }
         __syncthreads();
     }
@@ -604,6 +622,27 @@ regress_resampled_kernel(ResampParams P) {
 
 using namespace mm;
 
+// combines the per-split statistics (fixed order: deterministic); one thread per (gene, statistic, treatment column)
+__global__ void regress_asl_finish_kernel(RegParams P, int n_gene) {
+    const int NS = P.n_stat, T = P.T;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_gene * NS * T) return;
+    const int g = (int)(i / (NS * T)), st = (int)(i % (NS * T));
+    const unsigned char* good = P.seg_good + (long long)g * P.R;
+    int n_good = 0;
+    for (int r = 0; r < P.R; ++r) n_good += good[r];
+    if (n_good == 0) return;                       // written by regress_asl_kernel
+    double a = 0, b2 = 0, vmin = INFINITY, vmax = -INFINITY, stat = 0;
+    int h = 0, l = 0, n = 0;
+    for (int sp = 0; sp < P.n_split; ++sp) {
+        const double* w = P.split_ws + (((long long)g * P.n_split + sp) * NS * T + st) * 8;
+        a += w[0]; b2 += w[1]; h += (int)w[2]; l += (int)w[3];
+        vmin = fmin(vmin, w[4]); vmax = fmax(vmax, w[5]); n += (int)w[6];
+        stat = w[7];
+    }
+    regress_finish(P, i, stat, a, b2, h, l, vmin, vmax, n);
+}
+
 MM_EXPORT int mm_fill_log(int device, void* stream, const double* raw_mean, const double* raw_rv,
                           const uint8_t* seg_ok, const double* true_mean, const double* true_rv,
                           const int32_t* src_mean, const int32_t* src_rv, const int64_t* gene_id, int32_t R,
@@ -644,9 +683,10 @@ MM_EXPORT int mm_regress_asl(int device, void* stream, const double* boot0, cons
                              const uint8_t* seg_good, const int32_t* mask_id, const double* cmat,
                              int32_t n_gene, int32_t R, int32_t T, int32_t num_boot, int32_t approx,
                              double* coef_ws, double* out_coef, double* out_se, double* out_asl,
-                             int32_t* out_extreme, int32_t* out_nnull) {
+                             int32_t* out_extreme, int32_t* out_nnull, int32_t n_split, double* split_ws) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_gene >= 0 && R > 0 && T > 0 && num_boot > 0, "n_gene/R/T/num_boot");
+    MM_REQUIRE(n_split >= 1 && n_split <= 65535 && (n_split == 1 || split_ws), "n_split / split_ws");
     if (n_gene == 0) return 0;
     MM_REQUIRE(boot0 && seg_good && mask_id && cmat && out_coef && out_se && out_asl && out_extreme && out_nnull,
                "null pointer");
@@ -654,11 +694,17 @@ MM_EXPORT int mm_regress_asl(int device, void* stream, const double* boot0, cons
     P.boot[0] = boot0; P.boot[1] = boot1; P.n_stat = boot1 ? 2 : 1; P.seg_good = seg_good; P.mask_id = mask_id;
     P.cmat = cmat; P.R = R; P.T = T; P.B = num_boot; P.approx = approx; P.coef_ws = coef_ws;
     P.out_coef = out_coef; P.out_se = out_se; P.out_asl = out_asl; P.out_extreme = out_extreme;
-    P.out_nnull = out_nnull;
-    if (T == 1) regress_asl_kernel<1><<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
-    else if (T == 2) regress_asl_kernel<2><<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
-    else regress_asl_kernel<kMaxT><<<n_gene, kRegThreads, 0, (cudaStream_t)stream>>>(P);
-    return check_launch("mm_regress_asl");
+    P.out_nnull = out_nnull; P.n_split = n_split; P.split_ws = split_ws;
+    const dim3 grid((unsigned)n_gene, (unsigned)n_split);
+    if (T == 1) regress_asl_kernel<1><<<grid, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    else if (T == 2) regress_asl_kernel<2><<<grid, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    else regress_asl_kernel<kMaxT><<<grid, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    if (int s = check_launch("mm_regress_asl")) return s;
+    if (n_split > 1) {
+        const long long items = (long long)n_gene * P.n_stat * T;
+        regress_asl_finish_kernel<<<(unsigned)((items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, n_gene);
+    }
+    return check_launch("mm_regress_asl (finish)");
 }
 
 MM_EXPORT int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,

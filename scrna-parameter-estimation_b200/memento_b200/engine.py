@@ -11,6 +11,7 @@ from .device import ENTRY_BYTES, NULL_TIMER
 
 
 N_TABLE_MAX = 16384      # largest multiplicity with a universal Poisson inversion table
+REGRESS_MIN_CTAS = 592   # mm_regress_asl: CTAs wanted per launch (4 per SM)
 SEG_INFO_BYTES = 48      # sizeof(SegInfo) in csrc/bootstrap.cu
 _TABLES = {}             # per device: (offsets tensor, pool tensor)
 
@@ -157,8 +158,12 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
             raise _lib.MementoCudaError("resample_rep: a bootstrap column is non-finite in a valid group; the "
                                         "device path does not drop columns in this mode")
     else:
+        # one CTA per gene, unless that leaves the GPU empty (few genes per tile x many groups): then the replicate
+        # columns of a gene are split over several CTAs
+        n_split = int(min(64, max(1, -(-REGRESS_MIN_CTAS // n_gene)))) if n_gene < REGRESS_MIN_CTAS else 1
+        split_ws = torch.empty(n_gene * n_split * n_stat * T * 8, dtype=torch.float64, device=device) if n_split > 1 else None
         _lib.call("mm_regress_asl", device, boot0, boot1, seg_good, mask_id, cmat, n_gene, R, T, num_boot,
-                  1 if approx else 0, coef_ws, out_coef, out_se, out_asl, out_ext, out_nn)
+                  1 if approx else 0, coef_ws, out_coef, out_se, out_asl, out_ext, out_nn, n_split, split_ws)
     timer.stop("regress_asl", ev)
     shp = (n_gene, n_stat, T)
     return {"coef": out_coef.view(shp), "se": out_se.view(shp), "asl": out_asl.view(shp),

@@ -620,3 +620,19 @@ def test_get_corr_matrix_vs_reference(st, gpu_prepared):
     finally:
         mm_main.DENSE_BLOCK_MIN_PAIRS = old
     assert_close(cm, st["corr_matrix_g1"], 1e-8, atol=1e-11)
+
+
+def test_regress_asl_split_equals_single(monkeypatch, gpu_prepared, oracle_prepared):
+    """mm_regress_asl with the replicate columns of a gene split over several CTAs (tiles with few genes and
+    many groups) gives the results of the one-CTA-per-gene launch: counts exactly, sums to round-off."""
+    cov, tr = synth.design_from_groups(gpu_prepared.uns["memento"]["groups"], ["stim", "cell"])
+    res = {}
+    for name, min_ctas in (("single", 1), ("split", 1 << 20)):
+        monkeypatch.setattr(engine, "REGRESS_MIN_CTAS", min_ctas)
+        ad = gpu_prepared.copy()
+        memento.ht_1d_moments(ad, cov, tr, num_boot=2000, resampling="bootstrap", seed=3)
+        res[name] = ad.uns["memento"]["1d_ht"]
+    for k in ("mean_coef", "var_coef", "mean_asl", "var_asl"):
+        assert_close(res["split"][k], res["single"][k], 1e-12, what=k)
+    for k in ("mean_se", "var_se"):
+        assert_close(res["split"][k], res["single"][k], 1e-9, what=k)
