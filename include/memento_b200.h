@@ -41,7 +41,7 @@ int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32
  * n_cells = length of inv_sf.  chunk_seg (device int32[ceil(nnz / 512)]): index of the segment containing
  * nonzero 512 * i (the last segment whose start is <= 512 * i); edge: float64 scratch of
  * 10 * ceil(nnz / 512) entries.  With both (and 16-byte aligned vals / rows / inv_sf) the matrix is read as
- * ONE contiguous stream and the result is deterministic: segments averaging >= 64 nonzeros use the
+ * ONE contiguous stream and the result is deterministic: segments averaging >= 160 nonzeros use the
  * register-streaming span kernel (1/size_factor table in shared memory when n_cells * 8 fits), shorter ones
  * the TMA-staged tile kernel (4096-nonzero tiles bulk-copied into a shared-memory ring).  When either is
  * NULL the segments are reduced one by one from global memory and big_list (int32 scratch of

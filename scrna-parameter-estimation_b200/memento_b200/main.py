@@ -177,8 +177,8 @@ def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_p
 
     X = adata.X
     n_cells, n_genes = X.shape
-    if not X.has_sorted_indices:
-        X = X.sorted_indices()
+    # no need for sorted column indices: the re-layout below is a stable sort by (gene, group) over the row-major
+    # nonzeros, and the row sums add integers (exact in float64 in any order)
     st.csr = CsrOnDevice(X, dev, pinned)
     st.h2d_bytes += st.csr.h2d_bytes
     st.seg_all = SegMatrix.from_csr(st.csr)
