@@ -10,7 +10,8 @@ Same call signatures and ``adata.uns['memento']`` schema as the reference (memen
 """
 from .main import (compute_1d_moments, compute_2d_moments, create_groups, get_corr_matrix,  # noqa: F401
                    ht_1d_moments, ht_2d_moments, setup_memento)
-from .getters import get_1d_ht_result, get_1d_moments, get_groups  # noqa: F401
+from .getters import (fdrcorrect, get_1d_ht_result, get_1d_moments, get_2d_ht_result, get_2d_moments,  # noqa: F401
+                      get_groups, prepare_to_save)
 from .anndata_lite import AnnDataLite  # noqa: F401
 
 __version__ = "0.1.0"

@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(HERE, "ref_shim"))
 sys.path.insert(0, "/root/reference")
-sys.path.insert(0, os.path.join(ROOT, "scrna-parameter-estimation_b200"))
+sys.path.append(os.path.join(ROOT, "scrna-parameter-estimation_b200"))    # after the reference: its `memento` must win
 
 import memento.main as ref_main                      # noqa: E402  (the reference)
 import memento.estimator as ref_est                  # noqa: E402
@@ -218,9 +218,78 @@ def asl_cases():
     print("asl.npz:", {k: float(v) for k, v in out.items() if k.endswith("_asl")})
 
 
+def getters():
+    """The reference's result getters (main.py:523-670) and BH correction (util.py:22-29) on a small fabricated
+    ``uns['memento']`` (the getters only read the dictionary)."""
+    import memento.util as ref_util
+    from memento_b200.anndata_lite import AnnDataLite
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    G, n_pairs = 7, 9
+    groups = ["sg^ctrl^A", "sg^ctrl^B", "sg^stim^A", "sg^stim^B"]
+    n_cells = [30, 50, 20, 40]
+    obs = pd.DataFrame({"stim": np.repeat(["ctrl", "ctrl", "stim", "stim"], n_cells), "cell": np.repeat(["A", "B", "A", "B"], n_cells)})
+    var = pd.DataFrame(index=pd.Index(["g%d" % i for i in range(G)]))
+    ad = AnnDataLite(sp.csr_matrix((sum(n_cells), G)), obs, var)
+    mom = rng.gamma(2.0, 1.0, size=(len(groups), 3, G))
+    mom[0, 0, 2] = 0.0          # a zero mean (log -> -inf) and a NaN residual variance
+    mom[1, 2, 4] = np.nan
+    corr = rng.uniform(-1, 1, size=(len(groups), n_pairs))
+    corr[2, 3] = np.nan
+    pairs = [("g%d" % rng.integers(G), "g%d" % rng.integers(G)) for _ in range(n_pairs)]
+    ht = {k: rng.normal(size=G) for k in ("mean_coef", "mean_se", "var_coef", "var_se")}
+    ht.update({k: rng.uniform(size=G) for k in ("mean_asl", "var_asl")})
+    ht["treatment"] = pd.DataFrame({"stim": [0, 0, 1, 1]}, index=groups)
+    ht2 = {"corr_coef": rng.normal(size=n_pairs), "corr_se": rng.uniform(size=n_pairs), "corr_asl": rng.uniform(size=n_pairs)}
+    ad.uns["memento"] = {
+        "groups": groups, "label_columns": ["stim", "cell"], "label_delimiter": "^",
+        "group_cells": {g: sp.csr_matrix((n, G)) for g, n in zip(groups, n_cells)},
+        "1d_moments": {g: [mom[i, 0].copy(), mom[i, 1].copy(), mom[i, 2].copy()] for i, g in enumerate(groups)},
+        "2d_moments": {"gene_pairs": pairs, **{g: {"corr": corr[i].copy()} for i, g in enumerate(groups)}},
+        "1d_ht": ht, "2d_ht": ht2}
+    out = {"groups": np.array(groups), "n_cells": np.array(n_cells), "mom": mom, "corr": corr,
+           "pairs": np.array(pairs), "stim": np.array(obs["stim"].tolist(), dtype=str), "cell": np.array(obs["cell"].tolist(), dtype=str)}
+    for k, v in ht.items():
+        if k != "treatment":
+            out["ht_" + k] = v
+    for k, v in ht2.items():
+        out["ht2_" + k] = v
+    with np.errstate(divide="ignore", invalid="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m, v, counts = ref_main.get_1d_moments(ad)
+        out["m1_mean"], out["m1_var"] = m.drop(columns="gene").values, v.drop(columns="gene").values
+        out["m1_cols"] = np.array(m.columns[1:].tolist())
+        for gb in ("stim", "cell", "ALL"):
+            m, v = ref_main.get_1d_moments(ad, groupby=gb)
+            out["m1_%s_mean" % gb], out["m1_%s_var" % gb] = m.drop(columns="gene").values, v.drop(columns="gene").values
+            out["m1_%s_cols" % gb] = np.array(m.columns[1:].tolist())
+        c, _ = ref_main.get_2d_moments(ad)
+        out["m2_corr"] = c.drop(columns=["gene_1", "gene_2"]).values.astype(float)
+        for gb in ("cell", "ALL"):
+            # the reference zeroes the NaNs of uns['memento']['2d_moments'][g]['corr'] in place: give it a copy
+            ad.uns["memento"]["2d_moments"] = {"gene_pairs": pairs, **{g: {"corr": corr[i].copy()} for i, g in enumerate(groups)}}
+            c = ref_main.get_2d_moments(ad, groupby=gb)
+            out["m2_%s_corr" % gb] = c.drop(columns=["gene_1", "gene_2"]).values.astype(float)
+            out["m2_%s_cols" % gb] = np.array(c.columns[2:].tolist())
+        r1 = ref_main.get_1d_ht_result(ad)
+        out["r1_gene"], out["r1_tx"] = np.array(r1["gene"].tolist(), dtype=str), np.array(r1["tx"].tolist(), dtype=str)
+        out["r1_vals"] = r1[["de_coef", "de_se", "de_pval", "dv_coef", "dv_se", "dv_pval"]].values
+        r2 = ref_main.get_2d_ht_result(ad)
+        out["r2_vals"] = r2[["corr_coef", "corr_se", "corr_pval"]].values
+        p = rng.uniform(size=40) ** 2
+        p[[3, 17]] = np.nan
+        out["fdr_p"], out["fdr_q"] = p, ref_util._fdrcorrect(p.copy())
+    np.savez_compressed(os.path.join(HERE, "getters.npz"), **out)
+    print("getters.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "getters":
+        getters()
+        sys.exit(0)
     ad = stages()
     stages_f32()
     ht1d(ad)
     ht2d(ad)
     asl_cases()
+    getters()
