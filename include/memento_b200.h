@@ -203,10 +203,14 @@ int mm_regress_asl(int device, void* stream, const double* boot0, const double* 
  * does it) until a two-sided KS check at 0.05 passes, and replaces asl[row] by
  * N_exec/n * (cdf(-|stat|) + sf(|stat|)); status[i] = 1 if replaced, 0 if the empirical bound was
  * kept (no tail passed, a fit failed, or fewer than 300 usable replicates).
+ * flagged == NULL: the rows 0 .. n_flag - 1 are considered and selected ON THE DEVICE -- a row is refined
+ * when 0 <= extreme[row] <= max_extreme and asl[row] is finite (status -1 otherwise), so the caller needs no
+ * host round trip between mm_regress_asl and this stage.
  * Replaces: memento/hypothesis_test.py:94-141 (_compute_asl, GEV branch; scipy genextreme.fit +
  * kstest per tail, ~110 ms per fit on a CPU core). */
 int mm_gev_tail_asl(int device, void* stream, const double* coef_rows, const int32_t* flagged,
-                    int32_t n_flag, int32_t num_boot, double* asl, int32_t* status);
+                    int32_t n_flag, int32_t num_boot, double* asl, int32_t* status,
+                    const int32_t* extreme, int32_t max_extreme);
 
 /* ---- 2D (gene pair) bootstrap path.  item = pair * R + group; item_ptr[n_pairs * R + 1] = prefix sums
  * of (nnz of gene 1 + nnz of gene 2 in the group) = pool offsets of the items' tables.

@@ -19,7 +19,7 @@ lo = (seg.seg_ptr[:G*seg.R] - seg.seg_ptr[0]).long()
 idx = torch.cat([torch.arange(int(l), int(l)+int(u), device=U.device) for l,u in zip(lo.tolist()[:2000], U.tolist()[:2000])])
 nn = n_field[idx].cpu().numpy()
 print("segments", 2000, "mean U", U[:2000].float().mean().item(), "frac n<=16", (nn<=16).mean(), "frac n==1", (nn==1).mean(), "frac n<=4", (nn<=4).mean())
-for sampler in ("poisson", "poisson", "poisson"):
+for sampler in ("poisson", "chain", "poisson"):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -36,7 +36,9 @@ constexpr double kPenalty = 709.782712893384 * 100.0;   // log(DBL_MAX) * 100
 
 struct GevParams {
     const double* coef_rows;   // [n_rows][B + 1]
-    const int* flagged;        // [n_flag] row ids
+    const int* flagged;        // [n_flag] row ids; null: rows 0 .. n_flag - 1, filtered on the device by `extreme`
+    const int* extreme;        // [n_rows] extreme counts of mm_regress_asl (used when flagged is null)
+    int max_extreme;
     int n_flag, B, sort_cap;
     double* asl;               // [n_rows], updated in place where the GEV path succeeds
     int* status;               // [n_flag] 1 = GEV tails used, 0 = empirical bound kept
@@ -233,7 +235,14 @@ gev_tail_kernel(GevParams P) {
     __shared__ int s_cnt[3];
     __shared__ int s_state[2][kLadder];    // 0 pending, 1 pass, 2 ks-fail, 3 fit error
     __shared__ double s_val[2][kLadder];
-    const int row = P.flagged[blockIdx.x];
+    const int row = P.flagged ? P.flagged[blockIdx.x] : (int)blockIdx.x;
+    if (!P.flagged) {   // device-side selection (no host round trip): only tests with few extreme replicates
+        const int e = P.extreme[row];
+        if (e < 0 || e > P.max_extreme || !isfinite(P.asl[row])) {
+            if (threadIdx.x == 0) P.status[blockIdx.x] = -1;
+            return;
+        }
+    }
     const double* cr = P.coef_rows + (long long)row * (P.B + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double stat = cr[0], astat = fabs(stat);
@@ -347,14 +356,15 @@ gev_tail_kernel(GevParams P) {
 using namespace mm;
 
 MM_EXPORT int mm_gev_tail_asl(int device, void* stream, const double* coef_rows, const int32_t* flagged,
-                              int32_t n_flag, int32_t num_boot, double* asl, int32_t* status) {
+                              int32_t n_flag, int32_t num_boot, double* asl, int32_t* status,
+                              const int32_t* extreme, int32_t max_extreme) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_flag >= 0 && num_boot > 0, "n_flag/num_boot");
     if (n_flag == 0) return 0;
-    MM_REQUIRE(coef_rows && flagged && asl && status, "null pointer");
+    MM_REQUIRE(coef_rows && (flagged || extreme) && asl && status, "null pointer");
     GevParams P;
     P.coef_rows = coef_rows; P.flagged = flagged; P.n_flag = n_flag; P.B = num_boot; P.sort_cap = 0;
-    P.asl = asl; P.status = status;
+    P.asl = asl; P.status = status; P.extreme = extreme; P.max_extreme = max_extreme;
     gev_tail_kernel<<<n_flag, kGevThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_gev_tail_asl");
 }

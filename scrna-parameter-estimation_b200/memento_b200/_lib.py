@@ -37,7 +37,7 @@ SIGNATURES = {
     "mm_pair_prepare": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],
     "mm_pair_bootstrap": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _u64, _vp, _vp, _vp],
     "mm_pair_bootstrap_replay": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
-    "mm_gev_tail_asl": [_vp, _vp, _i32, _i32, _vp, _vp],
+    "mm_gev_tail_asl": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32],
     "mm_regress_asl": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
 }
 

@@ -414,9 +414,19 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
             gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
         for k in out:
             out[k][:] = res[k].cpu().numpy()
+        gev.count_tail_tests(stats_acc)
         genes_per_tile = G + 1
         st.last_replay = res
     gene_id = to_device(st.gene_index + st.gene_offset, st.device, np.int64)   # RNG stream ids (global)
+    # The GEV tail stage of a tile (latency-bound float64 fits on a few thousand warps) runs on a side stream,
+    # concurrently with the next tile's issue-bound bootstrap; results are read back once, at the end.
+    main_stream = torch.cuda.current_stream(st.device)
+    side = None
+    if not approx and replay is None:
+        side = getattr(st, "side_stream", None)
+        if side is None:
+            side = st.side_stream = torch.cuda.Stream(st.device)
+    pending = []
     for lo in range(0, G if replay is None else 0, genes_per_tile):
         n = min(genes_per_tile, G - lo)
         res = engine.ht_1d_tile(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
@@ -424,10 +434,20 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
                                 want_coef_rows=not approx, timer=st.timer, stats=stats_acc,
                                 gene_id=gene_id[lo:lo + n], sampler=sampler,
                                 min_accept=getattr(st, "min_accept", 0.2), resample_rep=resample_rep)
-        if not approx:
-            gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
+        if side is not None:
+            side.wait_stream(main_stream)
+            with torch.cuda.stream(side):
+                gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
+            for key in ("coef_rows", "asl", "extreme"):
+                res[key].record_stream(side)
+            del res["coef_rows"]            # the allocator keeps the block until the side stream is done with it
+        pending.append((lo, n, {k: res[k] for k in out}))
+    if side is not None:
+        main_stream.wait_stream(side)
+    for lo, n, res in pending:
         for k in out:
             out[k][lo:lo + n] = res[k].cpu().numpy()
+    gev.count_tail_tests(stats_acc)
     st.last_stats = stats_acc
 
     # flat gene-major / treatment-minor outputs (main.py:399-404)

@@ -401,7 +401,7 @@ def _gev_device(x):
     rows = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     flagged = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.call("mm_gev_tail_asl", dev, rows, flagged, 1, B, asl, status)
+    _lib.call("mm_gev_tail_asl", dev, rows, flagged, 1, B, asl, status, None, 10)
     torch.cuda.synchronize()
     return float(asl[0]), int(status[0]), c
 
