@@ -125,6 +125,13 @@ class SegMatrix:
     def n_seg(self):
         return self.G * self.R
 
+    @property
+    def seg_ptr_host(self):
+        """Host copy of seg_ptr (numpy int64), fetched once: tile planning reads offsets without a device sync."""
+        if getattr(self, "_seg_ptr_host", None) is None:
+            self._seg_ptr_host = self.seg_ptr.cpu().numpy()
+        return self._seg_ptr_host
+
     # ------------------------------------------------------------------ host staging (end-to-end path)
     def to_host_pinned(self):
         """Pinned host copies of the three arrays (what an end-to-end call uploads)."""

@@ -45,6 +45,7 @@ class GroupDesign:
     def __init__(self, device, n_cells, q, mv_fit, n_bins_present, bin_inv_sf):
         self.R = len(n_cells)
         self.n_cells_host = np.asarray(n_cells, dtype=np.int64)
+        self.n_cells_total = int(self.n_cells_host.sum())
         self.n_cells = torch.as_tensor(np.asarray(n_cells, dtype=np.int32), device=device)
         self.q = torch.as_tensor(np.asarray(q, dtype=np.float64), device=device)
         self.mv_fit = torch.as_tensor(np.ascontiguousarray(mv_fit, dtype=np.float64), device=device)
@@ -70,15 +71,15 @@ def unique_tables(seg, design, cell_bin, gene_lo, n_genes, estimator, timer=NULL
     dev = seg.device
     R = seg.R
     seg_lo, n_seg = gene_lo * R, n_genes * R
-    lo, hi = (int(v) for v in seg.seg_ptr[[seg_lo, seg_lo + n_seg]].tolist())
+    sp = seg.seg_ptr_host
+    lo, hi = int(sp[seg_lo]), int(sp[seg_lo + n_seg])
     pool = max(hi - lo, 1)
     entries = torch.empty(pool * ENTRY_BYTES, dtype=torch.uint8, device=dev)
     raw_key = torch.empty(pool, dtype=torch.int32, device=dev) if want_raw else None
     raw_cnt = torch.empty(pool, dtype=torch.int32, device=dev) if want_raw else None
     seg_U = torch.empty(n_seg, dtype=torch.int32, device=dev)
     big = torch.zeros(n_seg + 1, dtype=torch.int32, device=dev)
-    seg_len = seg.seg_ptr[seg_lo + 1:seg_lo + n_seg + 1] - seg.seg_ptr[seg_lo:seg_lo + n_seg]
-    need_scratch = bool((seg_len > 6144).any().item())
+    need_scratch = bool((np.diff(sp[seg_lo:seg_lo + n_seg + 1]) > 6144).any())
     sc_n = 3 * pool if need_scratch else 1
     sk = torch.empty(sc_n, dtype=torch.int32, device=dev)
     sc = torch.empty(sc_n, dtype=torch.int32, device=dev)
@@ -122,12 +123,16 @@ def wls_functional(device, covariate, treatment, weights, masks, one_sample, tim
 
 def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, treatment, weights, one_sample,
                  approx, want_coef_rows, timer=NULL_TIMER, resample_rep=False, seed=0, gene_id=None,
-                 assignments=None):
+                 assignments=None, good_host=None):
     """Shared tail of the 1D and 2D tests for one tile.  boot*: (n_gene*R, B+1) device tensors,
     seg_good: (n_gene*R,) uint8 device.  Returns dict of host arrays (n_gene, n_stat, T) + coef rows."""
     n_gene = seg_good.numel() // R
     n_stat = 2 if boot1 is not None else 1
-    good_h = seg_good.view(n_gene, R).cpu().numpy()
+    if good_host is not None:          # (pinned copy, event recorded behind it)
+        good_host[1].synchronize()
+        good_h = good_host[0].numpy().reshape(n_gene, R)
+    else:
+        good_h = seg_good.view(n_gene, R).cpu().numpy()
     masks, inverse = np.unique(good_h, axis=0, return_inverse=True)
     use_resampled = resample_rep and not one_sample      # reference: the one-sample branch ignores it
     if use_resampled:
@@ -204,14 +209,14 @@ def segment_modes(seg_info, n_seg):
     return seg_info.view(n_seg, SEG_INFO_BYTES)[:, :4].contiguous().view(torch.int32).reshape(-1)
 
 
-def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,
-               estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None, gene_id=None,
-               sampler="poisson", min_accept=0.2, resample_rep=False):
-    """One tile of genes through the whole test.  true_mean / true_rv: (n_genes, R) host arrays;
-    gene_id: int64 device vector of the tile's global gene ids (RNG stream ids)."""
+def ht_1d_tile_boot(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, num_boot, estimator, seed,
+                    timer=NULL_TIMER, stats=None, gene_id=None, sampler="poisson", min_accept=0.2):
+    """First half of a gene tile: compression -> bootstrap -> imputation / log rows.  Only enqueues work (no
+    device synchronisation), so the caller can queue the next tile's first half before it waits for this one.
+    true_mean / true_rv: (n_genes, R) host arrays; gene_id: int64 device vector of the tile's global gene ids
+    (RNG stream ids).  Returns the context ``ht_1d_tile_regress`` needs."""
     dev = seg.device
     R = seg.R
-    T = treatment.shape[1]
     n_seg = n_genes * R
     tab = unique_tables(seg, design, cell_bin, gene_lo, n_genes, estimator, timer)
     # a-priori validity: reference hypothesis_test.py:167-171
@@ -223,15 +228,6 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
     tv = torch.as_tensor(np.ascontiguousarray(true_rv.reshape(-1), dtype=np.float64), device=dev)
     raw_mean, raw_rv, seg_info = bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip,
                                                 gene_id, sampler, min_accept, timer)
-    if stats is not None:
-        u = tab["seg_U"].clamp(min=0) * seg_ok.to(torch.int32)
-        stats["category_draws"] = stats.get("category_draws", 0) + int(u.sum().item()) * num_boot
-        stats["unique_bytes"] = stats.get("unique_bytes", 0) + unique_bytes(tab, seg.n_cells)
-        stats["segments"] = stats.get("segments", 0) + n_seg
-        if seg_info is not None and stats.get("want_modes"):
-            modes = segment_modes(seg_info, n_seg)
-            stats["poisson_segments"] = stats.get("poisson_segments", 0) + int(((modes == 1) & (seg_ok != 0)).sum().item())
-            stats["chain_segments"] = stats.get("chain_segments", 0) + int(((modes == 0) & (seg_ok != 0)).sum().item())
     boot_mean = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
     boot_var = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
     seg_good = torch.empty(n_seg, dtype=torch.uint8, device=dev)
@@ -240,13 +236,65 @@ def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, cova
     _lib.call("mm_fill_log", dev, raw_mean, raw_rv, seg_ok, tm, tv, None, None, gene_id, R, n_seg, num_boot,
               seed, boot_mean, boot_var, seg_good, n_valid)
     timer.stop("fill_log", ev)
-    del raw_mean, raw_rv
-    res = regress_tile(dev, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
-                       design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer,
-                       resample_rep=resample_rep, seed=seed, gene_id=gene_id)
+    # the validity flags go to pinned host memory right behind fill_log, so that the regression half can read them
+    # as soon as THIS tile is done, whatever has been queued after it
+    good_host = torch.empty(n_seg, dtype=torch.uint8, pin_memory=True)
+    good_host.copy_(seg_good, non_blocking=True)
+    good_event = torch.cuda.Event()
+    good_event.record(torch.cuda.current_stream(dev))
+    return {"boot_mean": boot_mean, "boot_var": boot_var, "seg_good": seg_good, "tab": tab, "seg_ok": seg_ok,
+            "good_host": good_host, "good_event": good_event,
+            "seg_info": seg_info, "n_seg": n_seg, "gene_id": gene_id, "sampler": sampler, "stats": stats}
+
+
+def ht_1d_tile_regress(ctx, design, R, covariate, treatment, num_boot, seed, approx, one_sample, want_coef_rows,
+                       timer=NULL_TIMER, resample_rep=False):
+    """Second half of a gene tile: regression functional per validity mask -> coefficients, SE, ASL.  Waits for
+    the tile's first half (it reads the validity flags on the host)."""
+    dev = ctx["boot_mean"].device
+    T = treatment.shape[1]
+    stats = ctx["stats"]
     if stats is not None:
+        # device-side counters only (no synchronisation here); finalize_stats turns them into numbers at the end
+        tab, seg_ok, n_seg, seg_info = ctx["tab"], ctx["seg_ok"], ctx["n_seg"], ctx["seg_info"]
+        u = tab["seg_U"].clamp(min=0)
+        terms = {"draws": (u * seg_ok.to(torch.int32)).sum(), "total_U": u.sum(), "nnz": tab["nnz"], "n_seg": n_seg}
+        if seg_info is not None and stats.get("want_modes"):
+            modes = segment_modes(seg_info, n_seg)
+            terms["poisson"] = ((modes == 1) & (seg_ok != 0)).sum()
+            terms["chain"] = ((modes == 0) & (seg_ok != 0)).sum()
+        stats.setdefault("_terms", []).append(terms)
+        stats["segments"] = stats.get("segments", 0) + n_seg
         # unique x2 (+memset), prepare, bootstrap x2, fill, wls, regress
-        stats["launches"] = stats.get("launches", 0) + (9 if sampler == "poisson" else 7)
+        stats["launches"] = stats.get("launches", 0) + (9 if ctx["sampler"] == "poisson" else 7)
+    return regress_tile(dev, ctx["boot_mean"], ctx["boot_var"], ctx["seg_good"], R, T, num_boot, covariate, treatment,
+                        design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer,
+                        resample_rep=resample_rep, seed=seed, gene_id=ctx["gene_id"],
+                        good_host=(ctx["good_host"], ctx["good_event"]))
+
+
+def finalize_stats(stats, num_boot, n_cells):
+    """Turns the per-tile device counters of ht_1d_tile_regress into the numbers bench.py reports."""
+    for t in stats.pop("_terms", []):
+        total_U = int(t["total_U"].item())
+        stats["category_draws"] = stats.get("category_draws", 0) + int(t["draws"].item()) * num_boot
+        stats["unique_bytes"] = stats.get("unique_bytes", 0) + (t["nnz"] * 8 + n_cells + (t["n_seg"] + 1) * 8 +
+                                                                 total_U * ENTRY_BYTES + t["n_seg"] * 4)
+        if "poisson" in t:
+            stats["poisson_segments"] = stats.get("poisson_segments", 0) + int(t["poisson"].item())
+            stats["chain_segments"] = stats.get("chain_segments", 0) + int(t["chain"].item())
+
+
+def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,
+               estimator, seed, approx, one_sample, want_coef_rows, timer=NULL_TIMER, stats=None, gene_id=None,
+               sampler="poisson", min_accept=0.2, resample_rep=False):
+    """One tile of genes through the whole test (both halves back to back)."""
+    ctx = ht_1d_tile_boot(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, num_boot, estimator, seed,
+                          timer, stats, gene_id, sampler, min_accept)
+    res = ht_1d_tile_regress(ctx, design, seg.R, covariate, treatment, num_boot, seed, approx, one_sample,
+                             want_coef_rows, timer, resample_rep)
+    if stats is not None:
+        finalize_stats(stats, num_boot, design.n_cells_total)
     return res
 
 

@@ -427,13 +427,22 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         if side is None:
             side = st.side_stream = torch.cuda.Stream(st.device)
     pending = []
-    for lo in range(0, G if replay is None else 0, genes_per_tile):
-        n = min(genes_per_tile, G - lo)
-        res = engine.ht_1d_tile(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
-                                cov, tr_all, num_boot, estimator, seed, approx, one_sample,
-                                want_coef_rows=not approx, timer=st.timer, stats=stats_acc,
-                                gene_id=gene_id[lo:lo + n], sampler=sampler,
-                                min_accept=getattr(st, "min_accept", 0.2), resample_rep=resample_rep)
+    tiles = [(lo, min(genes_per_tile, G - lo)) for lo in range(0, G if replay is None else 0, genes_per_tile)]
+
+    def first_half(lo, n):      # compression -> bootstrap -> log rows: enqueued without waiting for the device
+        return engine.ht_1d_tile_boot(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
+                                      num_boot, estimator, seed, timer=st.timer, stats=stats_acc,
+                                      gene_id=gene_id[lo:lo + n], sampler=sampler,
+                                      min_accept=getattr(st, "min_accept", 0.2))
+
+    ctx = first_half(*tiles[0]) if tiles else None
+    for i, (lo, n) in enumerate(tiles):
+        # the next tile's bootstrap is queued before this tile's regression reads its validity flags on the host,
+        # so the device never waits for the host between tiles (two tiles of bootstrap rows are alive at a time)
+        nxt = first_half(*tiles[i + 1]) if i + 1 < len(tiles) else None
+        res = engine.ht_1d_tile_regress(ctx, st.design, R, cov, tr_all, num_boot, seed, approx, one_sample,
+                                        want_coef_rows=not approx, timer=st.timer, resample_rep=resample_rep)
+        ctx = nxt
         if side is not None:
             side.wait_stream(main_stream)
             with torch.cuda.stream(side):
@@ -448,6 +457,7 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         for k in out:
             out[k][lo:lo + n] = res[k].cpu().numpy()
     gev.count_tail_tests(stats_acc)
+    engine.finalize_stats(stats_acc, num_boot, st.design.n_cells_total)
     st.last_stats = stats_acc
 
     # flat gene-major / treatment-minor outputs (main.py:399-404)
