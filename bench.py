@@ -37,6 +37,24 @@ METRIC = "genes tested/sec (ht_1d, num_boot=10k)"
 UNIT = "genes/s"
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 -- NCCL prints its
+    version banner there from C -- is sent to stderr; emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def ncu_traffic(nnz):
     """DRAM bytes per mm_seg_moments launch from the committed `ncu --set full` capture of the same matrix
     (profiles/r01_seg_moments_stream.json: dram__bytes_read.sum + dram__bytes_write.sum of the span kernel and
@@ -171,7 +189,7 @@ def run_reference(a):
     ms = 1e3 * float(np.mean(times))
     value = min(n_sample, G) / (ms / 1e3)
     sample = "%d random genes of %d per step, all %d groups, num_boot=%d" % (min(n_sample, G), G, len(groups), a.num_boot)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_dict(a, len(groups), G),
@@ -349,13 +367,14 @@ def run_ours(a):
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clk}
         out.update(extra)
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     args = parse()
+    guard_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
