@@ -33,6 +33,24 @@ const char* mm_last_error(void);
 int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                     const float* data, int64_t n_rows, const uint8_t* gene_mask, double* out);
 
+/* Ingest re-layout, CSR (cells x genes, canonical: no duplicate entries) -> group-sorted CSC, as a stable counting
+ * transposition in three passes (csrc/relayout.cu).  New rows (cells ordered group by group; order[r] = original
+ * cell of new row r, NULL = identity) are cut into chunks of consecutive rows of ONE group: chunk_row_lo
+ * [n_chunks + 1], chunk_group [n_chunks], group_chunk_lo [R + 1] (chunks of group g).  cnt: int32 scratch
+ * [n_chunks][n_genes] shared by the two calls.
+ *   mm_relayout_count : per-chunk per-gene counts, their exclusive prefix over every group's chunks (left in cnt)
+ *                       and seg_len[gene * R + group]; the caller prefix-sums seg_len into seg_ptr [n_genes * R + 1].
+ *   mm_relayout_fill  : vals_out / rows_out (new row ids) in segment order, rows ascending inside a segment.
+ * Replaces: memento/main.py:115-132 + util.py:8-13 (per-group boolean scan + X[mask].tocsc() copy). */
+int mm_relayout_count(int device, void* stream, const int64_t* indptr, const int32_t* indices,
+                      const int32_t* order, const int32_t* chunk_row_lo, const int32_t* chunk_group,
+                      const int32_t* group_chunk_lo, int32_t n_chunks, int32_t n_genes, int32_t R,
+                      int32_t* cnt, int64_t* seg_len);
+int mm_relayout_fill(int device, void* stream, const int64_t* indptr, const int32_t* indices,
+                     const float* data, const int32_t* order, const int32_t* chunk_row_lo,
+                     const int32_t* chunk_group, int32_t n_chunks, int32_t n_genes, int32_t R, int32_t* cnt,
+                     const int64_t* seg_ptr, float* vals_out, int32_t* rows_out);
+
 /* One pass over the group-sorted CSC matrix: for every segment s,
  *   out[0*n_seg+s] = sum x          out[1*n_seg+s] = max x
  *   out[2*n_seg+s] = sum x/sf       out[3*n_seg+s] = sum x/sf^2     out[4*n_seg+s] = sum x^2/sf^2

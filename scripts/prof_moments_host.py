@@ -9,4 +9,4 @@ for name, f in (("setup", lambda: memento.setup_memento(ad, "q")), ("groups", la
                 ("moments", lambda: memento.compute_1d_moments(ad, min_perc_group=0.7))):
     pr = cProfile.Profile(); pr.enable(); f(); torch.cuda.synchronize(); pr.disable()
     s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(14)
-    print("=====", name); print("\n".join(l for l in s.getvalue().splitlines()[4:24]))
+    print("=====", name); print("\n".join(l[:150] for l in s.getvalue().splitlines()[4:22]))

@@ -162,6 +162,43 @@ class SegMatrix:
                                    n_groups, rank_of_cell)
 
     @staticmethod
+    def from_csr_grouped(csr, order=None, group_start=None, timer=NULL_TIMER):
+        """Re-layout of the uploaded CSR with the hand-written counting transposition (csrc/relayout.cu):
+        ``order`` = original cell of every new row (numpy int array, cells sorted group by group; None: one group,
+        original order), ``group_start`` = first new row of every group (numpy int64 [R + 1])."""
+        n_cells, n_genes = csr.shape
+        dev = csr.device
+        gs = np.asarray([0, n_cells], dtype=np.int64) if group_start is None else np.asarray(group_start, dtype=np.int64)
+        R = gs.size - 1
+        sizes = np.diff(gs)
+        # chunks of consecutive rows of one group; enough of them to fill the GPU, few enough for the counter array
+        rpc = int(np.clip(n_cells // 8192, 32, 1024))
+        rpc = max(rpc, int(np.ceil(n_cells * float(n_genes) * 4 / 1.5e9)))
+        per_group = (sizes + rpc - 1) // rpc
+        group_chunk_lo = np.concatenate([[0], np.cumsum(per_group)]).astype(np.int32)
+        n_chunks = int(group_chunk_lo[-1])
+        chunk_group = np.repeat(np.arange(R, dtype=np.int32), per_group)
+        within = np.arange(n_chunks, dtype=np.int64) - group_chunk_lo[chunk_group]
+        chunk_row_lo = np.concatenate([gs[chunk_group] + within * rpc, [n_cells]]).astype(np.int32)
+        # (a chunk ends where the next one starts: the next chunk of its group, or the first chunk of the next
+        # non-empty group, whose first row is this group's end)
+        d = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)  # noqa: E731
+        crl, cg, gcl = d(chunk_row_lo), d(chunk_group), d(group_chunk_lo)
+        order_d = None if order is None else d(np.asarray(order, dtype=np.int32))
+        cnt = torch.empty(max(n_chunks, 1) * n_genes, dtype=torch.int32, device=dev)
+        seg_ptr = torch.zeros(n_genes * R + 1, dtype=torch.int64, device=dev)
+        ev = timer.start()
+        _lib.call("mm_relayout_count", dev, csr.indptr, csr.indices, order_d, crl, cg, gcl, n_chunks, n_genes, R,
+                  cnt, seg_ptr[1:])
+        torch.cumsum(seg_ptr[1:], 0, out=seg_ptr[1:])
+        vals = torch.empty(csr.nnz, dtype=torch.float32, device=dev)
+        rows = torch.empty(csr.nnz, dtype=torch.int32, device=dev)
+        _lib.call("mm_relayout_fill", dev, csr.indptr, csr.indices, csr.data, order_d, crl, cg, n_chunks, n_genes, R,
+                  cnt, seg_ptr, vals, rows)
+        timer.stop("relayout", ev)
+        return SegMatrix(vals, rows, seg_ptr, n_genes, R, n_cells, gs if group_start is not None else None)
+
+    @staticmethod
     def _from_coo(vals, row_of_nnz, col_of_nnz, n_cells, n_genes, group_of_cell, n_groups, rank_of_cell):
         dev = vals.device
         key = col_of_nnz.to(torch.int64)

@@ -181,7 +181,7 @@ def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_p
     # nonzeros, and the row sums add integers (exact in float64 in any order)
     st.csr = CsrOnDevice(X, dev, pinned)
     st.h2d_bytes += st.csr.h2d_bytes
-    st.seg_all = SegMatrix.from_csr(st.csr)
+    st.seg_all = SegMatrix.from_csr_grouped(st.csr, timer=st.timer)
 
     # naive size factor = raw UMI totals (main.py:55-59); moments over all cells (:62-66)
     naive = st.csr.row_sums(None, st.timer)
@@ -246,9 +246,10 @@ def create_groups(adata, label_columns, label_delimiter="^", inplace=True):
     st.group_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     st.codes = codes
 
-    gid_d = to_device(codes, st.device, np.int32)
-    rank_d = to_device(rank, st.device, np.int32)
-    st.seg = st.seg_all.regroup(gid_d, R, rank_d)
+    if st.csr is not None:      # hand-written counting transposition of the uploaded CSR (csrc/relayout.cu)
+        st.seg = SegMatrix.from_csr_grouped(st.csr, order, st.group_start, timer=st.timer)
+    else:                       # create_groups called again on the same object: regroup the gene-sorted matrix
+        st.seg = st.seg_all.regroup(to_device(codes, st.device, np.int32), R, to_device(rank, st.device, np.int32))
     st.csr = None
     st.gene_index = np.arange(adata.shape[1])
     X = adata.X
