@@ -19,5 +19,4 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)/20
 print("kernel", os.environ.get("MM_MOMENTS_KERNEL","auto"), "threads", os.environ.get("MM_MOMENTS_THREADS","-"), "chunk", os.environ.get("MM_MOMENTS_CHUNK","-"), "notile", os.environ.get("MM_MOMENTS_NOTILE"), "nnz", sg.nnz, "n_seg", sg.n_seg, "ms", round(ms,4), "GB/s", round(sg.moments_bytes()/ms/1e6,1))
 PY
-for k in stream stream_l1; do for t in 512 640 768; do for c in 1 4; do MM_MOMENTS_KERNEL=$k MM_MOMENTS_THREADS=$t MM_MOMENTS_CHUNK=$c timeout 300 python /tmp/mom.py 2>&1 | grep GB/s; done; done; done
-MM_MOMENTS_KERNEL=tile timeout 300 python /tmp/mom.py 2>&1 | grep GB/s
+for c in 4 8; do for t in 640 896; do MM_MOMENTS_KERNEL=stream MM_MOMENTS_CHUNK=$c MM_MOMENTS_THREADS=$t timeout 300 python /tmp/mom.py 2>&1 | grep GB/s; done; done

@@ -100,6 +100,14 @@ struct Mom {
         // counts are non-negative, so the float order is the order of the bit patterns (no FTZ canonicalisation)
         mx = __int_as_float(max(__float_as_int(mx), __float_as_int(v)));
     }
+    // same with x = (double)v and xw = x * w already computed
+    __device__ __forceinline__ void add_terms(float v, double x, double xw, double w) {
+        sx += x;
+        s1 += xw;
+        s2 = fma(xw, w, s2);
+        s3 = fma(xw, xw, s3);
+        mx = __int_as_float(max(__float_as_int(mx), __float_as_int(v)));
+    }
 };
 
 // W lanes cooperate on one segment (W = 8, 16 or 32; 32 / W segments per warp): short segments keep
@@ -539,13 +547,17 @@ __device__ __forceinline__ double warp_sum4(double sx, double s1, double s2, dou
     return keep;      // lanes 0-7: sum sx, 8-15: sum s1, 16-23: sum s2, 24-31: sum s3
 }
 
-template <bool kSmemTable, int kStreamThreads, bool kPrefetch, int kC>
+template <bool kSmemTable, int kStreamThreads, bool kPrefetch, int kC, int kQ>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict__ rows,
                           const long long* __restrict__ seg_ptr, long long n_seg, long long nnz,
                           const int* __restrict__ chunk_seg, const double* __restrict__ inv_sf, int n_cells,
                           double* __restrict__ out, double* __restrict__ edge) {
     extern __shared__ __align__(16) double s_w[];
+    // per-warp window of 32 segment boundaries: read by all lanes with broadcast loads (a register window read
+    // with shuffles costs WARPSYNC + SHFL per access in this divergence-prone control flow)
+    __shared__ int s_bnd[kStreamThreads / 32][32];
+    int* wb = s_bnd[threadIdx.x >> 5];
     if constexpr (kSmemTable) {
         const int n2 = n_cells >> 1;
         for (int i = threadIdx.x; i < n2; i += kStreamThreads)
@@ -556,13 +568,14 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
     const int lane = threadIdx.x & 31;
     // A warp owns chunks of kC consecutive spans and carries its accumulators from span to span, so only the
     // two ends of a chunk can leave partial sums for the edge kernel.
-    constexpr int kChunkElems = kC * kSpanElems;
+    constexpr int kSpanQ = 128 * kQ;                     // nonzeros a warp loads at once (kQ quad rows of 128)
+    constexpr int kChunkElems = kC * kSpanQ;
     const long long n_spans = (nnz + kChunkElems - 1) / kChunkElems;            // chunks ("span" below = chunk index)
     const long long warps_total = (long long)gridDim.x * (kStreamThreads / 32);
     // Boundary metadata is fetched one chunk ahead (it is a chain of two dependent loads: the first segment
     // of the chunk from chunk_seg, then the segment starts from seg_ptr), so it never stalls the reduction.
-    auto first_seg = [&](long long sp) -> int { return (sp <= 0 || sp >= n_spans) ? 0 : __ldg(chunk_seg + sp * kC); };
-    auto last_seg = [&](long long sp) -> int { return sp + 1 < n_spans ? __ldg(chunk_seg + (sp + 1) * kC) : (int)(n_seg - 1); };
+    auto first_seg = [&](long long sp) -> int { return (sp <= 0 || sp >= n_spans) ? 0 : __ldg(chunk_seg + sp * (kChunkElems / kSpanElems)); };
+    auto last_seg = [&](long long sp) -> int { return sp + 1 < n_spans ? __ldg(chunk_seg + (sp + 1) * (kChunkElems / kSpanElems)) : (int)(n_seg - 1); };
     // lane k: clamped chunk-relative start of piece base + k of chunk sp (pieces = segments s0 .. s0 + np - 1)
     auto window = [&](long long sp, int s0, int np, int base) -> int {
         const long long t0 = sp * kChunkElems;
@@ -585,7 +598,10 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
         const int np = s1 - s0 + 1;                      // pieces (segments s0 .. s1) that can touch the span
         int wbase = 0;
         // piece k of the window: [B(k), B(k + 1)); valid for k - wbase <= 30
-        auto B = [&](int k) -> int { return __shfl_sync(kFull, bl, k - wbase); };
+        __syncwarp();
+        wb[lane] = bl;
+        __syncwarp();
+        auto B = [&](int k) -> int { return wb[k - wbase]; };
         int cur = 0;
         int cur_lo = B(0), cur_hi = B(1);
         Mom m;
@@ -594,7 +610,11 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
             // sum xw^2 / sum x^2w^2 and store them themselves (lane 0 also the maximum); empty segments get zeros
             double acc = 0.0;
             float mx = 0.f;
-            if (has_data) { acc = warp_sum4(m.sx, m.s1, m.s2, m.s3, lane); mx = warp_max(m.mx); }
+            if (has_data) {
+                acc = warp_sum4(m.sx, m.s1, m.s2, m.s3, lane);
+                // counts are >= 0: their float order is the order of the bit patterns -> one REDUX instruction
+                mx = __int_as_float(__reduce_max_sync(kFull, __float_as_int(m.mx)));
+            }
             const bool head = cur_lo < 0, tail = cur_hi > n;
             double* dst = (!head && !tail) ? out + ((long long)s0 + cur) : edge + (span * 2 + (head ? 0 : 1)) * 5;
             const long long stride = (!head && !tail) ? n_seg : 1;
@@ -604,7 +624,13 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
         };
         auto advance = [&]() {
             ++cur;
-            if (cur - wbase >= 31) { wbase = cur; bl = window(span, s0, np, wbase); }
+            if (cur - wbase >= 31) {
+                wbase = cur;
+                bl = window(span, s0, np, wbase);
+                __syncwarp();
+                wb[lane] = bl;
+                __syncwarp();
+            }
             cur_lo = B(cur); cur_hi = B(cur + 1);
         };
         // pieces that end at or before element 0 of the span: empty ones located here get zeros
@@ -615,25 +641,25 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
         int from = 0;
 #pragma unroll 1
         for (int j = 0; j < kC; ++j) {
-        const int sp_lo = j * kSpanElems;                    // first element of this span inside the chunk
+        const int sp_lo = j * kSpanQ;                        // first element of this span inside the chunk
         if (sp_lo >= n) break;
         // ---- the next span (of this chunk, or the first of the warp's next chunk) goes to L2 now (one 128-byte
         // line per lane and array): a register-free second buffer, so that its loads are L2 hits
-        if (kPrefetch) {
-            const long long p_lo = (j + 1 < kC ? t_lo + sp_lo + kSpanElems : (span + warps_total) * kChunkElems) + 32 * lane;
+        if (kPrefetch && (sp_lo & 1023) == 0) {              // one prefetch covers 32 lanes x 32 elements = 1024 nonzeros
+            const long long p_lo = (sp_lo + 1024 < kChunkElems ? t_lo + sp_lo + 1024 : (span + warps_total) * kChunkElems) + 32 * lane;
             if (p_lo + 32 <= nnz) { prefetch_l2(vals + p_lo); prefetch_l2(rows + p_lo); }
         }
         // ---- all streaming loads of the span: lane owns elements 128 q + 4 lane + {0..3}, q = 0..3
-        float4 v[4];
-        int4 r[4];
-        if (n - sp_lo >= kSpanElems) {
+        float4 v[kQ];
+        int4 r[kQ];
+        if (n - sp_lo >= kSpanQ) {
             const float4* v4 = reinterpret_cast<const float4*>(vals + t_lo + sp_lo) + lane;
             const int4* r4 = reinterpret_cast<const int4*>(rows + t_lo + sp_lo) + lane;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { v[q] = ld_stream4(v4 + 32 * q); r[q] = ld_stream4(r4 + 32 * q); }
+            for (int q = 0; q < kQ; ++q) { v[q] = ld_stream4(v4 + 32 * q); r[q] = ld_stream4(r4 + 32 * q); }
         } else {     // ragged end of the arrays
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kQ; ++q) {
                 const int e = sp_lo + 128 * q + 4 * lane;
                 v[q].x = e < n ? vals[t_lo + e] : 0.f;         r[q].x = e < n ? rows[t_lo + e] : 0;
                 v[q].y = e + 1 < n ? vals[t_lo + e + 1] : 0.f; r[q].y = e + 1 < n ? rows[t_lo + e + 1] : 0;
@@ -642,23 +668,27 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kQ; ++q) {
             const int row_lo = sp_lo + 128 * q, row_hi = row_lo + 128;
             const int e0 = row_lo + 4 * lane;
             double w0, w1, w2, w3;
             if constexpr (kSmemTable) { w0 = s_w[r[q].x]; w1 = s_w[r[q].y]; w2 = s_w[r[q].z]; w3 = s_w[r[q].w]; }
             else { w0 = __ldg(inv_sf + r[q].x); w1 = __ldg(inv_sf + r[q].y); w2 = __ldg(inv_sf + r[q].z); w3 = __ldg(inv_sf + r[q].w); }
             if (row_lo >= n) continue;
+            // the element terms are computed once; a row that contains segment boundaries only re-does the adds
+            const double x0 = (double)v[q].x, x1 = (double)v[q].y, x2 = (double)v[q].z, x3 = (double)v[q].w;
+            const double p0 = x0 * w0, p1 = x1 * w1, p2 = x2 * w2, p3 = x3 * w3;
             while (true) {
                 const int piece_end = cur_hi > n ? n : cur_hi;
                 const int upto = piece_end < row_hi ? piece_end : row_hi;
                 if (from <= row_lo && upto == row_hi) {
-                    m.add(v[q].x, w0); m.add(v[q].y, w1); m.add(v[q].z, w2); m.add(v[q].w, w3);
+                    m.add_terms(v[q].x, x0, p0, w0); m.add_terms(v[q].y, x1, p1, w1);
+                    m.add_terms(v[q].z, x2, p2, w2); m.add_terms(v[q].w, x3, p3, w3);
                 } else {
-                    if (e0 >= from && e0 < upto) m.add(v[q].x, w0);
-                    if (e0 + 1 >= from && e0 + 1 < upto) m.add(v[q].y, w1);
-                    if (e0 + 2 >= from && e0 + 2 < upto) m.add(v[q].z, w2);
-                    if (e0 + 3 >= from && e0 + 3 < upto) m.add(v[q].w, w3);
+                    if (e0 >= from && e0 < upto) m.add_terms(v[q].x, x0, p0, w0);
+                    if (e0 + 1 >= from && e0 + 1 < upto) m.add_terms(v[q].y, x1, p1, w1);
+                    if (e0 + 2 >= from && e0 + 2 < upto) m.add_terms(v[q].z, x2, p2, w2);
+                    if (e0 + 3 >= from && e0 + 3 < upto) m.add_terms(v[q].w, x3, p3, w3);
                 }
                 if (upto < piece_end) break;                    // `cur` continues in the next row
                 if (cur_hi > n) break;                          // `cur` continues after the span (tail, below)
@@ -849,25 +879,27 @@ static int launch_tile(cudaStream_t st, int n_sm, int regime, const float* vals,
     return check_launch("seg_moments_edge");
 }
 
-template <int kThreads, bool kPrefetch, int kC>
+template <int kThreads, bool kPrefetch, int kC, int kQ>
 static int launch_stream(cudaStream_t st, int n_sm, const float* vals, const int32_t* rows, const long long* sp,
                          long long n_seg, long long nnz, const int32_t* chunk_seg, const double* inv_sf,
                          long long n_cells, double* out, double* edge, bool smem_table) {
-    const long long n_spans = (nnz + kC * kSpanElems - 1) / (kC * kSpanElems);      // chunks of kC spans
+    constexpr int kChunk = kC * kQ * 128;
+    static_assert(kChunk % kSpanElems == 0, "chunks must be whole multiples of the chunk_seg granularity");
+    const long long n_spans = (nnz + kChunk - 1) / kChunk;      // chunks of kC spans
     long long grid = n_sm;
     const long long need = (n_spans + kThreads / 32 - 1) / (kThreads / 32);
     if (grid > need) grid = need;
     if (smem_table) {
         const size_t smem = (size_t)n_cells * sizeof(double);
-        MM_CUDA(cudaFuncSetAttribute(seg_moments_stream_kernel<true, kThreads, kPrefetch, kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        seg_moments_stream_kernel<true, kThreads, kPrefetch, kC><<<(unsigned)grid, kThreads, smem, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
+        MM_CUDA(cudaFuncSetAttribute(seg_moments_stream_kernel<true, kThreads, kPrefetch, kC, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        seg_moments_stream_kernel<true, kThreads, kPrefetch, kC, kQ><<<(unsigned)grid, kThreads, smem, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
                                                                                         inv_sf, (int)n_cells, out, edge);
     } else {
-        seg_moments_stream_kernel<false, kThreads, kPrefetch, kC><<<(unsigned)grid, kThreads, 0, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
+        seg_moments_stream_kernel<false, kThreads, kPrefetch, kC, kQ><<<(unsigned)grid, kThreads, 0, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
                                                                                       inv_sf, (int)n_cells, out, edge);
     }
     if (int s = check_launch("seg_moments_stream")) return s;
-    seg_moments_edge_kernel<kC * kSpanElems><<<(unsigned)((n_spans + 255) / 256), 256, 0, st>>>(sp, n_seg, nnz, chunk_seg, edge, out);
+    seg_moments_edge_kernel<kChunk><<<(unsigned)((n_spans + 255) / 256), 256, 0, st>>>(sp, n_seg, nnz, chunk_seg, edge, out);
     return check_launch("seg_moments_edge");
 }
 
@@ -906,9 +938,11 @@ MM_EXPORT int mm_seg_moments(int device, void* stream, const float* vals, const 
             if (const char* ov = getenv("MM_MOMENTS_THREADS")) threads = atoi(ov);      // tuning hooks
             if (const char* ov = getenv("MM_MOMENTS_PREFETCH")) pf = atoi(ov) != 0;
             int chunk_spans = 4;
-            if (const char* ov = getenv("MM_MOMENTS_CHUNK")) chunk_spans = atoi(ov) == 1 ? 1 : 4;
-#define MM_STREAM(T, PF) (chunk_spans == 1 ? launch_stream<T, PF, 1>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
-                                           : launch_stream<T, PF, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table))
+            if (const char* ov = getenv("MM_MOMENTS_CHUNK")) { int c = atoi(ov); chunk_spans = (c == 1 || c == 8) ? c : 4; }   // 8: 256-nonzero spans
+#define MM_STREAM(T, PF) (chunk_spans == 1 ? launch_stream<T, PF, 1, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
+                        : chunk_spans == 8 ? launch_stream<T, PF, 8, 2>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
+                                           : launch_stream<T, PF, 4, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table))
+            if (threads == 896) return pf ? MM_STREAM(896, true) : MM_STREAM(896, false);
             if (threads == 768) return pf ? MM_STREAM(768, true) : MM_STREAM(768, false);
             if (threads == 512) return pf ? MM_STREAM(512, true) : MM_STREAM(512, false);
             return pf ? MM_STREAM(640, true) : MM_STREAM(640, false);

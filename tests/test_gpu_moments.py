@@ -105,6 +105,14 @@ def test_seg_moments_stream_single_span_chunks(name, monkeypatch):
     _run(CASES[name], seed=8)
 
 
+@pytest.mark.parametrize("name", ["exact_span_edges", "exact_chunk_edges", "window_of_31", "ragged_end3", "mixed"])
+def test_seg_moments_stream_short_spans(name, monkeypatch):
+    monkeypatch.setenv("MM_MOMENTS_KERNEL", "stream")
+    monkeypatch.setenv("MM_MOMENTS_CHUNK", "8")
+    monkeypatch.setenv("MM_MOMENTS_THREADS", "896")
+    _run(CASES[name], seed=9)
+
+
 def test_seg_moments_table_too_large_for_smem(monkeypatch):
     monkeypatch.setenv("MM_MOMENTS_KERNEL", "stream")
     _run(CASES["mixed"], n_cells=40000, seed=7)
