@@ -122,6 +122,9 @@ int mm_seg_unique(int device, void* stream, const float* vals, const int32_t* ro
  * highest power first.  seg_skip (nullable): segments not to compute.  gene_id (nullable,
  * [n_seg / R]): global gene ids used in the RNG counter so that results do not depend on gene tiling
  * or sharding.
+ * log_rows != 0: out_mean / out_rv are the [n_seg][num_boot + 1] rows the regression reads; replicate b goes to
+ * column b + 1 as log(value), or NaN where the value is <= 0 or NaN, and n_invalid[2 s + {0, 1}] (zero-initialised
+ * by the caller) counts those NaNs, so that mm_fill_log (in-place mode) only has to visit the segments that have any.
  * Replaces: memento/bootstrap.py:74-116 (_bootstrap_1d), estimator.py:171-174 (tuple form),
  * hypothesis_test.py:186 -> estimator.py:103-111 (_residual_variance per replicate). */
 int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t* seg_ptr,
@@ -129,7 +132,7 @@ int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t
                     const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                     int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
                     const void* seg_info, const void* tab_pool, const uint32_t* acc_pool,
-                    double* out_mean, double* out_rv);
+                    double* out_mean, double* out_rv, int32_t log_rows, int32_t* n_invalid);
 
 /* Poissonised sampler support (see csrc/bootstrap.cu header).  seg_info == NULL in mm_bootstrap_1d
  * selects the conditional-binomial chain for every segment.
@@ -165,12 +168,14 @@ int mm_bootstrap_1d_replay(int device, void* stream, const double* x, const doub
  * row, then log; column 0 = log of the point estimate.  seg_ok = a-priori validity of the row;
  * seg_good (out) = seg_ok and at least one valid replicate of both statistics.  src_mean / src_rv
  * (nullable) replay host-supplied source indices instead of drawing.  boot_* are [n_seg][num_boot+1].
+ * In-place mode (raw_mean == raw_rv == NULL): boot_* already hold the log rows written by mm_bootstrap_1d with
+ * log_rows != 0 and n_invalid its counters; only column 0 and the NaN entries are written.
  * Replaces: memento/hypothesis_test.py:23-33 (_fill), :167-200 of _ht_1d. */
 int mm_fill_log(int device, void* stream, const double* raw_mean, const double* raw_rv,
                 const uint8_t* seg_ok, const double* true_mean, const double* true_rv,
                 const int32_t* src_mean, const int32_t* src_rv, const int64_t* gene_id, int32_t R,
                 int64_t n_seg, int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
-                uint8_t* seg_good, int32_t* n_valid);
+                uint8_t* seg_good, int32_t* n_valid, const int32_t* n_invalid);
 
 /* Batched small solves: for each of n_mask group-validity masks, the (T x R) linear functional C
  * with coef[t] = sum_r C[t,r] * y[r] equal to "residualise y and treatment on [1, covariate] with

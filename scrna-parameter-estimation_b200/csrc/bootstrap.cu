@@ -297,9 +297,28 @@ struct BootParams {
     const uint2* tab_pool;      // universal Poisson alias tables
     const uint32_t* acc_pool;   // acceptance tables
     int reps_per_block;         // replicates handled by one block of the Poisson kernel
-    double* out_mean;           // [n_seg][B]
-    double* out_rv;             // [n_seg][B]
+    double* out_mean;           // [n_seg][B], or the log rows [n_seg][B + 1] (columns 1 ..) when log_rows != 0
+    double* out_rv;
+    int log_rows;               // 1: write log(mean), log(res. var.) into the [B + 1] rows, NaN + counter where <= 0
+    int* n_invalid;             // [n_seg][2] replicates with a non-positive mean / residual variance (log_rows)
 };
+
+// one replicate's result: raw values, or (log_rows) their logs in the rows the regression reads -- the imputation
+// pass then only has to touch the segments that counted an invalid replicate
+__device__ __forceinline__ void store_replicate(const BootParams& P, long long seg_rel, int b, double mean, double rv) {
+    if (!P.log_rows) {
+        const long long o = seg_rel * (long long)P.B + b;
+        P.out_mean[o] = mean;
+        P.out_rv[o] = rv;
+        return;
+    }
+    const long long o = seg_rel * (long long)(P.B + 1) + 1 + b;
+    const bool okm = mean > 0.0, okv = rv > 0.0;
+    P.out_mean[o] = okm ? log(mean) : nan("");
+    P.out_rv[o] = okv ? log(rv) : nan("");
+    if (!okm) atomicAdd(P.n_invalid + 2 * seg_rel, 1);
+    if (!okv) atomicAdd(P.n_invalid + 2 * seg_rel + 1, 1);
+}
 
 __device__ __forceinline__ void finish_replicate(double M1, double M2, double n, int estimator,
                                                  const double* fit, double& mean, double& rv) {
@@ -323,8 +342,7 @@ bootstrap_1d_kernel(BootParams P) {
     const long long seg = P.seg_lo + seg_rel;
     const int r = (int)(seg % P.R);
     const int U = P.seg_U[seg_rel];
-    const long long o = seg_rel * (long long)P.B + b;
-    if (U < 0) { P.out_mean[o] = nan(""); P.out_rv[o] = nan(""); return; }
+    if (U < 0) { store_replicate(P, seg_rel, b, nan(""), nan("")); return; }
     if (P.info && P.info[seg_rel].mode == 1) return;      // handled by the Poissonised kernel
     const BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
     const int n_cells = P.group_ncells[r];
@@ -352,8 +370,7 @@ bootstrap_1d_kernel(BootParams P) {
     }
     double mean, rv;
     finish_replicate(M1, M2, (double)n_cells, P.estimator, P.mv_fit + 3 * r, mean, rv);
-    P.out_mean[o] = mean;
-    P.out_rv[o] = rv;
+    store_replicate(P, seg_rel, b, mean, rv);
 }
 
 // ---------------------------------------------------------------- Poissonised sampler
@@ -416,9 +433,7 @@ bootstrap_1d_poisson_kernel(BootParams P) {
             M2 = fma(si.rem_b, w, M2);
             double mean, rv;
             finish_replicate(M1, M2, (double)N, P.estimator, fit, mean, rv);
-            const long long o = seg_rel * (long long)P.B + b;
-            P.out_mean[o] = mean;
-            P.out_rv[o] = rv;
+            store_replicate(P, seg_rel, b, mean, rv);
             b = atomicAdd(&s_next, 1);                   // results depend on (seed, b) only, not on the lane
             fresh = true;
         }
@@ -525,7 +540,7 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
                               const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                               int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
                               const void* seg_info, const void* tab_pool, const uint32_t* acc_pool,
-                              double* out_mean, double* out_rv) {
+                              double* out_mean, double* out_rv, int32_t log_rows, int32_t* n_invalid) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_seg >= 0 && R > 0 && num_boot > 0, "n_seg/R/num_boot");
     MM_REQUIRE(n_seg <= 65535, "at most 65535 segments per launch (tile the genes)");
@@ -537,6 +552,8 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     P.n_seg = n_seg; P.R = R; P.seg_U = seg_U; P.seg_skip = seg_skip; P.group_ncells = group_ncells;
     P.mv_fit = mv_fit; P.estimator = estimator; P.B = num_boot; P.seed = seed;
     P.gene_id = (const long long*)gene_id; P.out_mean = out_mean; P.out_rv = out_rv;
+    P.log_rows = log_rows; P.n_invalid = n_invalid;
+    MM_REQUIRE(!log_rows || n_invalid, "log_rows needs the n_invalid counters (zero-initialised)");
     P.info = (const SegInfo*)seg_info; P.tab_pool = (const uint2*)tab_pool; P.acc_pool = acc_pool;
     // a block covers 20 replicates per lane of one segment; lanes claim replicates from a shared counter,
     // so rejections do not leave lanes idle at the end of the range

@@ -37,6 +37,7 @@ struct FillParams {
     double* boot_var;           // [n_seg][B+1]
     unsigned char* seg_good;    // [n_seg] final validity
     int* n_valid;               // [n_seg][2]
+    const int* n_invalid;       // in-place mode (raw_mean == null): [n_seg][2] invalid replicates counted by the bootstrap
 };
 
 __device__ __forceinline__ double pick_valid(const double* row, int B, int n_valid, Philox& rng) {
@@ -112,6 +113,70 @@ fill_log_kernel(FillParams P) {
         }
         om[b + 1] = log(m);
         ov[b + 1] = log(v);
+    }
+}
+
+// In-place variant: the bootstrap kernels already wrote log(mean) / log(res. var.) into columns 1 .. B of the rows
+// (NaN where the value was <= 0) and counted those NaNs per segment.  A segment without invalid replicates -- almost
+// all of them -- only needs column 0; the others build a bit mask of their invalid columns in shared memory and
+// impute each of them from a uniformly drawn VALID column (valid columns are never written, so this is race free
+// and does not depend on the order in which the threads run).
+constexpr int kFillMaskWords = 2048;     // covers num_boot <= 65536
+
+__device__ __forceinline__ double pick_valid_masked(const double* row, const unsigned* mask, int B, int n_valid, Philox& rng) {
+    for (int it = 0; it < 256; ++it) {
+        int j = (int)(rng.uniform() * (float)B);
+        if (j >= B) j = B - 1;
+        if (!((mask[j >> 5] >> (j & 31)) & 1u)) return row[j];
+    }
+    int want = (int)(rng.uniform() * (float)n_valid);
+    if (want >= n_valid) want = n_valid - 1;
+    for (int j = 0; j < B; ++j)
+        if (!((mask[j >> 5] >> (j & 31)) & 1u) && want-- == 0) return row[j];
+    return nan("");
+}
+
+__global__ void __launch_bounds__(kRegThreads)
+fill_rows_kernel(FillParams P) {
+    __shared__ unsigned s_mask[2][kFillMaskWords];
+    const long long seg = blockIdx.x;
+    const int B = P.B;
+    double* om = P.boot_mean + seg * (long long)(B + 1);
+    double* ov = P.boot_var + seg * (long long)(B + 1);
+    const int im = P.n_invalid[2 * seg], iv = P.n_invalid[2 * seg + 1];
+    const int nvm = B - im, nvr = B - iv;
+    const bool ok = P.seg_ok[seg] != 0 && nvm > 0 && nvr > 0;
+    if (threadIdx.x == 0) {
+        P.seg_good[seg] = ok ? 1 : 0;
+        P.n_valid[2 * seg] = nvm;
+        P.n_valid[2 * seg + 1] = nvr;
+    }
+    if (!ok) {
+        for (int b = threadIdx.x; b <= B; b += kRegThreads) { om[b] = nan(""); ov[b] = nan(""); }
+        return;
+    }
+    if (threadIdx.x == 0) { om[0] = log(P.true_mean[seg]); ov[0] = log(P.true_rv[seg]); }
+    if (im == 0 && iv == 0) return;
+    const int words = (B + 31) >> 5;
+    for (int i = threadIdx.x; i < words; i += kRegThreads) { s_mask[0][i] = 0u; s_mask[1][i] = 0u; }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += kRegThreads) {
+        if (isnan(om[b + 1])) atomicOr(&s_mask[0][b >> 5], 1u << (b & 31));
+        if (isnan(ov[b + 1])) atomicOr(&s_mask[1][b >> 5], 1u << (b & 31));
+    }
+    __syncthreads();
+    const long long sid = P.gene_id ? P.gene_id[seg / P.R] * P.R + (seg % P.R) : seg;
+    for (int b = threadIdx.x; b < B; b += kRegThreads) {
+        if ((s_mask[0][b >> 5] >> (b & 31)) & 1u) {
+            Philox rng;
+            rng.init(P.seed, (uint32_t)b, (uint32_t)sid, (uint32_t)(sid >> 32), 0xF111u);
+            om[b + 1] = pick_valid_masked(om + 1, s_mask[0], B, nvm, rng);
+        }
+        if ((s_mask[1][b >> 5] >> (b & 31)) & 1u) {
+            Philox rng;
+            rng.init(P.seed, (uint32_t)b, (uint32_t)sid, (uint32_t)(sid >> 32), 0xF112u);
+            ov[b + 1] = pick_valid_masked(ov + 1, s_mask[1], B, nvr, rng);
+        }
     }
 }
 
@@ -647,19 +712,24 @@ MM_EXPORT int mm_fill_log(int device, void* stream, const double* raw_mean, cons
                           const uint8_t* seg_ok, const double* true_mean, const double* true_rv,
                           const int32_t* src_mean, const int32_t* src_rv, const int64_t* gene_id, int32_t R,
                           int64_t n_seg, int32_t num_boot, uint64_t seed, double* boot_mean, double* boot_var,
-                          uint8_t* seg_good, int32_t* n_valid) {
+                          uint8_t* seg_good, int32_t* n_valid, const int32_t* n_invalid) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_seg >= 0 && num_boot > 0 && R > 0, "n_seg/num_boot/R");
     if (n_seg == 0) return 0;
-    MM_REQUIRE(raw_mean && raw_rv && seg_ok && true_mean && true_rv && boot_mean && boot_var && seg_good && n_valid,
-               "null pointer");
+    const bool in_place = raw_mean == nullptr;
+    MM_REQUIRE(seg_ok && true_mean && true_rv && boot_mean && boot_var && seg_good && n_valid, "null pointer");
+    MM_REQUIRE(in_place ? (n_invalid != nullptr && raw_rv == nullptr && !src_mean && !src_rv) : (raw_rv != nullptr),
+               "raw rows, or (in-place mode) the invalid counters of mm_bootstrap_1d with log_rows");
+    MM_REQUIRE(!in_place || num_boot <= 32 * kFillMaskWords, "in-place mode supports num_boot <= 65536");
     MM_REQUIRE(n_seg < 2147483647LL, "n_seg");
     FillParams P;
     P.raw_mean = raw_mean; P.raw_rv = raw_rv; P.seg_ok = seg_ok; P.true_mean = true_mean; P.true_rv = true_rv;
     P.src_mean = src_mean; P.src_rv = src_rv; P.gene_id = (const long long*)gene_id; P.R = R; P.B = num_boot;
     P.seed = seed;
     P.boot_mean = boot_mean; P.boot_var = boot_var; P.seg_good = seg_good; P.n_valid = n_valid;
-    fill_log_kernel<<<(unsigned)n_seg, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    P.n_invalid = n_invalid;
+    if (in_place) fill_rows_kernel<<<(unsigned)n_seg, kRegThreads, 0, (cudaStream_t)stream>>>(P);
+    else fill_log_kernel<<<(unsigned)n_seg, kRegThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_fill_log");
 }
 

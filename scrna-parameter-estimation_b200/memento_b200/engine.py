@@ -178,14 +178,18 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
 
 
 def bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip=None, gene_id=None,
-                   sampler="poisson", min_accept=0.2, timer=NULL_TIMER):
+                   sampler="poisson", min_accept=0.2, timer=NULL_TIMER, log_rows=None):
     """mm_boot_prepare (Poissonised sampler only) + mm_bootstrap_1d on the unique tables ``tab`` of a
     gene tile.  Returns (raw_mean, raw_rv, seg_info) device tensors; raw_* are [n_seg * num_boot]."""
     dev = seg.device
     R = seg.R
     n_seg = n_genes * R
-    raw_mean = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
-    raw_rv = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
+    if log_rows is None:
+        raw_mean = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
+        raw_rv = torch.empty(n_seg * num_boot, dtype=torch.float64, device=dev)
+        n_invalid = None
+    else:       # (boot_mean, boot_var, n_invalid): the kernels write log values straight into the regression's rows
+        raw_mean, raw_rv, n_invalid = log_rows
     seg_info = tab_pool = acc_pool = None
     if sampler == "poisson":
         tab_off, tab_pool = poisson_tables(dev)
@@ -199,7 +203,7 @@ def bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_ski
     ev = timer.start()
     _lib.call("mm_bootstrap_1d", dev, tab["entries"], seg.seg_ptr, tab["seg_lo"], n_seg, R, tab["seg_U"],
               seg_skip, design.n_cells, design.mv_fit, estimator, num_boot, seed, gene_id, seg_info, tab_pool,
-              acc_pool, raw_mean, raw_rv)
+              acc_pool, raw_mean, raw_rv, 0 if log_rows is None else 1, n_invalid)
     timer.stop("bootstrap_1d", ev)
     return raw_mean, raw_rv, seg_info
 
@@ -226,15 +230,18 @@ def ht_1d_tile_boot(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv,
     seg_skip = (seg_ok == 0).to(torch.uint8)
     tm = torch.as_tensor(np.ascontiguousarray(true_mean.reshape(-1), dtype=np.float64), device=dev)
     tv = torch.as_tensor(np.ascontiguousarray(true_rv.reshape(-1), dtype=np.float64), device=dev)
-    raw_mean, raw_rv, seg_info = bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip,
-                                                gene_id, sampler, min_accept, timer)
+    # the bootstrap kernels write log(mean) / log(res. var.) straight into the rows the regression reads and count
+    # the replicates they could not take the log of; the imputation pass then only visits segments that have any
     boot_mean = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
     boot_var = torch.empty(n_seg * (num_boot + 1), dtype=torch.float64, device=dev)
+    n_invalid = torch.zeros(2 * n_seg, dtype=torch.int32, device=dev)
+    _, _, seg_info = bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip, gene_id, sampler,
+                                    min_accept, timer, log_rows=(boot_mean, boot_var, n_invalid))
     seg_good = torch.empty(n_seg, dtype=torch.uint8, device=dev)
     n_valid = torch.empty(2 * n_seg, dtype=torch.int32, device=dev)
     ev = timer.start()
-    _lib.call("mm_fill_log", dev, raw_mean, raw_rv, seg_ok, tm, tv, None, None, gene_id, R, n_seg, num_boot,
-              seed, boot_mean, boot_var, seg_good, n_valid)
+    _lib.call("mm_fill_log", dev, None, None, seg_ok, tm, tv, None, None, gene_id, R, n_seg, num_boot,
+              seed, boot_mean, boot_var, seg_good, n_valid, n_invalid)
     timer.stop("fill_log", ev)
     # the validity flags go to pinned host memory right behind fill_log, so that the regression half can read them
     # as soon as THIS tile is done, whatever has been queued after it
@@ -333,7 +340,7 @@ def ht_1d_replay(device, R, replay, design_host, true_mean, true_rv, covariate, 
     src_v = d(replay["src_rv"], np.int32) if replay.get("src_rv") is not None else None
     _lib.call("mm_fill_log", device, raw_mean, raw_rv, seg_ok, d(true_mean.reshape(-1), np.float64),
               d(true_rv.reshape(-1), np.float64), src_m, src_v, None, R, n_seg, num_boot, 0, boot_mean, boot_var,
-              seg_good, n_valid)
+              seg_good, n_valid, None)
     res_keep = {"boot_mean": boot_mean.clone().view(n_seg, num_boot + 1), "boot_var": boot_var.clone().view(n_seg, num_boot + 1)}
     assign = (replay["rep_assign"], replay["iter_assign"]) if (resample_rep and replay.get("rep_assign") is not None) else None
     res = regress_tile(device, boot_mean, boot_var, seg_good, R, T, num_boot, covariate, treatment,
