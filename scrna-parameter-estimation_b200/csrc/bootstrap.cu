@@ -28,6 +28,7 @@
 // multiplicity above the table range, use the chain.  Each lane loops over its own replicates and simply retries on rejection, so
 // rejections cost their expected value, not a warp-wide maximum.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mm {
 
@@ -375,8 +376,30 @@ bootstrap_1d_kernel(BootParams P) {
 
 // ---------------------------------------------------------------- Poissonised sampler
 // Block = kBootThreads lanes, each looping over its own replicates of one segment (see header).
-__global__ void __launch_bounds__(kBootThreads)
+//
+// kFast (default) trims the three non-essential costs of the loop, measured in the SASS of the plain variant
+// (107 instructions per 4 draws, 40 of them Philox; ~490 per replicate outside the loop):
+//   * Philox4x32-7 instead of -10 (see Philox::rounds): 28 instead of 40 instructions per 4 draws;
+//   * count -> float64 by the 2^52 trick (one DADD on the FP64 pipe instead of I2F.F64 on the quarter-rate XU pipe);
+//   * log rows written directly: log(mean) and log(var) by the table-driven log_pos (no fp64 division, no
+//     exp / log round trip for the residual variance: log rv = log var - poly(log mean)).
+// The plain variant is kept for A/B measurements (MM_BOOT_PLAIN=1) and for raw (non-log) output rows.
+__device__ __forceinline__ double count_to_double(int k) {        // k >= 0
+    return __hiloint2double(0x43300000, k) - 4503599627370496.0;
+}
+
+// kSlots > 1: every lane runs kSlots replicates in lockstep over the same categories, so the warp-uniform 32-byte
+// category record is loaded once per kSlots draws.  ncu on the one-slot kernel: L1 data-pipe wavefronts are its most
+// loaded unit (67 %), and 8 of the 10 wavefronts of a draw are the record (32 lanes x 32 B written back to registers,
+// uniform address or not) -- two slots cut that to 6 per draw and amortise the record unpacking and loop overhead
+// (25 -> 19 instructions per draw).  A pass over one segment has the same length for every replicate, so slots never
+// wait for each other: an accepted slot claims the next replicate, a rejected one repeats its own.  The random numbers
+// of a replicate depend on (seed, replicate, segment, attempt) only, so every kSlots gives bit-identical rows.
+template <int kVariant, int kSlots>      // kVariant 0: plain, 1: Philox-7 + direct log rows, 2: 1 + 2^52 conversion
+__global__ void __launch_bounds__(kBootThreads, kVariant ? (kSlots == 1 ? 8 : kSlots == 2 ? 6 : kSlots == 3 ? 5 : 4) : 0)
 bootstrap_1d_poisson_kernel(BootParams P) {
+    constexpr bool kFast = kVariant > 0;
+    constexpr int kR = kFast ? 7 : 10;
     const long long seg_rel = blockIdx.y;
     if (P.seg_skip && P.seg_skip[seg_rel]) return;
     const SegInfo si = P.info[seg_rel];
@@ -391,51 +414,116 @@ bootstrap_1d_poisson_kernel(BootParams P) {
     const double* fit = P.mv_fit + 3 * r;
     const int b_end = min(P.B, (int)(blockIdx.x + 1) * P.reps_per_block);
     __shared__ int s_next;
-    if (threadIdx.x == 0) s_next = blockIdx.x * P.reps_per_block + kBootThreads;
+    __shared__ double2 s_log[kFast ? 128 : 1];
+    static_assert(kBootThreads >= 128, "one log-table entry per thread");
+    if (kFast && threadIdx.x < 128) log_tab_fill(s_log, threadIdx.x);
+    if (threadIdx.x == 0) s_next = blockIdx.x * P.reps_per_block + kSlots * kBootThreads;
     __syncthreads();
-    int b = blockIdx.x * P.reps_per_block + threadIdx.x;
-    Philox rng;
-    bool fresh = true;
-    while (b < b_end) {
-        if (fresh) { rng.init(P.seed, (uint32_t)b, (uint32_t)sid, 0u, (uint32_t)(sid >> 32) ^ 0x9015u); fresh = false; }
-        int S = 0;
-        double M1 = 0.0, M2 = 0.0;
-        // four categories per Philox block; the remainder category has len == 0 and table cell {0, 0},
-        // so it contributes k = 0 without a branch
-        auto draw = [&](int u, uint32_t rnd) {
-            const int4 lo4 = __ldg(reinterpret_cast<const int4*>(tab + u));
-            const int4 hi4 = __ldg(reinterpret_cast<const int4*>(tab + u) + 1);
+    const double inv_n = 1.0 / (double)N;
+    const double f0 = fit[0], f1 = fit[1], f2 = fit[2];
+    // Philox counter = (replicate, segment lo, block number, segment hi ^ tag); the block number runs on over the
+    // attempts of one replicate and restarts with a new replicate
+    const uint32_t key0 = (uint32_t)P.seed, key1 = (uint32_t)(P.seed >> 32);
+    const uint32_t c1 = (uint32_t)sid, c3 = (uint32_t)(sid >> 32) ^ 0x9015u;
+    int b[kSlots];
+    uint32_t blk[kSlots];
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j) { b[j] = blockIdx.x * P.reps_per_block + j * kBootThreads + threadIdx.x; blk[j] = 0; }
+    auto live = [&]() {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) any |= b[j] < b_end;
+        return any;
+    };
+    while (live()) {
+        int S[kSlots];
+        double M1[kSlots], M2[kSlots];
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) { S[j] = 0; M1[j] = 0.0; M2[j] = 0.0; }
+        auto fresh4 = [&](int j) {
+            return Philox::rounds<kR>(make_uint4((uint32_t)b[j], c1, blk[j]++, c3), key0, key1);
+        };
+        // the remainder category has len == 0 and table cell {0, 0}, so it contributes k = 0 without a branch
+        auto draw = [&](int j, const int4& lo4, const int4& hi4, uint32_t rnd) {
             const int k = alias_draw(P.tab_pool, (unsigned)hi4.x, (unsigned)hi4.y, hi4.w, rnd);
-            S += k;
-            const double kd = (double)k;
-            M1 = fma(__hiloint2double(lo4.y, lo4.x), kd, M1);
-            M2 = fma(__hiloint2double(lo4.w, lo4.z), kd, M2);
+            S[j] += k;
+            const double kd = kVariant == 2 ? count_to_double(k) : (double)k;
+            M1[j] = fma(__hiloint2double(lo4.y, lo4.x), kd, M1[j]);
+            M2[j] = fma(__hiloint2double(lo4.w, lo4.z), kd, M2[j]);
         };
         int u = 0;
-        for (; u + 4 <= U; u += 4) {
-            const uint4 r4 = rng.block();
-            draw(u, r4.x); draw(u + 1, r4.y); draw(u + 2, r4.z); draw(u + 3, r4.w);
+        for (; u + 4 <= U; u += 4) {        // four categories per Philox block
+            int4 lo4[4], hi4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                lo4[c] = __ldg(reinterpret_cast<const int4*>(tab + u + c));
+                hi4[c] = __ldg(reinterpret_cast<const int4*>(tab + u + c) + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) {
+                const uint4 r4 = fresh4(j);
+                draw(j, lo4[0], hi4[0], r4.x); draw(j, lo4[1], hi4[1], r4.y);
+                draw(j, lo4[2], hi4[2], r4.z); draw(j, lo4[3], hi4[3], r4.w);
+            }
         }
-        uint4 r4 = rng.block();
-        if (u < U) draw(u, r4.x);
-        if (u + 1 < U) draw(u + 1, r4.y);
-        if (u + 2 < U) draw(u + 2, r4.z);
-        if (si.zero_off >= 0)
-            S += alias_draw(P.tab_pool, (unsigned)si.zero_off, (unsigned)(si.zero_kl & 0xFFFF),
-                            (si.zero_kl >> 16) - si.zero_off, r4.w);
-        r4 = rng.block();
-        const int i = S - si.s_lo;
-        bool ok = (i >= 0) && (i < si.acc_len);
-        if (ok) ok = r4.x < __ldg(acc + i);
-        if (ok) {
-            const double w = (double)(N - S);            // the remainder category takes the rest
-            M1 = fma(si.rem_a, w, M1);
-            M2 = fma(si.rem_b, w, M2);
-            double mean, rv;
-            finish_replicate(M1, M2, (double)N, P.estimator, fit, mean, rv);
-            store_replicate(P, seg_rel, b, mean, rv);
-            b = atomicAdd(&s_next, 1);                   // results depend on (seed, b) only, not on the lane
-            fresh = true;
+        uint4 r4[kSlots];
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) r4[j] = fresh4(j);
+        if (u < U) {
+            const int4 lo4 = __ldg(reinterpret_cast<const int4*>(tab + u)), hi4 = __ldg(reinterpret_cast<const int4*>(tab + u) + 1);
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) draw(j, lo4, hi4, r4[j].x);
+        }
+        if (u + 1 < U) {
+            const int4 lo4 = __ldg(reinterpret_cast<const int4*>(tab + u + 1)), hi4 = __ldg(reinterpret_cast<const int4*>(tab + u + 1) + 1);
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) draw(j, lo4, hi4, r4[j].y);
+        }
+        if (u + 2 < U) {
+            const int4 lo4 = __ldg(reinterpret_cast<const int4*>(tab + u + 2)), hi4 = __ldg(reinterpret_cast<const int4*>(tab + u + 2) + 1);
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) draw(j, lo4, hi4, r4[j].z);
+        }
+        if (si.zero_off >= 0) {
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j)
+                S[j] += alias_draw(P.tab_pool, (unsigned)si.zero_off, (unsigned)(si.zero_kl & 0xFFFF),
+                                   (si.zero_kl >> 16) - si.zero_off, r4[j].w);
+        }
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+            const uint4 ra = fresh4(j);
+            const int i = S[j] - si.s_lo;
+            bool ok = (i >= 0) && (i < si.acc_len) && (b[j] < b_end);
+            if (ok) ok = ra.x < __ldg(acc + i);
+            if (ok) {
+                const double w = (double)(N - S[j]);            // the remainder category takes the rest
+                const double m1 = fma(si.rem_a, w, M1[j]), m2 = fma(si.rem_b, w, M2[j]);
+                if (kFast && P.log_rows) {
+                    double mean, var;
+                    if (P.estimator == 0) { mean = m1 * inv_n; var = m2 * inv_n - mean * mean; }
+                    else { mean = m1 * inv_n + 1.0; var = 10.0; }
+                    const long long o = seg_rel * (long long)(P.B + 1) + 1 + b[j];
+                    double lm = nan(""), lrv = nan("");
+                    if (mean > 0.0) {
+                        lm = log_pos(mean, s_log);
+                        if (var > 0.0) lrv = log_pos(var, s_log) - ((f0 * lm + f1) * lm + f2);
+                    } else {
+                        atomicAdd(P.n_invalid + 2 * seg_rel, 1);
+                    }
+                    // (an infinite log rv -- residual variance overflow -- counts as valid, as exp() -> inf does in
+                    // the reference; NaN covers var <= 0 and mean <= 0)
+                    if (!(lrv == lrv)) atomicAdd(P.n_invalid + 2 * seg_rel + 1, 1);
+                    P.out_mean[o] = lm;
+                    P.out_rv[o] = lrv;
+                } else {
+                    double mean, rv;
+                    finish_replicate(m1, m2, (double)N, P.estimator, fit, mean, rv);
+                    store_replicate(P, seg_rel, b[j], mean, rv);
+                }
+                b[j] = atomicAdd(&s_next, 1);                // results depend on (seed, replicate) only, not on the lane
+                blk[j] = 0;
+            }
         }
     }
 }
@@ -555,16 +643,26 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     P.log_rows = log_rows; P.n_invalid = n_invalid;
     MM_REQUIRE(!log_rows || n_invalid, "log_rows needs the n_invalid counters (zero-initialised)");
     P.info = (const SegInfo*)seg_info; P.tab_pool = (const uint2*)tab_pool; P.acc_pool = acc_pool;
-    // a block covers 20 replicates per lane of one segment; lanes claim replicates from a shared counter,
+    // a block covers 20 replicates per lane and slot of one segment; lanes claim replicates from a shared counter,
     // so rejections do not leave lanes idle at the end of the range
-    P.reps_per_block = kBootThreads * 20;
+    const int variant = getenv("MM_BOOT_VARIANT") ? atoi(getenv("MM_BOOT_VARIANT")) : 1;     // A/B hooks
+    const int slots = getenv("MM_BOOT_SLOTS") ? atoi(getenv("MM_BOOT_SLOTS")) : 2;
+    const int n_slots = (variant == 0 || slots <= 1) ? 1 : (slots >= 4 ? 4 : slots);
+    P.reps_per_block = kBootThreads * 20 * n_slots;
     MM_REQUIRE(!seg_info || (tab_pool && acc_pool), "seg_info needs tab_pool and acc_pool");
     dim3 grid((num_boot + kBootThreads - 1) / kBootThreads, (unsigned)n_seg);
     bootstrap_1d_kernel<<<grid, kBootThreads, 0, (cudaStream_t)stream>>>(P);
     if (int s = check_launch("mm_bootstrap_1d (chain)")) return s;
     if (seg_info) {
         dim3 grid2((num_boot + P.reps_per_block - 1) / P.reps_per_block, (unsigned)n_seg);
-        bootstrap_1d_poisson_kernel<<<grid2, kBootThreads, 0, (cudaStream_t)stream>>>(P);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (variant == 0) bootstrap_1d_poisson_kernel<0, 1><<<grid2, kBootThreads, 0, st>>>(P);
+        else if (variant == 2 && n_slots == 1) bootstrap_1d_poisson_kernel<2, 1><<<grid2, kBootThreads, 0, st>>>(P);
+        else if (variant == 2 && n_slots == 2) bootstrap_1d_poisson_kernel<2, 2><<<grid2, kBootThreads, 0, st>>>(P);
+        else if (n_slots == 1) bootstrap_1d_poisson_kernel<1, 1><<<grid2, kBootThreads, 0, st>>>(P);
+        else if (n_slots == 3) bootstrap_1d_poisson_kernel<1, 3><<<grid2, kBootThreads, 0, st>>>(P);
+        else if (n_slots == 4) bootstrap_1d_poisson_kernel<1, 4><<<grid2, kBootThreads, 0, st>>>(P);
+        else bootstrap_1d_poisson_kernel<1, 2><<<grid2, kBootThreads, 0, st>>>(P);
     }
     return check_launch("mm_bootstrap_1d");
 }

@@ -137,10 +137,14 @@ struct Philox {
         ctr = make_uint4(c0, c1, c2, c3);
         have = 0;
     }
-    __device__ __forceinline__ static uint4 round10(uint4 c, uint32_t k0, uint32_t k1) {
+    // kRounds = 10 is the Random123 / cuRAND default; 7 is the smallest round count of Philox4x32 that its authors
+    // report as passing the full BigCrush battery ("Crush-resistant", Salmon et al., SC'11, table 2) -- used by the
+    // Poissonised samplers, whose inner loop is 40 % Philox at 10 rounds
+    template <int kRounds>
+    __device__ __forceinline__ static uint4 rounds(uint4 c, uint32_t k0, uint32_t k1) {
         constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
+        for (int i = 0; i < kRounds; ++i) {
             uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
             uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
             c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
@@ -149,9 +153,11 @@ struct Philox {
         }
         return c;
     }
+    __device__ __forceinline__ static uint4 round10(uint4 c, uint32_t k0, uint32_t k1) { return rounds<10>(c, k0, k1); }
     // four fresh words (does not touch the word buffer of next())
+    template <int kRounds = 10>
     __device__ __forceinline__ uint4 block() {
-        uint4 o = round10(ctr, key0, key1);
+        uint4 o = rounds<kRounds>(ctr, key0, key1);
         ctr.z += 1;
         return o;
     }
@@ -168,6 +174,31 @@ struct Philox {
     // uniform in (0, 1): 24 random bits, never 0 or 1
     __device__ __forceinline__ float uniform() { return ((next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 };
+
+// ---------------------------------------------------------------- log of a positive float64, table driven
+// log(x) = e ln 2 + log(c_i) + log1p(m / c_i - 1): x = 2^e m, m in [1, 2), i = top 7 mantissa bits, c_i the midpoint of
+// the i-th 1/128 interval.  tab[i] = {1 / c_i rounded to float (so the FMA below is exact in m), -log(that)}; the
+// series stops at r^7 (|r| <= 2^-8: next term < 1e-20).  Absolute error ~ 2e-16 max(1, |e|); ~20 instructions
+// instead of the ~100 of log().  Denormals / non-finite values take the library path.
+__device__ __forceinline__ void log_tab_fill(double2* tab, int i) {      // i in 0..127; one entry per thread
+    const double c = 1.0 + ((double)i + 0.5) * (1.0 / 128.0);
+    const double ic = (double)(float)(1.0 / c);
+    tab[i] = make_double2(ic, -log(ic));
+}
+__device__ __forceinline__ double log_pos(double x, const double2* __restrict__ tab) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x);
+    const double2 t = tab[(hi >> 13) & 127];
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double r = fma(m, t.x, -1.0);
+    double q = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    q = fma(r, q, 0.2);
+    q = fma(r, q, -0.25);
+    q = fma(r, q, 1.0 / 3.0);
+    q = fma(r, q, -0.5);
+    const double p = fma(r * r, q, r);
+    return fma((double)((hi >> 20) - 1023), 0.6931471805599453094, t.y) + p;
+}
 
 // ---------------------------------------------------------------- alias-table draw (Poissonised samplers)
 // Cell `off + j` of the pool keeps j with probability prob / 2^32 and otherwise yields its alias; cells store

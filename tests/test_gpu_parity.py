@@ -360,6 +360,51 @@ def test_samplers_agree_exact_moments(gpu_prepared):
     assert np.abs(ratio - 1).max() < 0.06, np.abs(ratio - 1).max()
 
 
+def test_poisson_sampler_slots_and_log_rows(gpu_prepared, monkeypatch):
+    """The Poissonised kernel runs several replicates per lane in lockstep (MM_BOOT_SLOTS); a replicate's random
+    numbers depend on (seed, replicate, segment, attempt) only, so every slot count must give bit-identical rows.
+    The log rows it writes directly (table-driven log, log rv = log var - trend) must agree with the logs of the
+    raw rows to round-off, with the invalid-replicate counters matching the NaN pattern."""
+    mem = gpu_prepared.uns["memento"]
+    dstate = mem["_b200"]
+    seg = dstate.seg
+    G, R = seg.G, seg.R
+    B = 3000            # not a multiple of the block's replicate range
+    n_seg = G * R
+    tab = engine.unique_tables(seg, dstate.design, dstate.cell_bin, 0, G, 0)
+    raw = {}
+    for slots in ("1", "2", "3", "4"):
+        monkeypatch.setenv("MM_BOOT_SLOTS", slots)
+        m, v, _ = engine.bootstrap_tile(seg, dstate.design, tab, G, 0, B, 4321)
+        torch.cuda.synchronize()
+        raw[slots] = (m.cpu().numpy().reshape(n_seg, B), v.cpu().numpy().reshape(n_seg, B))
+    for slots in ("2", "3", "4"):
+        np.testing.assert_array_equal(raw["1"][0], raw[slots][0])
+        np.testing.assert_array_equal(raw["1"][1], raw[slots][1])
+    logs = {}
+    for slots in ("1", "2"):
+        monkeypatch.setenv("MM_BOOT_SLOTS", slots)
+        bm = torch.full((n_seg * (B + 1),), -7.0, dtype=torch.float64, device=seg.device)
+        bv = torch.full((n_seg * (B + 1),), -7.0, dtype=torch.float64, device=seg.device)
+        ninv = torch.zeros(2 * n_seg, dtype=torch.int32, device=seg.device)
+        engine.bootstrap_tile(seg, dstate.design, tab, G, 0, B, 4321, log_rows=(bm, bv, ninv))
+        torch.cuda.synchronize()
+        logs[slots] = (bm.cpu().numpy().reshape(n_seg, B + 1), bv.cpu().numpy().reshape(n_seg, B + 1),
+                       ninv.cpu().numpy().reshape(n_seg, 2))
+    for k in range(3):
+        np.testing.assert_array_equal(logs["1"][k], logs["2"][k])
+    lm, lv, ninv = logs["2"]
+    rm, rv = raw["2"]
+    assert (lm[:, 0] == -7.0).all() and (lv[:, 0] == -7.0).all()          # column 0 belongs to the caller
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want_m = np.where(rm > 0, np.log(rm), np.nan)
+        want_v = np.where(rv > 0, np.log(rv), np.nan)
+    assert_close(lm[:, 1:], want_m, 0, 1e-13, "log mean rows")
+    assert_close(lv[:, 1:], want_v, 1e-9, 1e-9, "log residual variance rows")   # var = M2/n - mean^2 cancels
+    np.testing.assert_array_equal(ninv[:, 0], np.isnan(lm[:, 1:]).sum(axis=1))
+    np.testing.assert_array_equal(ninv[:, 1], np.isnan(lv[:, 1:]).sum(axis=1))
+
+
 def test_rng_ht_1d_vs_oracle_pvalues(gpu_prepared, oracle_prepared):
     """RNG-driven p-values: rank concordance with the oracle across genes and KS agreement of the
     p-value distribution on the null genes (north star: 'within Monte Carlo error')."""
