@@ -116,7 +116,8 @@ int mm_seg_unique(int device, void* stream, const float* vals, const int32_t* ro
 
 /* Fused bootstrap of segments [seg_lo, seg_lo + n_seg) (n_seg <= 65535 per call): for every
  * replicate b < num_boot draw multinomial resample counts over the segment's categories
- * (Philox4x32-10, counter = (b, segment), key = seed), accumulate the moments and write
+ * (Philox4x32, counter = (b, segment, block), key = seed; 7 rounds in the Poissonised sampler, 10 in the chain),
+ * accumulate the moments and write
  *   out_mean[s*num_boot + b] = bootstrapped mean,  out_rv[...] = residual variance
  * (NaN where mean <= 0 or variance <= 0).  mv_fit[R][3] = quadratic log-log trend per group,
  * highest power first.  seg_skip (nullable): segments not to compute.  gene_id (nullable,
@@ -125,6 +126,8 @@ int mm_seg_unique(int device, void* stream, const float* vals, const int32_t* ro
  * log_rows != 0: out_mean / out_rv are the [n_seg][num_boot + 1] rows the regression reads; replicate b goes to
  * column b + 1 as log(value), or NaN where the value is <= 0 or NaN, and n_invalid[2 s + {0, 1}] (zero-initialised
  * by the caller) counts those NaNs, so that mm_fill_log (in-place mode) only has to visit the segments that have any.
+ * seg_order (nullable, [n_seg]): the segment block row y of the Poissonised kernel works on -- pass the segments by
+ * decreasing table length so that the longest blocks are dispatched first; results do not depend on it.
  * Replaces: memento/bootstrap.py:74-116 (_bootstrap_1d), estimator.py:171-174 (tuple form),
  * hypothesis_test.py:186 -> estimator.py:103-111 (_residual_variance per replicate). */
 int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t* seg_ptr,
@@ -132,7 +135,8 @@ int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t
                     const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                     int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
                     const void* seg_info, const void* tab_pool, const uint32_t* acc_pool,
-                    double* out_mean, double* out_rv, int32_t log_rows, int32_t* n_invalid);
+                    double* out_mean, double* out_rv, int32_t log_rows, int32_t* n_invalid,
+                    const int32_t* seg_order);
 
 /* Poissonised sampler support (see csrc/bootstrap.cu header).  seg_info == NULL in mm_bootstrap_1d
  * selects the conditional-binomial chain for every segment.
@@ -250,6 +254,8 @@ int mm_gev_tail_asl(int device, void* stream, const double* coef_rows, const int
  *                      variances -> 1).  item_good[item] = 0 for skipped items (NaN row).  <= 65535 items
  *                      per call.  Replaces memento/bootstrap.py:119-157, estimator.py:214-218, :281-290,
  *                      hypothesis_test.py:322-351.
+ *                      item_order (nullable, [n_items]): the item block row y works on (longest tables first);
+ *                      results do not depend on it.
  *   mm_pair_bootstrap_replay : covariance, both variances and the correlation from HOST-SUPPLIED
  *                      resample counts (tables in the reference's order; W as in mm_bootstrap_1d_replay). */
 int mm_pair_unique(int device, void* stream, const float* vals, const int32_t* rows,
@@ -266,7 +272,7 @@ int mm_pair_bootstrap(int device, void* stream, const void* entries, const int64
                       int64_t n_items, int32_t R, const void* info, const int32_t* group_ncells,
                       const double* true_corr, const void* tab_pool, const uint32_t* acc_pool,
                       int32_t num_boot, uint64_t seed, const int64_t* item_id, double* boot_corr,
-                      uint8_t* item_good);
+                      uint8_t* item_good, const int32_t* item_order);
 int mm_pair_bootstrap_replay(int device, void* stream, const double* x, const double* y,
                              const double* inv_sf, const int64_t* W, const int64_t* tab_ptr,
                              const int32_t* n_cells, const double* q, int32_t n_tab, int32_t num_boot,

@@ -302,6 +302,7 @@ struct BootParams {
     double* out_rv;
     int log_rows;               // 1: write log(mean), log(res. var.) into the [B + 1] rows, NaN + counter where <= 0
     int* n_invalid;             // [n_seg][2] replicates with a non-positive mean / residual variance (log_rows)
+    const int* seg_order;       // [n_seg] nullable: segment handled by block row y (Poissonised kernel; longest first)
 };
 
 // one replicate's result: raw values, or (log_rows) their logs in the rows the regression reads -- the imputation
@@ -400,7 +401,9 @@ __global__ void __launch_bounds__(kBootThreads, kVariant ? (kSlots == 1 ? 8 : kS
 bootstrap_1d_poisson_kernel(BootParams P) {
     constexpr bool kFast = kVariant > 0;
     constexpr int kR = kFast ? 7 : 10;
-    const long long seg_rel = blockIdx.y;
+    // block rows are dispatched in order: with seg_order = segments by decreasing table length the long blocks (a
+    // dense gene's block runs 10 x the average) start first instead of leaving a tail of a few busy SMs
+    const long long seg_rel = P.seg_order ? P.seg_order[blockIdx.y] : blockIdx.y;
     if (P.seg_skip && P.seg_skip[seg_rel]) return;
     const SegInfo si = P.info[seg_rel];
     if (si.mode != 1) return;
@@ -628,7 +631,8 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
                               const uint8_t* seg_skip, const int32_t* group_ncells, const double* mv_fit,
                               int32_t estimator, int32_t num_boot, uint64_t seed, const int64_t* gene_id,
                               const void* seg_info, const void* tab_pool, const uint32_t* acc_pool,
-                              double* out_mean, double* out_rv, int32_t log_rows, int32_t* n_invalid) {
+                              double* out_mean, double* out_rv, int32_t log_rows, int32_t* n_invalid,
+                              const int32_t* seg_order) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_seg >= 0 && R > 0 && num_boot > 0, "n_seg/R/num_boot");
     MM_REQUIRE(n_seg <= 65535, "at most 65535 segments per launch (tile the genes)");
@@ -640,15 +644,21 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     P.n_seg = n_seg; P.R = R; P.seg_U = seg_U; P.seg_skip = seg_skip; P.group_ncells = group_ncells;
     P.mv_fit = mv_fit; P.estimator = estimator; P.B = num_boot; P.seed = seed;
     P.gene_id = (const long long*)gene_id; P.out_mean = out_mean; P.out_rv = out_rv;
-    P.log_rows = log_rows; P.n_invalid = n_invalid;
+    P.log_rows = log_rows; P.n_invalid = n_invalid; P.seg_order = seg_order;
     MM_REQUIRE(!log_rows || n_invalid, "log_rows needs the n_invalid counters (zero-initialised)");
     P.info = (const SegInfo*)seg_info; P.tab_pool = (const uint2*)tab_pool; P.acc_pool = acc_pool;
-    // a block covers 20 replicates per lane and slot of one segment; lanes claim replicates from a shared counter,
-    // so rejections do not leave lanes idle at the end of the range
     const int variant = getenv("MM_BOOT_VARIANT") ? atoi(getenv("MM_BOOT_VARIANT")) : 1;     // A/B hooks
     const int slots = getenv("MM_BOOT_SLOTS") ? atoi(getenv("MM_BOOT_SLOTS")) : 2;
     const int n_slots = (variant == 0 || slots <= 1) ? 1 : (slots >= 4 ? 4 : slots);
-    P.reps_per_block = kBootThreads * 20 * n_slots;
+    // replicates per block: lanes claim replicates from the block's counter, so only the block's last pass has idle
+    // lanes -- one block per segment when there are enough segments to fill the GPU (C2: 40 passes 165 ms, 20 passes
+    // 173 ms, 10 passes 189 ms), more blocks per segment otherwise
+    const long long want_blocks = (148 * 6 * 2 + n_seg - 1) / n_seg;
+    int passes = (int)((num_boot + (long long)kBootThreads * n_slots * want_blocks - 1) / ((long long)kBootThreads * n_slots * want_blocks));
+    if (passes > 40) passes = 40;
+    if (getenv("MM_BOOT_PASSES")) passes = atoi(getenv("MM_BOOT_PASSES"));      // A/B hook
+    if (passes < 1) passes = 1;
+    P.reps_per_block = kBootThreads * passes * n_slots;
     MM_REQUIRE(!seg_info || (tab_pool && acc_pool), "seg_info needs tab_pool and acc_pool");
     dim3 grid((num_boot + kBootThreads - 1) / kBootThreads, (unsigned)n_seg);
     bootstrap_1d_kernel<<<grid, kBootThreads, 0, (cudaStream_t)stream>>>(P);

@@ -10,6 +10,7 @@
 // two ascending row lists; their union is enumerated by binary-searching each list in the other.
 // Cells where both counts are zero are the implicit remainder-like category with all coefficients 0.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mm {
 
@@ -314,11 +315,17 @@ struct PairBootParams {
     int reps_per_block;
     double* boot_corr;          // [n_items][B + 1]
     unsigned char* item_good;   // [n_items]
+    const int* item_order;      // [n_items] nullable: item handled by block row y (longest tables first)
 };
 
+// kSlots replicates per lane run in lockstep over the same categories (see bootstrap_1d_poisson_kernel): the
+// warp-uniform 64-byte category record is loaded once per kSlots draws.  Philox4x32-7; the random numbers of a
+// replicate depend on (seed, replicate, item, attempt) only, so every kSlots gives bit-identical rows.
+template <int kSlots>
 __global__ void __launch_bounds__(kPairThreads)
 pair_bootstrap_kernel(PairBootParams P) {
-    const long long item = blockIdx.y;
+    constexpr int kR = 7;
+    const long long item = P.item_order ? P.item_order[blockIdx.y] : blockIdx.y;
     const PairInfo pi = P.info[item];
     const int B1 = P.B + 1;
     double* out = P.boot_corr + item * (long long)B1;
@@ -343,45 +350,104 @@ pair_bootstrap_kernel(PairBootParams P) {
     const uint32_t* acc = P.acc_pool + pi.acc_off;
     const long long sid = P.item_id ? P.item_id[item] : item;
     __shared__ int s_next;
-    if (threadIdx.x == 0) s_next = b_lo + kPairThreads;
+    if (threadIdx.x == 0) s_next = b_lo + kSlots * kPairThreads;
     __syncthreads();
-    int b = b_lo + threadIdx.x;
-    Philox rng;
-    bool fresh = true;
-    while (b < b_end) {
-        if (fresh) { rng.init(P.seed, (uint32_t)b, (uint32_t)sid, 0u, (uint32_t)(sid >> 32) ^ 0x2D2Du); fresh = false; }
-        int S = 0;
-        double acc5[5] = {0, 0, 0, 0, 0};
-        auto draw = [&](int u, uint32_t rnd) {
-            const PairEntry e = tab[u];
-            const int k = alias_draw(P.tab_pool, (unsigned)e.off, (unsigned)(e.kl & 0xFFFF), (e.kl >> 16) - e.off, rnd);
-            S += k;
-            const double kd = (double)k;
-            acc5[0] = fma(e.c1, kd, acc5[0]); acc5[1] = fma(e.c2, kd, acc5[1]); acc5[2] = fma(e.cx, kd, acc5[2]);
-            acc5[3] = fma(e.v1, kd, acc5[3]); acc5[4] = fma(e.v2, kd, acc5[4]);
-        };
-        int u = 0;
-        for (; u + 4 <= pi.U; u += 4) {
-            const uint4 r4 = rng.block();
-            draw(u, r4.x); draw(u + 1, r4.y); draw(u + 2, r4.z); draw(u + 3, r4.w);
+    const uint32_t key0 = (uint32_t)P.seed, key1 = (uint32_t)(P.seed >> 32);
+    const uint32_t c1 = (uint32_t)sid, c3 = (uint32_t)(sid >> 32) ^ 0x2D2Du;
+    int b[kSlots];
+    uint32_t blk[kSlots];
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j) { b[j] = b_lo + j * kPairThreads + threadIdx.x; blk[j] = 0; }
+    auto live = [&]() {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) any |= b[j] < b_end;
+        return any;
+    };
+    while (live()) {
+        int S[kSlots];
+        double acc5[kSlots][5];
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+            S[j] = 0;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) acc5[j][c] = 0.0;
         }
-        uint4 r4 = rng.block();
-        if (u < pi.U) draw(u, r4.x);
-        if (u + 1 < pi.U) draw(u + 1, r4.y);
-        if (u + 2 < pi.U) draw(u + 2, r4.z);
-        if (pi.zero_off >= 0)
-            S += alias_draw(P.tab_pool, (unsigned)pi.zero_off, (unsigned)(pi.zero_kl & 0xFFFF),
-                            (pi.zero_kl >> 16) - pi.zero_off, r4.w);
-        r4 = rng.block();
-        const int i = S - pi.s_lo;
-        bool ok = (i >= 0) && (i < pi.acc_len);
-        if (ok) ok = r4.x < __ldg(acc + i);
-        if (ok) {
-            const double w = (double)(N - S);
-            for (int c = 0; c < 5; ++c) acc5[c] = fma(pi.rem[c], w, acc5[c]);
-            out[b + 1] = corr_replicate(acc5, (double)N);
-            b = atomicAdd(&s_next, 1);
-            fresh = true;
+        auto fresh4 = [&](int j) {
+            return Philox::rounds<kR>(make_uint4((uint32_t)b[j], c1, blk[j]++, c3), key0, key1);
+        };
+        auto draw = [&](int j, const PairEntry& e, uint32_t rnd) {
+            const int k = alias_draw(P.tab_pool, (unsigned)e.off, (unsigned)(e.kl & 0xFFFF), (e.kl >> 16) - e.off, rnd);
+            S[j] += k;
+            const double kd = (double)k;
+            acc5[j][0] = fma(e.c1, kd, acc5[j][0]); acc5[j][1] = fma(e.c2, kd, acc5[j][1]);
+            acc5[j][2] = fma(e.cx, kd, acc5[j][2]); acc5[j][3] = fma(e.v1, kd, acc5[j][3]);
+            acc5[j][4] = fma(e.v2, kd, acc5[j][4]);
+        };
+        uint4 r4[kSlots];
+        int u = 0;
+        for (; u + 4 <= pi.U; u += 4) {     // four categories per Philox block and slot; one record live at a time
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) r4[j] = fresh4(j);
+            {
+                const PairEntry e = tab[u];
+#pragma unroll
+                for (int j = 0; j < kSlots; ++j) draw(j, e, r4[j].x);
+            }
+            {
+                const PairEntry e = tab[u + 1];
+#pragma unroll
+                for (int j = 0; j < kSlots; ++j) draw(j, e, r4[j].y);
+            }
+            {
+                const PairEntry e = tab[u + 2];
+#pragma unroll
+                for (int j = 0; j < kSlots; ++j) draw(j, e, r4[j].z);
+            }
+            {
+                const PairEntry e = tab[u + 3];
+#pragma unroll
+                for (int j = 0; j < kSlots; ++j) draw(j, e, r4[j].w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) r4[j] = fresh4(j);
+        if (u < pi.U) {
+            const PairEntry e = tab[u];
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) draw(j, e, r4[j].x);
+        }
+        if (u + 1 < pi.U) {
+            const PairEntry e = tab[u + 1];
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) draw(j, e, r4[j].y);
+        }
+        if (u + 2 < pi.U) {
+            const PairEntry e = tab[u + 2];
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j) draw(j, e, r4[j].z);
+        }
+        if (pi.zero_off >= 0) {
+#pragma unroll
+            for (int j = 0; j < kSlots; ++j)
+                S[j] += alias_draw(P.tab_pool, (unsigned)pi.zero_off, (unsigned)(pi.zero_kl & 0xFFFF),
+                                   (pi.zero_kl >> 16) - pi.zero_off, r4[j].w);
+        }
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+            const uint4 ra = fresh4(j);
+            const int i = S[j] - pi.s_lo;
+            bool ok = (i >= 0) && (i < pi.acc_len) && (b[j] < b_end);
+            if (ok) ok = ra.x < __ldg(acc + i);
+            if (ok) {
+                const double w = (double)(N - S[j]);
+                double fin[5];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) fin[c] = fma(pi.rem[c], w, acc5[j][c]);
+                out[b[j] + 1] = corr_replicate(fin, (double)N);
+                b[j] = atomicAdd(&s_next, 1);
+                blk[j] = 0;
+            }
         }
     }
 }
@@ -470,7 +536,7 @@ MM_EXPORT int mm_pair_bootstrap(int device, void* stream, const void* entries, c
                                 int64_t n_items, int32_t R, const void* info, const int32_t* group_ncells,
                                 const double* true_corr, const void* tab_pool, const uint32_t* acc_pool,
                                 int32_t num_boot, uint64_t seed, const int64_t* item_id, double* boot_corr,
-                                uint8_t* item_good) {
+                                uint8_t* item_good, const int32_t* item_order) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_items >= 0 && R > 0 && num_boot > 0, "n_items/R/num_boot");
     MM_REQUIRE(n_items <= 65535, "at most 65535 (pair, group) items per launch");
@@ -481,10 +547,19 @@ MM_EXPORT int mm_pair_bootstrap(int device, void* stream, const void* entries, c
     P.entries = (const PairEntry*)entries; P.item_ptr = (const long long*)item_ptr; P.n_items = n_items; P.R = R;
     P.info = (const PairInfo*)info; P.group_ncells = group_ncells; P.true_corr = true_corr;
     P.tab_pool = (const uint2*)tab_pool; P.acc_pool = acc_pool; P.B = num_boot; P.seed = seed;
-    P.item_id = (const long long*)item_id; P.reps_per_block = kPairThreads * 20;
-    P.boot_corr = boot_corr; P.item_good = item_good;
+    const int slots = getenv("MM_PAIR_SLOTS") ? atoi(getenv("MM_PAIR_SLOTS")) : 2;      // A/B hook
+    const int n_slots = slots <= 1 ? 1 : (slots >= 3 ? 3 : 2);
+    const long long want_blocks = (148 * 4 * 2 + n_items - 1) / n_items;     // see mm_bootstrap_1d
+    int passes = (int)((num_boot + (long long)kPairThreads * n_slots * want_blocks - 1) / ((long long)kPairThreads * n_slots * want_blocks));
+    if (passes > 40) passes = 40;
+    if (getenv("MM_BOOT_PASSES")) passes = atoi(getenv("MM_BOOT_PASSES"));      // A/B hook
+    if (passes < 1) passes = 1;
+    P.item_id = (const long long*)item_id; P.reps_per_block = kPairThreads * passes * n_slots;
+    P.boot_corr = boot_corr; P.item_good = item_good; P.item_order = item_order;
     dim3 grid((num_boot + P.reps_per_block - 1) / P.reps_per_block, (unsigned)n_items);
-    pair_bootstrap_kernel<<<grid, kPairThreads, 0, (cudaStream_t)stream>>>(P);
+    if (n_slots == 1) pair_bootstrap_kernel<1><<<grid, kPairThreads, 0, (cudaStream_t)stream>>>(P);
+    else if (n_slots == 3) pair_bootstrap_kernel<3><<<grid, kPairThreads, 0, (cudaStream_t)stream>>>(P);
+    else pair_bootstrap_kernel<2><<<grid, kPairThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_pair_bootstrap");
 }
 

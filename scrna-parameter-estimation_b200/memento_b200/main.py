@@ -8,6 +8,8 @@ per-(gene, group) moments, compression, bootstrap, regression, ASL) runs in the 
 ``np.quantile`` / ``np.polyfit`` / ``binned_statistic`` semantics are part of the contract.
 There is no CPU fallback: without a CUDA device or the built library every call raises.
 """
+import os
+
 import numpy as np
 import pandas as pd
 import scipy.sparse as sp
@@ -365,13 +367,14 @@ def _refresh_design(adata):
 
 # --------------------------------------------------------------------------- ht_1d_moments
 def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=True, num_boot=10000,
-                  verbose=1, num_cpus=1, seed=0, workspace_bytes=6 << 30, replay=None, sampler="poisson",
+                  verbose=1, num_cpus=1, seed=0, workspace_bytes=None, replay=None, sampler="poisson",
                   **kwargs):
     """Hypothesis test for the mean and the residual variance.  reference: main.py:341-415.
 
     ``num_cpus`` / ``verbose`` are accepted and ignored (the GPU grid replaces the process pool).
     Test keywords as in the reference: ``resampling='bootstrap'`` (only mode on the device path),
-    ``approx``, ``resample_rep``.  Build-only: ``seed`` (Philox key), ``workspace_bytes``,
+    ``approx``, ``resample_rep``.  Build-only: ``seed`` (Philox key), ``workspace_bytes`` (bootstrap rows of one
+    gene tile; two tiles are alive at a time; default: 24 GB or a sixth of the free device memory, whichever is less),
     ``replay`` (deterministic parity mode: host-supplied unique tables, resample counts and
     imputation sources for every (gene, group); see engine.ht_1d_replay), ``sampler`` ("poisson":
     Poissonised exact multinomial with the conditional-binomial chain as per-segment fallback;
@@ -400,7 +403,15 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     true_mean = np.stack([mem["1d_moments"][g][0] for g in groups], axis=1)   # (G, R)
     true_rv = np.stack([mem["1d_moments"][g][2] for g in groups], axis=1)
 
+    if workspace_bytes is None:
+        # few, large tiles: every tile ends with the tail of its longest bootstrap blocks and the last tile's GEV
+        # stage has nothing to hide under (C2: 24 GB = 2 tiles 194 ms, 6 GB = 7 tiles 200 ms per step)
+        workspace_bytes = min(24 << 30, torch.cuda.mem_get_info(st.device)[0] // 6)
     genes_per_tile = engine.tile_plan(st.seg, num_boot, workspace_bytes)
+    if os.environ.get("MM_WORKSPACE_GB"):           # tuning hook
+        genes_per_tile = engine.tile_plan(st.seg, num_boot, int(float(os.environ["MM_WORKSPACE_GB"]) * (1 << 30)))
+    if G > genes_per_tile and os.environ.get("MM_TILE_BALANCE", "0") != "0":      # equal tiles instead of full ones + a sliver
+        genes_per_tile = -(-G // -(-G // genes_per_tile))
     out = {k: np.full((G, 2, T), np.nan) for k in ("coef", "se", "asl")}
     stats_acc = {"want_modes": bool(getattr(st, "count_modes", False))}
     if sampler not in ("poisson", "chain"):
