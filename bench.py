@@ -73,7 +73,7 @@ def ncu_traffic(nnz):
 
 def engine_tile_genes(seg, num_boot):
     from memento_b200 import engine
-    return engine.tile_plan(seg, num_boot)
+    return engine.tile_plan(seg, num_boot, engine.default_workspace(seg.device))
 
 
 def parse():
@@ -363,7 +363,7 @@ def run_ours(a):
                    "l2": "inputs larger than L2: group-sorted matrix %.0f MB streamed per step, plus ~%.1f GB of "
                          "bootstrap rows written and re-read per gene tile"
                          % (seg.nnz * 8 / 1e6 if seg is not None else 0,
-                            min(G, engine_tile_genes(seg, a.num_boot)) * seg.R * (a.num_boot + 1) * 32 / 1e9)}),
+                            min(G, engine_tile_genes(seg, a.num_boot)) * seg.R * (a.num_boot + 1) * 16 / 1e9)}),
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clk}
         out.update(extra)

@@ -60,6 +60,13 @@ class GroupDesign:
         self.acc_slot = torch.as_tensor(np.concatenate([[0], np.cumsum(slot)[:-1]]).astype(np.int64), device=device)
 
 
+def default_workspace(device):
+    """Bootstrap-row budget of one gene tile (two tiles are alive at a time): 24 GB or a sixth of the free device
+    memory.  Few, large tiles: every tile ends with the tail of its longest bootstrap blocks and the last tile's GEV
+    stage has nothing to hide under (C2: 24 GB = 2 tiles 194 ms, 6 GB = 7 tiles 200 ms per step)."""
+    return min(24 << 30, torch.cuda.mem_get_info(device)[0] // 6)
+
+
 def tile_plan(seg, num_boot, workspace_bytes=6 << 30):
     """Genes per tile: bounded by the bootstrap grid (65535 segments) and by the workspace
     (32 bytes per (segment, replicate): raw mean/rv + log mean/var)."""

@@ -404,9 +404,7 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     true_rv = np.stack([mem["1d_moments"][g][2] for g in groups], axis=1)
 
     if workspace_bytes is None:
-        # few, large tiles: every tile ends with the tail of its longest bootstrap blocks and the last tile's GEV
-        # stage has nothing to hide under (C2: 24 GB = 2 tiles 194 ms, 6 GB = 7 tiles 200 ms per step)
-        workspace_bytes = min(24 << 30, torch.cuda.mem_get_info(st.device)[0] // 6)
+        workspace_bytes = engine.default_workspace(st.device)
     genes_per_tile = engine.tile_plan(st.seg, num_boot, workspace_bytes)
     if os.environ.get("MM_WORKSPACE_GB"):           # tuning hook
         genes_per_tile = engine.tile_plan(st.seg, num_boot, int(float(os.environ["MM_WORKSPACE_GB"]) * (1 << 30)))
