@@ -148,9 +148,12 @@ int mm_bootstrap_1d(int device, void* stream, const void* entries, const int64_t
  *   mm_boot_prepare       : per segment, picks the remainder category and the sampler, rewrites the
  *                           entries for Poisson-mode segments and builds the acceptance table
  *                           g(s)/max g at acc_pool[(gene - gene_lo) * acc_stride + acc_slot[group]];
- *                           seg_info = n_seg records of 48 bytes; segments whose expected acceptance
- *                           rate is below min_accept, or with a multiplicity above n_table_max, keep
- *                           the chain. */
+ *                           seg_info = n_seg records of 48 bytes followed by 4 + 2 n_seg int32 (work
+ *                           lists of the chain and the direct kernel: 48 n_seg + 16 + 8 n_seg bytes in all);
+ *                           segments whose expected acceptance rate is below min_accept, or with a
+ *                           multiplicity above n_table_max, are resampled cell by cell from a shared-memory
+ *                           table when their nonzero cells fit it (<= 3072) and the table is at least a
+ *                           sixth of the group, and keep the conditional-binomial chain otherwise. */
 int mm_poisson_table_size(int32_t n_max, int32_t* offsets, int64_t* total);
 int mm_poisson_tables(int device, void* stream, int32_t n_max, const int32_t* offsets_dev, void* pool,
                       double* scratch_p, int32_t* scratch_a, int32_t* scratch_b);

@@ -20,5 +20,5 @@ for ma in (0.2, 0.1, 0.05, 0.02, 0.3, 0.2):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     ms = st.timer.collect()
     print("min_accept", ma, "step %.1f ms" % (dt * 1e3), "bootstrap %.1f ms" % ms.get("bootstrap_1d", 0),
-          "poisson segs", st.last_stats.get("poisson_segments"), "chain segs", st.last_stats.get("chain_segments"))
+          "poisson segs", st.last_stats.get("poisson_segments"), "chain segs", st.last_stats.get("chain_segments"), "direct segs", st.last_stats.get("direct_segments"))
     st.timer.ms.clear()

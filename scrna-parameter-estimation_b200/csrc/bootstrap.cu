@@ -39,6 +39,7 @@ struct __align__(32) BootEntry {   // must match unique.cu
 };
 
 constexpr int kBootThreads = 128;
+constexpr int kDirectMaxCells = 3072;   // nonzero cells of a segment the direct kernel can stage (16 B each, 48 KB)
 
 __device__ __forceinline__ float stirling_tail(float k) {
     // log(k!) - [(k + 1/2) log(k + 1) - (k + 1) + 1/2 log(2 pi)]
@@ -157,9 +158,9 @@ __global__ void poisson_tables_kernel(int n_max, const int* __restrict__ off, ui
     poisson_alias_fill((double)n, klo, len, pool + off[n], sp + off[n], ss + off[n], sl + off[n]);
 }
 
-struct __align__(16) SegInfo {     // written by boot_prepare_kernel, one per segment of the tile
-    int mode;        // 0: conditional-binomial chain, 1: Poissonised sampler, -1: all-NaN row
-    int s_lo;        // acceptance table covers S in [s_lo, s_lo + acc_len)
+struct __align__(16) SegInfo {     // written by boot_prepare_kernel, one per segment of the tile (48 bytes)
+    int mode;        // 0: conditional-binomial chain, 1: Poissonised sampler, 2: direct cell resampling, -1: all-NaN row
+    int s_lo;        // acceptance table covers S in [s_lo, s_lo + acc_len); mode 2: number of nonzero cells
     int acc_len;
     int zero_off;    // table of the zero-count category when it is not the remainder (else -1)
     int zero_kl;     // klo << 16 | len of that table
@@ -167,6 +168,22 @@ struct __align__(16) SegInfo {     // written by boot_prepare_kernel, one per se
     long long acc_off;
     double rem_a, rem_b;
 };
+
+// Sampler work lists, stored right behind the n_seg SegInfo records of the seg_info buffer: counters {chain, direct,
+// -, -}, then the chain list (modes 0 and -1) and the direct list, n_seg entries each.  The chain and direct kernels
+// run over these lists with small grids: an empty block costs ~1 ns of the block scheduler, and one block row per
+// segment of the tile was 5.2 M of them per launch (4 ms) for ten chain segments.
+struct SegLists {
+    int* count;
+    int* chain;
+    int* direct;
+};
+__host__ __device__ inline SegLists seg_lists(const void* seg_info, long long n_seg) {
+    int* base = reinterpret_cast<int*>(const_cast<char*>(static_cast<const char*>(seg_info)) + n_seg * 48);
+    return SegLists{base, base + 4, base + 4 + n_seg};
+}
+
+static_assert(sizeof(SegInfo) == 48, "SegInfo layout (seg_lists, engine.py SEG_INFO_BYTES)");
 
 struct PrepParams {
     BootEntry* entries;
@@ -181,7 +198,8 @@ struct PrepParams {
     long long acc_stride;        // acceptance-table entries per gene
     uint32_t* acc_pool;          // [n_genes_tile * acc_stride]
     SegInfo* info;               // [n_seg]
-    float min_accept;            // fall back to the chain below this expected acceptance rate
+    float min_accept;            // fall back to the chain / direct resampling below this expected acceptance rate
+    int allow_direct;            // 0: chain only
 };
 
 // One warp per segment: choose the remainder category, decide the sampler, rewrite the entries'
@@ -198,7 +216,14 @@ boot_prepare_kernel(PrepParams P) {
     SegInfo si;
     si.mode = 0; si.s_lo = 0; si.acc_len = 0; si.zero_off = -1; si.zero_kl = 0; si.rem_index = -1;
     si.acc_off = 0; si.rem_a = 0.0; si.rem_b = 0.0;
-    if (U < 0) { si.mode = -1; if (lane == 0) P.info[seg_rel] = si; return; }
+    const SegLists lists = seg_lists(P.info, P.n_seg);
+    auto publish = [&]() {
+        if (lane != 0) return;
+        P.info[seg_rel] = si;
+        if (si.mode <= 0) lists.chain[atomicAdd(lists.count, 1)] = (int)seg_rel;
+        else if (si.mode == 2) lists.direct[atomicAdd(lists.count + 1, 1)] = (int)seg_rel;
+    };
+    if (U < 0) { si.mode = -1; publish(); return; }
     BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
     const int N = P.group_ncells[r];
     // largest category and total nonzero mass
@@ -226,7 +251,7 @@ boot_prepare_kernel(PrepParams P) {
     too_big = __any_sync(kFull, too_big);
     if (too_big || M <= 0 || rem_n <= 0) {
         // M == 0: a single category holds every cell (chain handles it trivially)
-        if (lane == 0) P.info[seg_rel] = si;
+        publish();
         return;
     }
     // acceptance table: log g(s) = lgamma(N+1) - lgamma(N-s+1) - s log N + (N-s) log(rem_n / N) + M
@@ -246,7 +271,10 @@ boot_prepare_kernel(PrepParams P) {
     for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(kFull, best, o));
     // expected acceptance = 1 / max g
     if (exp(-best) < (double)P.min_accept) {
-        if (lane == 0) P.info[seg_rel] = si;
+        // flat, dense gene: if its nonzero cells fit the direct kernel's shared-memory table and the table is not
+        // much shorter than the group (chain ~ 90 U instructions per replicate, direct ~ 14 N), resample cells
+        if (P.allow_direct && mass <= kDirectMaxCells && (long long)N <= 6LL * U) { si.mode = 2; si.s_lo = (int)mass; }
+        publish();
         return;
     }
     for (int i = lane; i < len; i += 32) {
@@ -277,7 +305,7 @@ boot_prepare_kernel(PrepParams P) {
         }
     }
     si.mode = 1; si.s_lo = s_lo; si.acc_len = len; si.rem_index = rem_i; si.acc_off = acc_off;
-    if (lane == 0) P.info[seg_rel] = si;
+    publish();
 }
 
 struct BootParams {
@@ -335,17 +363,13 @@ __device__ __forceinline__ void finish_replicate(double M1, double M2, double n,
     }
 }
 
-__global__ void __launch_bounds__(kBootThreads)
-bootstrap_1d_kernel(BootParams P) {
-    const long long seg_rel = blockIdx.y;
-    const int b = blockIdx.x * kBootThreads + threadIdx.x;
-    if (b >= P.B) return;
+__device__ __forceinline__ void chain_segment(const BootParams& P, long long seg_rel, int b) {
     if (P.seg_skip && P.seg_skip[seg_rel]) return;
     const long long seg = P.seg_lo + seg_rel;
     const int r = (int)(seg % P.R);
     const int U = P.seg_U[seg_rel];
     if (U < 0) { store_replicate(P, seg_rel, b, nan(""), nan("")); return; }
-    if (P.info && P.info[seg_rel].mode == 1) return;      // handled by the Poissonised kernel
+    if (P.info && P.info[seg_rel].mode > 0) return;       // handled by the Poissonised / direct kernel
     const BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
     const int n_cells = P.group_ncells[r];
     // RNG stream id: global (gene, group) so that results do not depend on tiling or gene sharding
@@ -373,6 +397,47 @@ bootstrap_1d_kernel(BootParams P) {
     double mean, rv;
     finish_replicate(M1, M2, (double)n_cells, P.estimator, P.mv_fit + 3 * r, mean, rv);
     store_replicate(P, seg_rel, b, mean, rv);
+}
+
+// block row y: segment y (no sampler choice: chain everywhere), or the entries y, y + gridDim.y, ... of the chain list
+__global__ void __launch_bounds__(kBootThreads)
+bootstrap_1d_kernel(BootParams P) {
+    const int b = blockIdx.x * kBootThreads + threadIdx.x;
+    if (b >= P.B) return;
+    if (!P.info) { chain_segment(P, blockIdx.y, b); return; }
+    const SegLists lists = seg_lists(P.info, P.n_seg);
+    const int n_list = lists.count[0];
+    for (int i = blockIdx.y; i < n_list; i += gridDim.y) chain_segment(P, lists.chain[i], b);
+}
+
+// One finished replicate: kFast && log_rows writes log(mean) and log(residual variance) straight into the regression's
+// rows (table-driven log, no division, log rv = log var - trend(log mean)); otherwise the library-math path.
+template <bool kFast>
+__device__ __forceinline__ void emit_replicate(const BootParams& P, long long seg_rel, int b, double m1, double m2,
+                                               int N, double inv_n, const double* __restrict__ fit,
+                                               const double2* s_log) {
+    if (kFast && P.log_rows) {
+        double mean, var;
+        if (P.estimator == 0) { mean = m1 * inv_n; var = m2 * inv_n - mean * mean; }
+        else { mean = m1 * inv_n + 1.0; var = 10.0; }
+        const long long o = seg_rel * (long long)(P.B + 1) + 1 + b;
+        double lm = nan(""), lrv = nan("");
+        if (mean > 0.0) {
+            lm = log_pos(mean, s_log);
+            if (var > 0.0) lrv = log_pos(var, s_log) - ((fit[0] * lm + fit[1]) * lm + fit[2]);
+        } else {
+            atomicAdd(P.n_invalid + 2 * seg_rel, 1);
+        }
+        // (an infinite log rv -- residual variance overflow -- counts as valid, as exp() -> inf does in the
+        // reference; NaN covers var <= 0 and mean <= 0)
+        if (!(lrv == lrv)) atomicAdd(P.n_invalid + 2 * seg_rel + 1, 1);
+        P.out_mean[o] = lm;
+        P.out_rv[o] = lrv;
+    } else {
+        double mean, rv;
+        finish_replicate(m1, m2, (double)N, P.estimator, fit, mean, rv);
+        store_replicate(P, seg_rel, b, mean, rv);
+    }
 }
 
 // ---------------------------------------------------------------- Poissonised sampler
@@ -423,7 +488,6 @@ bootstrap_1d_poisson_kernel(BootParams P) {
     if (threadIdx.x == 0) s_next = blockIdx.x * P.reps_per_block + kSlots * kBootThreads;
     __syncthreads();
     const double inv_n = 1.0 / (double)N;
-    const double f0 = fit[0], f1 = fit[1], f2 = fit[2];
     // Philox counter = (replicate, segment lo, block number, segment hi ^ tag); the block number runs on over the
     // attempts of one replicate and restarts with a new replicate
     const uint32_t key0 = (uint32_t)P.seed, key1 = (uint32_t)(P.seed >> 32);
@@ -502,31 +566,83 @@ bootstrap_1d_poisson_kernel(BootParams P) {
             if (ok) {
                 const double w = (double)(N - S[j]);            // the remainder category takes the rest
                 const double m1 = fma(si.rem_a, w, M1[j]), m2 = fma(si.rem_b, w, M2[j]);
-                if (kFast && P.log_rows) {
-                    double mean, var;
-                    if (P.estimator == 0) { mean = m1 * inv_n; var = m2 * inv_n - mean * mean; }
-                    else { mean = m1 * inv_n + 1.0; var = 10.0; }
-                    const long long o = seg_rel * (long long)(P.B + 1) + 1 + b[j];
-                    double lm = nan(""), lrv = nan("");
-                    if (mean > 0.0) {
-                        lm = log_pos(mean, s_log);
-                        if (var > 0.0) lrv = log_pos(var, s_log) - ((f0 * lm + f1) * lm + f2);
-                    } else {
-                        atomicAdd(P.n_invalid + 2 * seg_rel, 1);
-                    }
-                    // (an infinite log rv -- residual variance overflow -- counts as valid, as exp() -> inf does in
-                    // the reference; NaN covers var <= 0 and mean <= 0)
-                    if (!(lrv == lrv)) atomicAdd(P.n_invalid + 2 * seg_rel + 1, 1);
-                    P.out_mean[o] = lm;
-                    P.out_rv[o] = lrv;
-                } else {
-                    double mean, rv;
-                    finish_replicate(m1, m2, (double)N, P.estimator, fit, mean, rv);
-                    store_replicate(P, seg_rel, b[j], mean, rv);
-                }
+                emit_replicate<kFast>(P, seg_rel, b[j], m1, m2, N, inv_n, fit, s_log);
                 b[j] = atomicAdd(&s_next, 1);                // results depend on (seed, replicate) only, not on the lane
                 blk[j] = 0;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- direct resampling of dense segments
+// Segments the Poissonised sampler rejects too often (flat, dense genes: the largest category holds < 4 % of the
+// cells) have almost as many categories as cells, so compression buys nothing: the conditional-binomial chain pays
+// ~90 instructions per category and replicate.  Here the block expands the table into one (a, b) pair per nonzero
+// cell in shared memory and a replicate is N uniform cell draws (one Philox word, one IMAD.HI, one 16-byte
+// shared-memory gather, two DADD each) -- the textbook bootstrap, exactly multinomial(N, n / N) by construction.
+constexpr int kDirectReps = kBootThreads * 10;      // replicates per block
+
+__global__ void __launch_bounds__(kBootThreads)
+bootstrap_1d_direct_kernel(BootParams P) {
+    extern __shared__ __align__(16) double2 s_cell[];        // [nonzero cells] (a, b)
+    __shared__ double2 s_log[128];
+    __shared__ int s_scan[kBootThreads + 1];
+    log_tab_fill(s_log, threadIdx.x);
+    const SegLists lists = seg_lists(P.info, P.n_seg);
+    const int n_list = lists.count[1];
+    const uint32_t key0 = (uint32_t)P.seed, key1 = (uint32_t)(P.seed >> 32);
+    for (int li = blockIdx.y; li < n_list; li += gridDim.y) {        // uniform over the block
+        const long long seg_rel = lists.direct[li];
+        if (P.seg_skip && P.seg_skip[seg_rel]) continue;
+        const SegInfo si = P.info[seg_rel];
+        const long long seg = P.seg_lo + seg_rel;
+        const int r = (int)(seg % P.R);
+        const int U = P.seg_U[seg_rel];
+        const BootEntry* tab = P.entries + (P.seg_ptr[seg] - P.seg_ptr[P.seg_lo]);
+        const int N = P.group_ncells[r];
+        const int M = si.s_lo;                                   // nonzero cells
+        const long long sid = P.gene_id ? P.gene_id[seg_rel / P.R] * P.R + r : seg;
+        const double* fit = P.mv_fit + 3 * r;
+        __syncthreads();                                         // the previous segment's table is no longer read
+        // expansion: thread t owns entries [t * per, (t + 1) * per); exclusive scan of their multiplicities
+        const int per = (U + kBootThreads - 1) / kBootThreads;
+        const int u_lo = min(U, (int)threadIdx.x * per), u_hi = min(U, u_lo + per);
+        int mine = 0;
+        for (int u = u_lo; u < u_hi; ++u) mine += tab[u].n;
+        s_scan[threadIdx.x + 1] = mine;
+        if (threadIdx.x == 0) s_scan[0] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) for (int t = 1; t <= kBootThreads; ++t) s_scan[t] += s_scan[t - 1];
+        __syncthreads();
+        int at = s_scan[threadIdx.x];
+        for (int u = u_lo; u < u_hi; ++u) {
+            const BootEntry e = tab[u];
+            for (int i = 0; i < e.n; ++i) s_cell[at + i] = make_double2(e.a, e.b);
+            at += e.n;
+        }
+        __syncthreads();
+        const double inv_n = 1.0 / (double)N;
+        const uint32_t c1 = (uint32_t)sid, c3 = (uint32_t)(sid >> 32) ^ 0xD1CEu;
+        const int b_end = min(P.B, (int)(blockIdx.x + 1) * kDirectReps);
+        for (int b = blockIdx.x * kDirectReps + threadIdx.x; b < b_end; b += kBootThreads) {
+            double M1 = 0.0, M2 = 0.0, M1b = 0.0, M2b = 0.0;     // two chains: the adds are dependent otherwise
+            auto draw = [&](uint32_t rnd, double& s1, double& s2) {
+                const unsigned idx = __umulhi(rnd, (unsigned)N);
+                if (idx < (unsigned)M) { const double2 ab = s_cell[idx]; s1 += ab.x; s2 += ab.y; }
+            };
+            uint32_t blk = 0;
+            int i = 0;
+            for (; i + 4 <= N; i += 4) {
+                const uint4 r4 = Philox::rounds<7>(make_uint4((uint32_t)b, c1, blk++, c3), key0, key1);
+                draw(r4.x, M1, M2); draw(r4.y, M1b, M2b); draw(r4.z, M1, M2); draw(r4.w, M1b, M2b);
+            }
+            if (i < N) {
+                const uint4 r4 = Philox::rounds<7>(make_uint4((uint32_t)b, c1, blk++, c3), key0, key1);
+                draw(r4.x, M1, M2);
+                if (i + 1 < N) draw(r4.y, M1b, M2b);
+                if (i + 2 < N) draw(r4.z, M1, M2);
+            }
+            emit_replicate<true>(P, seg_rel, b, M1 + M1b, M2 + M2b, N, inv_n, fit, s_log);
         }
     }
 }
@@ -620,8 +736,10 @@ MM_EXPORT int mm_boot_prepare(int device, void* stream, void* entries, const int
     P.R = R; P.seg_U = seg_U; P.group_ncells = group_ncells; P.n_table_max = n_table_max; P.tab_off = tab_off;
     P.acc_slot = (const long long*)acc_slot; P.acc_stride = acc_stride; P.acc_pool = acc_pool;
     P.info = (SegInfo*)seg_info; P.min_accept = min_accept;
+    P.allow_direct = !(getenv("MM_BOOT_DIRECT") && !atoi(getenv("MM_BOOT_DIRECT")));      // A/B hook
     long long blocks = (n_seg + 7) / 8;
     MM_REQUIRE(blocks < 2147483647LL, "too many segments");
+    MM_CUDA(cudaMemsetAsync(seg_lists(seg_info, n_seg).count, 0, 4 * sizeof(int), (cudaStream_t)stream));
     boot_prepare_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_boot_prepare");
 }
@@ -660,7 +778,8 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     if (passes < 1) passes = 1;
     P.reps_per_block = kBootThreads * passes * n_slots;
     MM_REQUIRE(!seg_info || (tab_pool && acc_pool), "seg_info needs tab_pool and acc_pool");
-    dim3 grid((num_boot + kBootThreads - 1) / kBootThreads, (unsigned)n_seg);
+    // with a sampler choice the chain kernel walks the chain list (modes 0 / -1: usually a handful of segments)
+    dim3 grid((num_boot + kBootThreads - 1) / kBootThreads, (unsigned)(seg_info ? (n_seg < 512 ? n_seg : 512) : n_seg));
     bootstrap_1d_kernel<<<grid, kBootThreads, 0, (cudaStream_t)stream>>>(P);
     if (int s = check_launch("mm_bootstrap_1d (chain)")) return s;
     if (seg_info) {
@@ -673,6 +792,12 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
         else if (n_slots == 3) bootstrap_1d_poisson_kernel<1, 3><<<grid2, kBootThreads, 0, st>>>(P);
         else if (n_slots == 4) bootstrap_1d_poisson_kernel<1, 4><<<grid2, kBootThreads, 0, st>>>(P);
         else bootstrap_1d_poisson_kernel<1, 2><<<grid2, kBootThreads, 0, st>>>(P);
+        if (int s = check_launch("mm_bootstrap_1d (Poissonised)")) return s;
+        // dense segments boot_prepare marked for direct cell resampling (blocks of other segments exit at once)
+        const size_t smem = (size_t)kDirectMaxCells * sizeof(double2);
+        MM_CUDA(cudaFuncSetAttribute(bootstrap_1d_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid3((num_boot + kDirectReps - 1) / kDirectReps, (unsigned)(n_seg < 1024 ? n_seg : 1024));
+        bootstrap_1d_direct_kernel<<<grid3, kBootThreads, smem, st>>>(P);
     }
     return check_launch("mm_bootstrap_1d");
 }

@@ -203,7 +203,8 @@ def bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_ski
     if sampler == "poisson":
         tab_off, tab_pool = poisson_tables(dev)
         acc_pool = torch.empty(max(1, n_genes * design.acc_stride), dtype=torch.int32, device=dev)
-        seg_info = torch.empty(n_seg * SEG_INFO_BYTES, dtype=torch.uint8, device=dev)
+        # n_seg SegInfo records + the sampler work lists {4 counters, chain list, direct list} (csrc/bootstrap.cu seg_lists)
+        seg_info = torch.empty(n_seg * SEG_INFO_BYTES + 4 * (4 + 2 * n_seg), dtype=torch.uint8, device=dev)
         ev = timer.start()
         _lib.call("mm_boot_prepare", dev, tab["entries"], seg.seg_ptr, tab["seg_lo"], n_seg, R, tab["seg_U"],
                   design.n_cells, N_TABLE_MAX, tab_off, design.acc_slot, design.acc_stride, acc_pool, seg_info,
@@ -222,8 +223,8 @@ def bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_ski
 
 
 def segment_modes(seg_info, n_seg):
-    """int32 tensor of the sampler chosen per segment (1 Poissonised, 0 chain, -1 all-NaN)."""
-    return seg_info.view(n_seg, SEG_INFO_BYTES)[:, :4].contiguous().view(torch.int32).reshape(-1)
+    """int32 tensor of the sampler chosen per segment (1 Poissonised, 2 direct cell resampling, 0 chain, -1 all-NaN)."""
+    return seg_info[:n_seg * SEG_INFO_BYTES].view(n_seg, SEG_INFO_BYTES)[:, :4].contiguous().view(torch.int32).reshape(-1)
 
 
 def ht_1d_tile_boot(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, num_boot, estimator, seed,
@@ -283,6 +284,7 @@ def ht_1d_tile_regress(ctx, design, R, covariate, treatment, num_boot, seed, app
             modes = segment_modes(seg_info, n_seg)
             terms["poisson"] = ((modes == 1) & (seg_ok != 0)).sum()
             terms["chain"] = ((modes == 0) & (seg_ok != 0)).sum()
+            terms["direct"] = ((modes == 2) & (seg_ok != 0)).sum()
         stats.setdefault("_terms", []).append(terms)
         stats["segments"] = stats.get("segments", 0) + n_seg
         # unique x2 (+memset), prepare, bootstrap x2, fill, wls, regress
@@ -303,6 +305,7 @@ def finalize_stats(stats, num_boot, n_cells):
         if "poisson" in t:
             stats["poisson_segments"] = stats.get("poisson_segments", 0) + int(t["poisson"].item())
             stats["chain_segments"] = stats.get("chain_segments", 0) + int(t["chain"].item())
+            stats["direct_segments"] = stats.get("direct_segments", 0) + int(t["direct"].item())
 
 
 def ht_1d_tile(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv, covariate, treatment, num_boot,

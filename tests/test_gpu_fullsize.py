@@ -85,3 +85,53 @@ def test_ht_1d_invariant_to_gene_tiling_full_size(full):
         else:
             np.testing.assert_allclose(res[0][k], res[1][k], rtol=1e-9, atol=0, equal_nan=True, err_msg=k)
     assert np.isfinite(res[0]["mean_asl"]).mean() > 0.9
+
+
+def test_direct_resampling_matches_chain_on_dense_segments(full, monkeypatch):
+    """Dense genes (largest category < 4 % of the cells: acceptance of the Poissonised sampler below 0.2) are
+    resampled cell by cell from a shared-memory table.  On the most expressed genes of the full-size matrix: the
+    direct kernel is the one that ran, and its bootstrap distribution agrees with the conditional-binomial chain
+    (both exact multinomial samplers) in mean, spread and by a two-sample KS test per segment."""
+    from scipy import stats
+    from memento_b200 import engine
+    ad, X, _ = full
+    st = ad.uns["memento"]["_b200"]
+    if st.design is None:
+        from memento_b200 import main as M
+        M._refresh_design(ad)
+    seg = st.seg
+    R = seg.R
+    nnz_gene = (seg.seg_ptr_host[R::R] - seg.seg_ptr_host[:-1:R])
+    g0 = int(np.argmax(nnz_gene))                         # the densest gene and its neighbours
+    lo = max(0, min(g0 - 8, seg.G - 16))
+    G, B = 16, 4000
+    n_seg = G * R
+    out = {}
+    for sampler in ("poisson", "chain"):
+        tab = engine.unique_tables(seg, st.design, st.cell_bin, lo, G, 0)       # boot_prepare rewrites the tables
+        m, v, info = engine.bootstrap_tile(seg, st.design, tab, G, 0, B, 77, sampler=sampler)
+        torch.cuda.synchronize()
+        out[sampler] = (m.cpu().numpy().reshape(n_seg, B), v.cpu().numpy().reshape(n_seg, B))
+        if sampler == "poisson":
+            modes = engine.segment_modes(info, n_seg).cpu().numpy()
+    direct = np.flatnonzero(modes == 2)
+    assert direct.size >= R, (direct.size, np.bincount(modes + 1))             # the dense gene really took this path
+    pv = []
+    for s in direct:
+        a, b = out["poisson"][0][s], out["chain"][0][s]
+        se = np.sqrt((a.var() + b.var()) / B)
+        assert abs(a.mean() - b.mean()) < 5.5 * se, (s, a.mean(), b.mean(), se)
+        assert abs(a.std() / b.std() - 1) < 0.1, (s, a.std(), b.std())
+        pv.append(stats.ks_2samp(a, b).pvalue)
+        ra, rb = out["poisson"][1][s], out["chain"][1][s]
+        assert np.isfinite(ra).all() == np.isfinite(rb).all()
+        pv.append(stats.ks_2samp(ra[np.isfinite(ra)], rb[np.isfinite(rb)]).pvalue)
+    pv = np.array(pv)
+    assert pv.min() > 1e-5, pv.min()
+    assert stats.kstest(pv, "uniform").pvalue > 1e-3
+    # direct rows do not depend on the Poissonised kernel's slot count or on being enabled per block order
+    monkeypatch.setenv("MM_BOOT_LPT", "0")
+    tab = engine.unique_tables(seg, st.design, st.cell_bin, lo, G, 0)
+    m2, _, _ = engine.bootstrap_tile(seg, st.design, tab, G, 0, B, 77)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(m2.cpu().numpy().reshape(n_seg, B), out["poisson"][0])
