@@ -19,6 +19,7 @@ With N > 1 (torchrun) every rank runs its own gene shard of the same shape (weak
 independent units, no data-path collective); rank 0 prints one JSON line.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -115,7 +116,9 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.lines, self.proc = [], None
+        # started BEFORE the warm-up steps (nvidia-smi's own start-up takes driver locks for a few hundred ms);
+        # mark() opens the timed region, only samples that arrive after it are reported
+        self.lines, self.proc, self.t_mark = [], None, 0.0
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -127,7 +130,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -136,7 +142,9 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t_arr, ln in self.lines:
+            if t_arr < self.t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -264,20 +272,31 @@ def run_ours(a):
     kw = dict(num_boot=a.num_boot, resampling="bootstrap", approx=bool(a.approx))
 
     # ---- resident-input steps
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
+        t0 = time.perf_counter()
         memento.ht_1d_moments(ad, cov, tr, seed=1, **kw)
+        if rank == 0:
+            print("warm-up step %.1f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
     st.timer.collect()
     st.timer.ms.clear(); st.timer.calls.clear()
+    gc.collect()
+    gc.disable()            # no collector pauses inside the timed region
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     launches = 0
     for i in range(a.steps):
-        memento.ht_1d_moments(ad, cov, tr, seed=100 + i, **kw)
+        t0 = time.perf_counter()
+        memento.ht_1d_moments(ad, cov, tr, seed=100 + i, **kw)      # returns after its device-to-host result copies
         launches += st.last_stats.get("launches", 0)
+        if rank == 0:
+            print("timed step %.1f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
     e1.record()
     barrier()
+    gc.enable()
     ms_total = e0.elapsed_time(e1)
     clk = clocks.stop() if clocks else None
     stage_ms = st.timer.collect()
