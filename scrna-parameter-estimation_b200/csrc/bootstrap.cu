@@ -9,8 +9,8 @@
 // categories (the zero-count category is the remainder and contributes nothing, so it is never
 // drawn).  Binomial sampler: sequential inversion when the expected count is small, Hormann's BTRS
 // transformed rejection otherwise (log-pmf ratio evaluated in a cancellation-free log1p form so
-// that float32 is enough at n ~ 1e6).  Randomness: Philox4x32-10, counter = (replicate, segment,
-// block, stream tag), key = seed: any replicate of any segment can be regenerated independently.
+// that float32 is enough at n ~ 1e6).  Randomness: Philox4x32 (10 rounds in the chain, 7 in the Poissonised and
+// direct samplers), counter = (replicate, segment, block, stream tag), key = seed: any replicate of any segment can be regenerated independently.
 // Moments accumulate in float64.  No U x B matrix is ever materialised.
 //
 // mm_bootstrap_1d_replay evaluates the same moments from host-supplied resample counts (the
@@ -25,8 +25,14 @@
 // Because multinomial(x) / prod Poisson(x_u) depends on x only through s = sum x_u, the accepted
 // draw is EXACTLY multinomial(N, n / N); the acceptance rate is 1 / max g ~ sqrt(1 - P) (0.88 at 23 %
 // nonzero cells).  Segments where this would be below min_accept (flat, dense genes), or with a
-// multiplicity above the table range, use the chain.  Each lane loops over its own replicates and simply retries on rejection, so
-// rejections cost their expected value, not a warp-wide maximum.
+// multiplicity above the table range, are resampled cell by cell from a shared-memory table (bootstrap_1d_direct_kernel)
+// when their nonzero cells fit it, and use the chain otherwise.  Each lane loops over its own replicates and simply
+// retries on rejection, so rejections cost their expected value, not a warp-wide maximum.
+//
+// Three kernels per launch of mm_bootstrap_1d: the chain over its work list (NaN rows, the rare leftovers), the
+// Poissonised kernel over all segments in longest-table-first order, the direct kernel over its work list.  The
+// random numbers of a replicate depend on (seed, replicate, global segment id, attempt) only: results are
+// independent of tiling, sharding, block order and the number of replicates a lane runs in lockstep.
 #include "common.cuh"
 #include <stdlib.h>
 
