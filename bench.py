@@ -133,6 +133,11 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def mark(self):
+        # nvidia-smi attaches to the driver for 1-2 s before its first line; entering the timed region while it does
+        # cost up to 80 ms on the first timed steps (measured), so wait for the first sample
+        t_end = time.perf_counter() + 5.0
+        while self.proc is not None and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.02)
         self.t_mark = time.perf_counter()
 
     def stop(self):

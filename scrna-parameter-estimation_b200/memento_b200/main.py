@@ -433,9 +433,9 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     main_stream = torch.cuda.current_stream(st.device)
     side = None
     if not approx and replay is None:
-        side = getattr(st, "side_stream", None)
-        if side is None:
-            side = st.side_stream = torch.cuda.Stream(st.device)
+        if getattr(st, "side_streams", None) is None:
+            st.side_streams = [torch.cuda.Stream(st.device), torch.cuda.Stream(st.device)]
+        side = st.side_streams[0]
     pending = []
     tiles = [(lo, min(genes_per_tile, G - lo)) for lo in range(0, G if replay is None else 0, genes_per_tile)]
 
@@ -454,6 +454,7 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
                                         want_coef_rows=not approx, timer=st.timer, resample_rep=resample_rep)
         ctx = nxt
         if side is not None:
+            side = st.side_streams[i & 1]       # consecutive tiles' GEV stages (latency-bound) may overlap each other
             side.wait_stream(main_stream)
             with torch.cuda.stream(side):
                 gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
@@ -462,7 +463,8 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
             del res["coef_rows"]            # the allocator keeps the block until the side stream is done with it
         pending.append((lo, n, {k: res[k] for k in out}))
     if side is not None:
-        main_stream.wait_stream(side)
+        for sd in st.side_streams:
+            main_stream.wait_stream(sd)
     for lo, n, res in pending:
         for k in out:
             out[k][lo:lo + n] = res[k].cpu().numpy()
