@@ -132,12 +132,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
-    def mark(self):
+    def wait_ready(self):
         # nvidia-smi attaches to the driver for 1-2 s before its first line; entering the timed region while it does
         # cost up to 80 ms on the first timed steps (measured), so wait for the first sample
         t_end = time.perf_counter() + 5.0
         while self.proc is not None and not self.lines and time.perf_counter() < t_end:
             time.sleep(0.02)
+
+    def mark(self):
         self.t_mark = time.perf_counter()
 
     def stop(self):
@@ -260,6 +262,7 @@ def run_ours(a):
 
     # rank r owns gene block r of the same cells (weak scaling: 10k genes per GPU); the UMI totals are
     # all-reduced and the moment vectors all-gathered inside setup_memento / compute_1d_moments
+    clocks = ClockSampler(local) if (rank == 0 and not os.environ.get("MM_NO_CLOCKS")) else None      # diagnostic switch
     ad = make_data(a, rank, dev)
     ad_host = ad.copy() if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     ctx = None
@@ -277,7 +280,13 @@ def run_ours(a):
     kw = dict(num_boot=a.num_boot, resampling="bootstrap", approx=bool(a.approx))
 
     # ---- resident-input steps
-    clocks = ClockSampler(local) if rank == 0 else None
+    # (the clock sampler was started before the data was made: its start-up is over by now; nothing between the last
+    # warm-up step and the timed region leaves the device idle -- an idle second there costs the first timed steps
+    # 20-80 ms while the clocks ramp up again)
+    if clocks:
+        clocks.wait_ready()
+    gc.collect()
+    gc.disable()            # no collector pauses inside the warm-up + timed steps
     for _ in range(a.warmup):
         t0 = time.perf_counter()
         memento.ht_1d_moments(ad, cov, tr, seed=1, **kw)
@@ -285,8 +294,6 @@ def run_ours(a):
             print("warm-up step %.1f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
     st.timer.collect()
     st.timer.ms.clear(); st.timer.calls.clear()
-    gc.collect()
-    gc.disable()            # no collector pauses inside the timed region
     barrier()
     if clocks:
         clocks.mark()

@@ -404,7 +404,10 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     true_rv = np.stack([mem["1d_moments"][g][2] for g in groups], axis=1)
 
     if workspace_bytes is None:
-        workspace_bytes = engine.default_workspace(st.device)
+        # asked once per data set: cudaMemGetInfo in front of every call showed up as an occasional 85 ms stall
+        if getattr(st, "workspace_default", None) is None:
+            st.workspace_default = engine.default_workspace(st.device)
+        workspace_bytes = st.workspace_default
     genes_per_tile = engine.tile_plan(st.seg, num_boot, workspace_bytes)
     if os.environ.get("MM_WORKSPACE_GB"):           # tuning hook
         genes_per_tile = engine.tile_plan(st.seg, num_boot, int(float(os.environ["MM_WORKSPACE_GB"]) * (1 << 30)))
