@@ -31,7 +31,11 @@ for _ in range(3):
     memento.ht_1d_moments(ad, cov, tr, num_boot=10000, resampling="bootstrap", seed=1)
 gc.collect(); gc.disable()
 steps = []
+E2E = bool(os.environ.get("MM_DIAG_E2E"))      # host-staged mode: the matrix is uploaded inside every call
+st = ad.uns["memento"]["_b200"]
 for i in range(40):
+    if E2E:
+        st.offload()
     trace.clear(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     memento.ht_1d_moments(ad, cov, tr, num_boot=10000, resampling="bootstrap", seed=10 + i)

@@ -139,11 +139,51 @@ class SegMatrix:
                 "seg_ptr": self.seg_ptr.cpu().pin_memory(), "G": self.G, "R": self.R, "n_cells": self.n_cells,
                 "group_start": self.group_start_host}
 
+    _copy_streams = {}
+
     @staticmethod
-    def from_host_pinned(h, device):
-        seg = SegMatrix(h["vals"].to(device, non_blocking=True), h["rows"].to(device, non_blocking=True),
-                        h["seg_ptr"].to(device, non_blocking=True), h["G"], h["R"], h["n_cells"], h["group_start"])
-        return seg
+    def from_host_pinned(h, device, split_gene=None):
+        """Upload of the pinned host copies.  Returns (matrix, pending_tail).  With ``split_gene`` only the nonzeros of
+        the genes below it are copied now; ``SegMatrix.upload_tail(pending_tail)`` copies the rest on a separate stream
+        and returns the event to wait for before anything reads it.  The caller issues it AFTER it has queued the first
+        gene tile's kernels: the copy engine is first-in first-out, so every small synchronous upload issued behind the
+        big second slice would wait for it (measured: first kernel at 9.7 ms instead of 5)."""
+        seg_ptr = h["seg_ptr"].to(device, non_blocking=True)
+        G, R = int(h["G"]), int(h["R"])
+        pending = None
+        if split_gene is None or split_gene <= 0 or split_gene >= G:
+            vals, rows = h["vals"].to(device, non_blocking=True), h["rows"].to(device, non_blocking=True)
+        else:
+            split = int(h["seg_ptr"][split_gene * R])
+            nnz = h["vals"].numel()
+            vals = torch.empty(nnz, dtype=torch.float32, device=device)
+            rows = torch.empty(nnz, dtype=torch.int32, device=device)
+            vals[:split].copy_(h["vals"][:split], non_blocking=True)
+            rows[:split].copy_(h["rows"][:split], non_blocking=True)
+            head = torch.cuda.Event()
+            head.record(torch.cuda.current_stream(device))
+            pending = (h, split, vals, rows, head)
+        seg = SegMatrix(vals, rows, seg_ptr, G, R, h["n_cells"], h["group_start"])
+        seg._seg_ptr_host = h["seg_ptr"].numpy()        # the host copy is at hand: no read-back, no synchronisation
+        return seg, pending
+
+    @staticmethod
+    def upload_tail(pending):
+        h, split, vals, rows, head = pending
+        device = vals.device
+        key = (device.type, device.index)
+        if key not in SegMatrix._copy_streams:
+            SegMatrix._copy_streams[key] = torch.cuda.Stream(device)
+        cs = SegMatrix._copy_streams[key]
+        cs.wait_event(head)
+        with torch.cuda.stream(cs):
+            vals[split:].copy_(h["vals"][split:], non_blocking=True)
+            rows[split:].copy_(h["rows"][split:], non_blocking=True)
+            tail = torch.cuda.Event()
+            tail.record(cs)
+        vals.record_stream(cs)
+        rows.record_stream(cs)
+        return tail
 
     @staticmethod
     def host_bytes(h):

@@ -70,9 +70,13 @@ def default_workspace(device):
 def tile_plan(seg, num_boot, workspace_bytes=6 << 30):
     """Genes per tile: bounded by the bootstrap grid (65535 segments) and by the workspace
     (32 bytes per (segment, replicate): raw mean/rv + log mean/var)."""
+    return tile_plan_groups(seg.R, num_boot, workspace_bytes)
+
+
+def tile_plan_groups(R, num_boot, workspace_bytes):
     per_seg = 32 * (num_boot + 1)
-    max_seg = max(seg.R, min(65535, workspace_bytes // per_seg))
-    return max(1, max_seg // seg.R)
+    max_seg = max(R, min(65535, workspace_bytes // per_seg))
+    return max(1, max_seg // R)
 
 
 def unique_tables(seg, design, cell_bin, gene_lo, n_genes, estimator, timer=NULL_TIMER, want_raw=False):

@@ -47,6 +47,8 @@ class DeviceState:
         self.cell_bin_host = None
         self.last_stats = {}
         self.host = None         # pinned host staging copies (end-to-end mode)
+        self.pending_tail = None # second part of a split upload, not issued yet
+        self.tail_event = None   # ... issued, to be waited for before it is read
         self.dist = None         # DistContext when the genes are sharded over ranks
         self.gene_offset = 0     # global index of this rank's first gene column
 
@@ -62,12 +64,21 @@ class DeviceState:
             self.host = {"seg": self.seg.to_host_pinned(), "cell_bin": self.cell_bin.cpu().pin_memory(),
                          "inv_sf": self.inv_sf_sorted.cpu().pin_memory()}
         self.seg = self.cell_bin = self.inv_sf_sorted = self.design = self.seg_all = None
+        self.pending_tail = self.tail_event = None
         self.h2d_bytes = 0
 
-    def ensure_resident(self):
+    def upload_tail(self):
+        if self.pending_tail is not None:
+            self.tail_event = SegMatrix.upload_tail(self.pending_tail)
+            self.pending_tail = None
+
+    def ensure_resident(self, split_gene=None):
+        """``split_gene`` (ht_1d_moments only): upload the genes below it now and leave the rest to ``upload_tail()``,
+        which the caller issues once the first tile's kernels are queued (see SegMatrix.from_host_pinned);
+        ``self.tail_event`` then has to be waited for before the second part is read."""
         if self.seg is None:
             h = self.host
-            self.seg = SegMatrix.from_host_pinned(h["seg"], self.device)
+            self.seg, self.pending_tail = SegMatrix.from_host_pinned(h["seg"], self.device, split_gene)
             self.cell_bin = h["cell_bin"].to(self.device, non_blocking=True)
             self.inv_sf_sorted = h["inv_sf"].to(self.device, non_blocking=True)
             self.h2d_bytes += SegMatrix.host_bytes(h["seg"]) + h["cell_bin"].numel() + h["inv_sf"].numel() * 8
@@ -390,9 +401,21 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         raise NotImplementedError("only resampling='bootstrap' is implemented on the device path")
     mem = adata.uns["memento"]
     st = _state(adata)
-    st.ensure_resident()
     groups = mem["groups"]
     R, G = len(groups), adata.shape[1]
+    if workspace_bytes is None:
+        # asked once per data set: cudaMemGetInfo in front of every call showed up as an occasional 85 ms stall
+        if getattr(st, "workspace_default", None) is None:
+            st.workspace_default = engine.default_workspace(st.device)
+        workspace_bytes = st.workspace_default
+    genes_per_tile = engine.tile_plan_groups(R, num_boot, workspace_bytes)
+    if os.environ.get("MM_WORKSPACE_GB"):           # tuning hook
+        genes_per_tile = engine.tile_plan_groups(R, num_boot, int(float(os.environ["MM_WORKSPACE_GB"]) * (1 << 30)))
+    if G > genes_per_tile and os.environ.get("MM_TILE_BALANCE", "0") != "0":      # equal tiles instead of full ones + a sliver
+        genes_per_tile = -(-G // -(-G // genes_per_tile))
+    # host-staged matrix (end-to-end mode): the second and later gene tiles are uploaded behind the first one's
+    # slice, under the first tile's kernels
+    st.ensure_resident(split_gene=genes_per_tile if (replay is None and G > genes_per_tile) else None)
     estimator = _estimator_code(mem["estimator_type"])
     if st.design is None:
         _refresh_design(adata)
@@ -403,16 +426,6 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     true_mean = np.stack([mem["1d_moments"][g][0] for g in groups], axis=1)   # (G, R)
     true_rv = np.stack([mem["1d_moments"][g][2] for g in groups], axis=1)
 
-    if workspace_bytes is None:
-        # asked once per data set: cudaMemGetInfo in front of every call showed up as an occasional 85 ms stall
-        if getattr(st, "workspace_default", None) is None:
-            st.workspace_default = engine.default_workspace(st.device)
-        workspace_bytes = st.workspace_default
-    genes_per_tile = engine.tile_plan(st.seg, num_boot, workspace_bytes)
-    if os.environ.get("MM_WORKSPACE_GB"):           # tuning hook
-        genes_per_tile = engine.tile_plan(st.seg, num_boot, int(float(os.environ["MM_WORKSPACE_GB"]) * (1 << 30)))
-    if G > genes_per_tile and os.environ.get("MM_TILE_BALANCE", "0") != "0":      # equal tiles instead of full ones + a sliver
-        genes_per_tile = -(-G // -(-G // genes_per_tile))
     out = {k: np.full((G, 2, T), np.nan) for k in ("coef", "se", "asl")}
     stats_acc = {"want_modes": bool(getattr(st, "count_modes", False))}
     if sampler not in ("poisson", "chain"):
@@ -449,9 +462,13 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
                                       min_accept=getattr(st, "min_accept", 0.2))
 
     ctx = first_half(*tiles[0]) if tiles else None
+    st.upload_tail()            # split upload: the later tiles' slice goes out under the first tile's kernels
     for i, (lo, n) in enumerate(tiles):
         # the next tile's bootstrap is queued before this tile's regression reads its validity flags on the host,
         # so the device never waits for the host between tiles (two tiles of bootstrap rows are alive at a time)
+        if i + 1 < len(tiles) and st.tail_event is not None:      # split upload: the later tiles' slice
+            main_stream.wait_event(st.tail_event)
+            st.tail_event = None
         nxt = first_half(*tiles[i + 1]) if i + 1 < len(tiles) else None
         res = engine.ht_1d_tile_regress(ctx, st.design, R, cov, tr_all, num_boot, seed, approx, one_sample,
                                         want_coef_rows=not approx, timer=st.timer, resample_rep=resample_rep)
@@ -468,6 +485,10 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     if side is not None:
         for sd in st.side_streams:
             main_stream.wait_stream(sd)
+    st.upload_tail()
+    if st.tail_event is not None:
+        main_stream.wait_event(st.tail_event)
+        st.tail_event = None
     for lo, n, res in pending:
         for k in out:
             out[k][lo:lo + n] = res[k].cpu().numpy()

@@ -487,6 +487,38 @@ def test_ht_1d_replay_gev_branch(gpu_prepared, oracle_prepared):
         assert (res[key][ok] > 0).all() and (res[key][ok] <= 1).all()
 
 
+def test_host_staged_ht_1d_equals_resident(gpu_prepared):
+    """End-to-end mode: the matrix lives in pinned host memory and every ht_1d_moments call uploads it -- the later
+    gene tiles' slice on a copy stream, under the first tile's kernels.  Same seed, same tiling: bit-identical to the
+    run on the resident matrix (three tiles, so the split upload and its event are exercised), and the matrix that
+    ends up on the device is the one that was staged."""
+    ad = gpu_prepared.copy()
+    st = ad.uns["memento"]["_b200"]
+    cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+    B = 1500
+    G, R = ad.shape[1], len(ad.uns["memento"]["groups"])
+    ws = 32 * (B + 1) * R * (G // 3 + 1)
+    kw = dict(num_boot=B, resampling="bootstrap", seed=21, workspace_bytes=ws)
+    memento.ht_1d_moments(ad, cov, tr, **kw)
+    want = {k: np.array(v) for k, v in ad.uns["memento"]["1d_ht"].items() if k.endswith(("coef", "se", "asl"))}
+    vals, rows, ptr = st.seg.vals.clone(), st.seg.rows.clone(), st.seg.seg_ptr.clone()
+    try:
+        for _ in range(2):
+            st.offload()
+            assert st.seg is None
+            memento.ht_1d_moments(ad, cov, tr, **kw)
+            assert st.h2d_bytes >= vals.numel() * 8
+            got = ad.uns["memento"]["1d_ht"]
+            for k, v in want.items():
+                np.testing.assert_array_equal(np.asarray(got[k]), v, err_msg=k)
+            torch.cuda.synchronize()
+            assert st.tail_event is None
+            assert torch.equal(st.seg.vals, vals) and torch.equal(st.seg.rows, rows) and torch.equal(st.seg.seg_ptr, ptr)
+    finally:
+        st.ensure_resident()        # the fixture's state is shared with the other tests
+        torch.cuda.synchronize()
+
+
 def test_rng_ht_1d_default_kwargs_vs_oracle(gpu_prepared, oracle_prepared):
     """RNG mode with the reference's default kwargs (approx=False: counting + GEV tails) at B=2000:
     rank concordance of -log10 p with the oracle, agreement on the strongly significant genes."""
