@@ -134,6 +134,17 @@ def wls_functional(device, covariate, treatment, weights, masks, one_sample, tim
     return cmat.view(n_mask, T, R)
 
 
+def distinct_masks(good):
+    """Distinct rows of a (n_gene, R) 0/1 uint8 array and, per gene, the index of its row among them (the partition
+    ``np.unique(good, axis=0, return_inverse=True)`` gives, in another order): rows are packed to bits and compared as
+    byte strings -- np.unique(axis=0) takes 5-10 ms for 4000 x 16 flags, host time the device idles through at the
+    end of the last tile."""
+    packed = np.ascontiguousarray(np.packbits(good, axis=1))
+    _, first, inverse = np.unique(packed.view(np.dtype((np.void, packed.shape[1]))).ravel(), return_index=True,
+                                  return_inverse=True)
+    return np.ascontiguousarray(good[first]), inverse.reshape(-1)
+
+
 def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, treatment, weights, one_sample,
                  approx, want_coef_rows, timer=NULL_TIMER, resample_rep=False, seed=0, gene_id=None,
                  assignments=None, good_host=None):
@@ -146,12 +157,7 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
         good_h = good_host[0].numpy().reshape(n_gene, R)
     else:
         good_h = seg_good.view(n_gene, R).cpu().numpy()
-    # distinct validity masks: rows packed to bits and compared as byte strings (np.unique(axis=0) takes 5-10 ms for
-    # 4000 x 16 flags -- host time the device idles through at the end of the last tile)
-    packed = np.ascontiguousarray(np.packbits(good_h, axis=1))
-    _, first, inverse = np.unique(packed.view(np.dtype((np.void, packed.shape[1]))).ravel(), return_index=True,
-                                  return_inverse=True)
-    masks = np.ascontiguousarray(good_h[first])
+    masks, inverse = distinct_masks(good_h)
     use_resampled = resample_rep and not one_sample      # reference: the one-sample branch ignores it
     if use_resampled:
         cmat, zmat, znorm2, w_d = wls_functional(device, covariate, treatment, weights, masks, one_sample, timer,

@@ -1,0 +1,40 @@
+"""Host-side helpers of the test engine that need no GPU: validity-mask partition, gene-tile planning."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scrna-parameter-estimation_b200"))
+
+from memento_b200 import engine  # noqa: E402
+
+
+@pytest.mark.parametrize("n,R,p", [(1, 1, 0.5), (7, 3, 0.5), (3782, 16, 0.97), (32, 2001, 0.9), (500, 64, 0.99),
+                                   (500, 65, 0.99), (100, 8, 1.0), (100, 8, 0.0)])
+def test_distinct_masks_is_the_partition_of_np_unique(n, R, p):
+    """The packed-bit partition of the per-gene validity masks = np.unique(axis=0)'s (reference
+    hypothesis_test.py:249-251 drops groups per gene; genes with the same surviving groups share one weighted
+    least-squares functional)."""
+    rng = np.random.default_rng(n * 1000 + R)
+    good = (rng.random((n, R)) < p).astype(np.uint8)
+    masks, inv = engine.distinct_masks(good)
+    want_masks, want_inv = np.unique(good, axis=0, return_inverse=True)
+    assert masks.shape == want_masks.shape and masks.dtype == np.uint8
+    assert inv.shape == (n,)
+    np.testing.assert_array_equal(masks[inv], good)                       # every gene maps to its own mask
+    assert len({m.tobytes() for m in masks}) == masks.shape[0]            # and the masks are distinct
+    # same partition: genes share a mask here iff they share one there
+    pairs = set(zip(inv.tolist(), np.asarray(want_inv).reshape(-1).tolist()))
+    assert len(pairs) == masks.shape[0]
+
+
+def test_tile_plan_respects_grid_and_workspace_limits():
+    B = 10000
+    per_seg = 32 * (B + 1)
+    assert engine.tile_plan_groups(16, B, 6 << 30) == (6 << 30) // per_seg // 16          # workspace-bound
+    assert engine.tile_plan_groups(16, B, 1 << 40) == 65535 // 16                         # grid-bound (65535 rows)
+    assert engine.tile_plan_groups(4000, B, 24 << 30) == 65535 // 4000
+    assert engine.tile_plan_groups(70000, B, 24 << 30) == 1                               # one gene always fits the plan
+    assert engine.tile_plan_groups(16, B, 1) == 1
