@@ -13,5 +13,6 @@ from .main import (compute_1d_moments, compute_2d_moments, create_groups, get_co
 from .getters import (fdrcorrect, get_1d_ht_result, get_1d_moments, get_2d_ht_result, get_2d_moments,  # noqa: F401
                       get_groups, prepare_to_save)
 from .anndata_lite import AnnDataLite  # noqa: F401
+from .io import load_results, read_10x_mtx, save_results, write_10x_mtx  # noqa: F401
 
 __version__ = "0.1.0"
