@@ -33,6 +33,11 @@ const char* mm_last_error(void);
 int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                     const float* data, int64_t n_rows, const uint8_t* gene_mask, double* out);
 
+/* Ingest check: counts must be non-negative integers below 2^24 (the compression keys of mm_seg_unique /
+ * mm_pair_unique hold the count in 24 bits; the reference's _unique_expr, memento/bootstrap.py:62-71, takes any
+ * value).  flags[0]: bit 0 = a negative or NaN value, bit 1 = a fractional value, bit 2 = a value >= 2^24. */
+int mm_validate_counts(int device, void* stream, const float* data, int64_t nnz, int32_t* flags);
+
 /* Ingest re-layout, CSR (cells x genes, canonical: no duplicate entries) -> group-sorted CSC, as a stable counting
  * transposition in three passes (csrc/relayout.cu).  New rows (cells ordered group by group; order[r] = original
  * cell of new row r, NULL = identity) are cut into chunks of consecutive rows of ONE group: chunk_row_lo
@@ -41,15 +46,19 @@ int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32
  *   mm_relayout_count : per-chunk per-gene counts, their exclusive prefix over every group's chunks (left in cnt)
  *                       and seg_len[gene * R + group]; the caller prefix-sums seg_len into seg_ptr [n_genes * R + 1].
  *   mm_relayout_fill  : vals_out / rows_out (new row ids) in segment order, rows ascending inside a segment.
+ * sorted_rows != 0 (both calls alike): the column indices of every CSR row ascend (scipy's canonical form) and no
+ * chunk has more than 256 rows -- the passes then run as a tiled transposition through shared memory with one
+ * coalesced run per (chunk, gene) instead of 4-byte scatters; err_flag (nullable) is set to 1 when a row turns
+ * out not to be sorted (the output is then undefined, never out of bounds).  Both paths give identical arrays.
  * Replaces: memento/main.py:115-132 + util.py:8-13 (per-group boolean scan + X[mask].tocsc() copy). */
 int mm_relayout_count(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                       const int32_t* order, const int32_t* chunk_row_lo, const int32_t* chunk_group,
                       const int32_t* group_chunk_lo, int32_t n_chunks, int32_t n_genes, int32_t R,
-                      int32_t* cnt, int64_t* seg_len);
+                      int32_t* cnt, int64_t* seg_len, int32_t sorted_rows, int32_t* err_flag);
 int mm_relayout_fill(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                      const float* data, const int32_t* order, const int32_t* chunk_row_lo,
                      const int32_t* chunk_group, int32_t n_chunks, int32_t n_genes, int32_t R, int32_t* cnt,
-                     const int64_t* seg_ptr, float* vals_out, int32_t* rows_out);
+                     const int64_t* seg_ptr, float* vals_out, int32_t* rows_out, int32_t sorted_rows);
 
 /* One pass over the group-sorted CSC matrix: for every segment s,
  *   out[0*n_seg+s] = sum x          out[1*n_seg+s] = max x
@@ -186,16 +195,20 @@ int mm_fill_log(int device, void* stream, const double* raw_mean, const double* 
 
 /* Batched small solves: for each of n_mask group-validity masks, the (T x R) linear functional C
  * with coef[t] = sum_r C[t,r] * y[r] equal to "residualise y and treatment on [1, covariate] with
- * weights, then weighted marginal slope".  covariate [R][n_cov], treatment [R][T], weights [R],
- * masks [n_mask][R]; scratch [n_mask][R][n_cov+T]; cmat [n_mask][T][R].  one_sample != 0: weighted
- * average over groups.  znorm2 (nullable) [n_mask][n_cov]: squared weighted norms of the orthogonalised
+ * weights, then weighted marginal slope".  A "design" k = a group-validity mask plus T treatment columns:
+ * covariate [R][n_cov], treatment [R][T_full], weights [R], masks [n_mask][R], col_idx (nullable)
+ * [n_mask][T] = the treatment columns of design k (NULL: columns 0 .. T-1, then T_full >= T);
+ * scratch [n_mask][R][n_cov+T]; cmat [n_mask][T][R].  one_sample != 0: weighted average over groups for
+ * every design; one_sample == 0: decided per design as the reference does per gene (its selected treatment
+ * columns are all ones on its valid groups, hypothesis_test.py:262); one_flag (nullable) [n_mask] receives
+ * the decision.  znorm2 (nullable) [n_mask][n_cov]: squared weighted norms of the orthogonalised
  * covariate directions left in scratch (0 = dropped as linearly dependent).
- * Replaces: memento/hypothesis_test.py:262-271 (three sklearn LinearRegression fits per gene) and
- * :218-228 (_cross_coef). */
+ * Replaces: memento/hypothesis_test.py:262-271 (three sklearn LinearRegression fits per gene),
+ * :218-228 (_cross_coef) and the per-gene column selection of main.py:368-373, :392. */
 int mm_wls_functional(int device, void* stream, const double* covariate, const double* treatment,
                       const double* weights, const uint8_t* masks, int32_t R, int32_t n_cov,
                       int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat,
-                      double* znorm2);
+                      double* znorm2, int32_t T_full, const int32_t* col_idx, int32_t* one_flag);
 
 /* resample_rep=True: hierarchical bootstrap over replicates.  boot0 / boot1 are residualised IN PLACE
  * on [1, covariate]; zmat / znorm2 = scratch / znorm2 of mm_wls_functional (orthogonalised covariate
@@ -204,6 +217,8 @@ int mm_wls_functional(int device, void* stream, const double* covariate, const d
  * slot (Philox, or rep_assign / iter_assign [n_gene][R][num_boot] in replay mode, indices into the
  * gene's list of valid groups resp. 1..num_boot).  coef_ws (nullable): [n_gene][n_stat][T][num_boot].
  * bad_flag is set when a non-finite bootstrap column is met (the caller raises).
+ * gene_list (nullable) [n_gene]: launched gene i reads the row block gene_list[i] of boot / seg_good /
+ * gene_id / the replay assignments; mask_id and every output are indexed by i (NULL: identity).
  * Replaces: memento/hypothesis_test.py:231-239 (_cross_coef_resampled), :273-286. */
 int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
                          const uint8_t* seg_good, const int32_t* mask_id, const double* zmat,
@@ -211,7 +226,8 @@ int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
                          int32_t n_cov, int32_t T, int32_t num_boot, int32_t approx, uint64_t seed,
                          const int64_t* gene_id, const int32_t* rep_assign, const int32_t* iter_assign,
                          double* coef_ws, double* out_coef, double* out_se, double* out_asl,
-                         int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag);
+                         int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag,
+                         const int32_t* gene_list);
 
 /* Per gene: coefficient of every bootstrap column, SE (population std of columns 1..), and the ASL:
  * approx != 0 -> two-sided normal tail; else extreme count c and (c+1)/(n+1) (out_extreme carries c
@@ -220,12 +236,16 @@ int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
  * n_split >= 1: CTAs per gene; with n_split > 1 the replicate columns of a gene are split between them
  * (for tiles with few genes and thousands of groups) and split_ws (float64 scratch of
  * n_gene * n_split * n_stat * T * 8) carries their partial statistics to a deterministic combine step.
+ * gene_list (nullable) [n_gene]: launched gene i reads the row block gene_list[i] of boot / seg_good;
+ * mask_id (the design of mm_wls_functional) and every output are indexed by i (NULL: identity) -- this is
+ * how genes with different numbers of treatment columns (treatment_for_gene) go out in one launch per T.
  * Replaces: memento/hypothesis_test.py:242-300 (_regress_1d), :367-414 (_regress_2d), :57-92. */
 int mm_regress_asl(int device, void* stream, const double* boot0, const double* boot1,
                    const uint8_t* seg_good, const int32_t* mask_id, const double* cmat,
                    int32_t n_gene, int32_t R, int32_t T, int32_t num_boot, int32_t approx,
                    double* coef_ws, double* out_coef, double* out_se, double* out_asl,
-                   int32_t* out_extreme, int32_t* out_nnull, int32_t n_split, double* split_ws);
+                   int32_t* out_extreme, int32_t* out_nnull, int32_t n_split, double* split_ws,
+                   const int32_t* gene_list);
 
 /* GEV tail refinement of the ASL for the tests listed in `flagged` (row ids into coef_rows / asl):
  * sorts the null (coef_rows[row][1..] - coef_rows[row][0], finite entries), fits a generalised extreme

@@ -187,11 +187,16 @@ fill_rows_kernel(FillParams P) {
 // C[t, r] = w_r * a~_tr / sum_r w_r a~_tr^2.  One CTA per mask; the work matrix lives in global scratch.
 struct WlsParams {
     const double* covariate;    // [R][P]
-    const double* treatment;    // [R][T]
+    const double* treatment;    // [R][T_full]
     const double* weights;      // [R]  (cells per group)
     const unsigned char* masks; // [n_mask][R]
     int R, Pc, T, n_mask;
-    int one_sample;             // treatment is all ones: weighted average over groups
+    int T_full;                 // columns of the treatment matrix
+    const int* col_idx;         // nullable [n_mask][T]: the treatment columns of design k (reference main.py:368-373,
+                                // 392: treatment[treatment_for_gene[gene]]); null: columns 0 .. T-1
+    int one_sample;             // 1: forced; 0: decided per design (reference hypothesis_test.py:262: the selected
+                                // treatment columns are all ones on the valid groups -> weighted average over groups)
+    int* one_flag;              // nullable [n_mask]: the decision taken
     double* scratch;            // [n_mask][R][Pc + T]
     double* cmat;               // [n_mask][T][R]
     double* znorm2;             // optional [n_mask][Pc]: squared W-norms of the orthogonalised covariate
@@ -212,17 +217,25 @@ __global__ void __launch_bounds__(kRegThreads)
 wls_functional_kernel(WlsParams P) {
     __shared__ double sred[kRegThreads / 32];
     const int k = blockIdx.x;
-    const int R = P.R, Pc = P.Pc, T = P.T, K = Pc + T;
+    const int R = P.R, Pc = P.Pc, T = P.T, K = Pc + T, TF = P.T_full;
     const unsigned char* mask = P.masks + (long long)k * R;
     double* Z = P.scratch + (long long)k * R * K;
     double* C = P.cmat + (long long)k * T * R;
+    const int* cols = P.col_idx ? P.col_idx + (long long)k * T : nullptr;
     const int tid = threadIdx.x;
+    auto tcol = [&](int t) { return cols ? cols[t] : t; };
 
-    double wl = 0.0;
-    for (int r = tid; r < R; r += kRegThreads) wl += mask[r] ? P.weights[r] : 0.0;
+    double wl = 0.0, not_one = 0.0;
+    for (int r = tid; r < R; r += kRegThreads) {
+        if (!mask[r]) continue;
+        wl += P.weights[r];
+        for (int t = 0; t < T; ++t) not_one += (P.treatment[(long long)r * TF + tcol(t)] != 1.0) ? 1.0 : 0.0;
+    }
     const double wsum = block_sum(wl, sred);
+    const bool one_sample = P.one_sample != 0 || block_sum(not_one, sred) == 0.0;
+    if (P.one_flag && tid == 0) P.one_flag[k] = one_sample ? 1 : 0;
 
-    if (P.one_sample) {
+    if (one_sample) {
         for (int i = tid; i < T * R; i += kRegThreads) {
             int r = i % R;
             C[i] = mask[r] ? P.weights[r] / wsum : 0.0;
@@ -233,12 +246,12 @@ wls_functional_kernel(WlsParams P) {
     for (int c = 0; c < K; ++c) {
         double s = 0.0;
         for (int r = tid; r < R; r += kRegThreads) {
-            double v = c < Pc ? P.covariate[(long long)r * Pc + c] : P.treatment[(long long)r * T + (c - Pc)];
+            double v = c < Pc ? P.covariate[(long long)r * Pc + c] : P.treatment[(long long)r * TF + tcol(c - Pc)];
             s += mask[r] ? P.weights[r] * v : 0.0;
         }
         double mu = block_sum(s, sred) / wsum;
         for (int r = tid; r < R; r += kRegThreads) {
-            double v = c < Pc ? P.covariate[(long long)r * Pc + c] : P.treatment[(long long)r * T + (c - Pc)];
+            double v = c < Pc ? P.covariate[(long long)r * Pc + c] : P.treatment[(long long)r * TF + tcol(c - Pc)];
             Z[(long long)r * K + c] = mask[r] ? v - mu : 0.0;
         }
     }
@@ -273,7 +286,7 @@ wls_functional_kernel(WlsParams P) {
         for (int r = tid; r < R; r += kRegThreads) {
             double a = Z[(long long)r * K + Pc + t];
             s += P.weights[r] * a * a;
-            double v0 = P.treatment[(long long)r * T + t];
+            double v0 = P.treatment[(long long)r * TF + tcol(t)];
             s0 += mask[r] ? P.weights[r] * v0 * v0 : 0.0;
         }
         double ss = block_sum(s, sred);
@@ -291,7 +304,9 @@ struct RegParams {
     const double* boot[2];      // [n_gene][R][B+1]; boot[1] may be null (single statistic, 2D path)
     int n_stat;
     const unsigned char* seg_good;  // [n_gene][R]
-    const int* mask_id;         // [n_gene]
+    const int* mask_id;         // [n_gene] design (validity mask x treatment columns) of every launched gene
+    const int* gene_list;       // nullable [n_gene]: row block (gene of the tile) every launched gene reads; outputs and
+                                // mask_id are indexed by the launch index
     const double* cmat;         // [n_mask][T][R]
     int R, T, B;
     int approx;                 // 1: normal approximation of the ASL
@@ -342,10 +357,11 @@ regress_asl_kernel(RegParams P) {
     __shared__ int s_cnt[kRegThreads / 32][2 * TT][2];
     __shared__ double s_mm[kRegThreads / 32][2 * TT][2];
     __shared__ int s_nvalid[kRegThreads / 32];
-    const int g = blockIdx.x;
+    const int gi = blockIdx.x;                                   // launch index: outputs, mask_id
+    const int g = P.gene_list ? P.gene_list[gi] : gi;            // rows of the tile
     const int R = P.R, T = P.T, B1 = P.B + 1, NS = P.n_stat;
     const unsigned char* good = P.seg_good + (long long)g * R;
-    const double* C = P.cmat + (long long)P.mask_id[g] * T * R;
+    const double* C = P.cmat + (long long)P.mask_id[gi] * T * R;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // regression functional of this gene's mask: shared memory when it fits, global (L1) otherwise
     __shared__ double s_Cbuf[kRegCmax];
@@ -361,7 +377,7 @@ regress_asl_kernel(RegParams P) {
 
     int n_good = 0;
     for (int r = 0; r < R; ++r) n_good += good[r];
-    const long long obase = (long long)g * NS * T;
+    const long long obase = (long long)gi * NS * T;
     if (n_good == 0) {   // reference hypothesis_test.py:203-204
         for (int i = tid; i < NS * T && blockIdx.y == 0; i += kRegThreads) {
             P.out_coef[obase + i] = nan(""); P.out_se[obase + i] = nan(""); P.out_asl[obase + i] = nan("");
@@ -437,7 +453,7 @@ regress_asl_kernel(RegParams P) {
                         if (t < tn) {
                             double c = finite ? acc[s][t] : nan("");
                             if (P.coef_ws)
-                                P.coef_ws[(((long long)g * NS + s) * T + t0 + t) * B1 + b] = c;
+                                P.coef_ws[(((long long)gi * NS + s) * T + t0 + t) * B1 + b] = c;
                             if (finite) {
                                 mn[s][t] = fmin(mn[s][t], c);
                                 mx[s][t] = fmax(mx[s][t], c);
@@ -493,7 +509,7 @@ regress_asl_kernel(RegParams P) {
             const double stat = s_stat[s][t];
             const long long o = obase + (long long)s * T + t0 + t;
             if (P.n_split > 1) {
-                double* w = P.split_ws + ((((long long)g * P.n_split + blockIdx.y) * NS + s) * T + t0 + t) * 8;
+                double* w = P.split_ws + ((((long long)gi * P.n_split + blockIdx.y) * NS + s) * T + t0 + t) * 8;
                 w[0] = a; w[1] = b2; w[2] = (double)h; w[3] = (double)l; w[4] = vmin; w[5] = vmax; w[6] = (double)n; w[7] = stat;
             } else {
                 regress_finish(P, o, stat, a, b2, h, l, vmin, vmax, n);
@@ -512,7 +528,8 @@ struct ResampParams {
     double* boot[2];            // [n_gene][R][B+1]; overwritten by the residualised rows
     int n_stat;
     const unsigned char* seg_good;  // [n_gene][R]
-    const int* mask_id;         // [n_gene]
+    const int* mask_id;         // [n_gene] (launch index)
+    const int* gene_list;       // nullable [n_gene]: see RegParams
     const double* zmat;         // wls scratch: [n_mask][R][Pc + T]
     const double* znorm2;       // [n_mask][Pc]
     const double* weights;      // [R]
@@ -533,11 +550,12 @@ regress_resampled_kernel(ResampParams P) {
     extern __shared__ int s_good[];                   // R ints: list of valid groups
     __shared__ double sred[kRegThreads / 32];
     __shared__ int s_ngood;
-    const int g = blockIdx.x, tid = threadIdx.x;
+    const int gi = blockIdx.x, tid = threadIdx.x;
+    const int g = P.gene_list ? P.gene_list[gi] : gi;
     const int R = P.R, Pc = P.Pc, T = P.T, B = P.B, B1 = B + 1, K = Pc + T, NS = P.n_stat;
     const unsigned char* good = P.seg_good + (long long)g * R;
-    const double* Z = P.zmat + (long long)P.mask_id[g] * R * K;
-    const double* zn = P.znorm2 + (long long)P.mask_id[g] * Pc;
+    const double* Z = P.zmat + (long long)P.mask_id[gi] * R * K;
+    const double* zn = P.znorm2 + (long long)P.mask_id[gi] * Pc;
     if (tid == 0) {
         int n = 0;
         for (int r = 0; r < R; ++r) if (good[r]) s_good[n++] = r;
@@ -545,7 +563,7 @@ regress_resampled_kernel(ResampParams P) {
     }
     __syncthreads();
     const int ng = s_ngood;
-    const long long obase = (long long)g * NS * T;
+    const long long obase = (long long)gi * NS * T;
     if (ng == 0) {
         for (int i = tid; i < NS * T; i += kRegThreads) {
             P.out_coef[obase + i] = nan(""); P.out_se[obase + i] = nan(""); P.out_asl[obase + i] = nan("");
@@ -641,7 +659,7 @@ regress_resampled_kernel(ResampParams P) {
             int hi = 0, lo = 0, cnt = 0;
             for (int j = tid; j < B; j += kRegThreads) {
                 double c = (j == 0) ? stat : slope(bt, t, j);
-                if (P.coef_ws) P.coef_ws[(((long long)g * NS + s) * T + t) * B + j] = c;
+                if (P.coef_ws) P.coef_ws[(((long long)gi * NS + s) * T + t) * B + j] = c;
                 if (!isfinite(c)) continue;        // degenerate resample (reference: dropped by isfinite / nanstd)
                 vmin = fmin(vmin, c); vmax = fmax(vmax, c);
                 if (j > 0) {
@@ -693,7 +711,7 @@ __global__ void regress_asl_finish_kernel(RegParams P, int n_gene) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n_gene * NS * T) return;
     const int g = (int)(i / (NS * T)), st = (int)(i % (NS * T));
-    const unsigned char* good = P.seg_good + (long long)g * P.R;
+    const unsigned char* good = P.seg_good + (long long)(P.gene_list ? P.gene_list[g] : g) * P.R;
     int n_good = 0;
     for (int r = 0; r < P.R; ++r) n_good += good[r];
     if (n_good == 0) return;                       // written by regress_asl_kernel
@@ -736,14 +754,16 @@ MM_EXPORT int mm_fill_log(int device, void* stream, const double* raw_mean, cons
 MM_EXPORT int mm_wls_functional(int device, void* stream, const double* covariate, const double* treatment,
                                 const double* weights, const uint8_t* masks, int32_t R, int32_t n_cov,
                                 int32_t T, int32_t n_mask, int32_t one_sample, double* scratch, double* cmat,
-                                double* znorm2) {
+                                double* znorm2, int32_t T_full, const int32_t* col_idx, int32_t* one_flag) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(R > 0 && n_cov >= 0 && T > 0 && n_mask >= 0, "R/n_cov/T/n_mask");
+    MM_REQUIRE(T_full >= T || (col_idx && T_full > 0), "T_full");
     if (n_mask == 0) return 0;
     MM_REQUIRE(treatment && weights && masks && scratch && cmat && (covariate || n_cov == 0), "null pointer");
     WlsParams P;
     P.covariate = covariate; P.treatment = treatment; P.weights = weights; P.masks = masks;
     P.R = R; P.Pc = n_cov; P.T = T; P.n_mask = n_mask; P.one_sample = one_sample;
+    P.T_full = T_full; P.col_idx = col_idx; P.one_flag = one_flag;
     P.scratch = scratch; P.cmat = cmat; P.znorm2 = znorm2;
     wls_functional_kernel<<<n_mask, kRegThreads, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_wls_functional");
@@ -753,7 +773,8 @@ MM_EXPORT int mm_regress_asl(int device, void* stream, const double* boot0, cons
                              const uint8_t* seg_good, const int32_t* mask_id, const double* cmat,
                              int32_t n_gene, int32_t R, int32_t T, int32_t num_boot, int32_t approx,
                              double* coef_ws, double* out_coef, double* out_se, double* out_asl,
-                             int32_t* out_extreme, int32_t* out_nnull, int32_t n_split, double* split_ws) {
+                             int32_t* out_extreme, int32_t* out_nnull, int32_t n_split, double* split_ws,
+                             const int32_t* gene_list) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_gene >= 0 && R > 0 && T > 0 && num_boot > 0, "n_gene/R/T/num_boot");
     MM_REQUIRE(n_split >= 1 && n_split <= 65535 && (n_split == 1 || split_ws), "n_split / split_ws");
@@ -762,6 +783,7 @@ MM_EXPORT int mm_regress_asl(int device, void* stream, const double* boot0, cons
                "null pointer");
     RegParams P;
     P.boot[0] = boot0; P.boot[1] = boot1; P.n_stat = boot1 ? 2 : 1; P.seg_good = seg_good; P.mask_id = mask_id;
+    P.gene_list = gene_list;
     P.cmat = cmat; P.R = R; P.T = T; P.B = num_boot; P.approx = approx; P.coef_ws = coef_ws;
     P.out_coef = out_coef; P.out_se = out_se; P.out_asl = out_asl; P.out_extreme = out_extreme;
     P.out_nnull = out_nnull; P.n_split = n_split; P.split_ws = split_ws;
@@ -783,7 +805,8 @@ MM_EXPORT int mm_regress_resampled(int device, void* stream, double* boot0, doub
                                    int32_t n_cov, int32_t T, int32_t num_boot, int32_t approx, uint64_t seed,
                                    const int64_t* gene_id, const int32_t* rep_assign, const int32_t* iter_assign,
                                    double* coef_ws, double* out_coef, double* out_se, double* out_asl,
-                                   int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag) {
+                                   int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag,
+                                   const int32_t* gene_list) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_gene >= 0 && R > 0 && T > 0 && num_boot > 1 && n_cov >= 0, "n_gene/R/T/num_boot/n_cov");
     if (n_gene == 0) return 0;
@@ -793,6 +816,7 @@ MM_EXPORT int mm_regress_resampled(int device, void* stream, double* boot0, doub
     MM_REQUIRE((size_t)R * sizeof(int) <= 200 * 1024, "too many groups for the shared valid-group list");
     ResampParams P;
     P.boot[0] = boot0; P.boot[1] = boot1; P.n_stat = boot1 ? 2 : 1; P.seg_good = seg_good; P.mask_id = mask_id;
+    P.gene_list = gene_list;
     P.zmat = zmat; P.znorm2 = znorm2; P.weights = weights; P.R = R; P.Pc = n_cov; P.T = T; P.B = num_boot;
     P.approx = approx; P.seed = seed; P.gene_id = (const long long*)gene_id; P.rep_assign = rep_assign;
     P.iter_assign = iter_assign; P.coef_ws = coef_ws; P.out_coef = out_coef; P.out_se = out_se; P.out_asl = out_asl;

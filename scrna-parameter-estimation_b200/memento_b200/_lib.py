@@ -18,8 +18,9 @@ _i32, _i64, _u64, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 SIGNATURES = {
     "mm_csr_row_sums": [_vp, _vp, _vp, _i64, _vp, _vp],
     "mm_seg_moments": [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
-    "mm_relayout_count": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
-    "mm_relayout_fill": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "mm_validate_counts": [_vp, _i64, _vp],
+    "mm_relayout_count": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+    "mm_relayout_fill": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32],
     "mm_block_panels": [_vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp],
     "mm_block_gemm": [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64],
     "mm_pair_products": [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],
@@ -31,16 +32,17 @@ SIGNATURES = {
     "mm_boot_prepare": [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, C.c_float],
     "mm_bootstrap_1d_replay": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "mm_fill_log": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _u64, _vp, _vp, _vp, _vp, _vp],
-    "mm_wls_functional": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "mm_wls_functional": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "mm_regress_resampled": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _u64, _vp, _vp,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mm_pair_unique": [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp],
     "mm_pair_prepare": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],
     "mm_pair_bootstrap": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _u64, _vp, _vp, _vp, _vp],
     "mm_pair_bootstrap_replay": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "mm_gev_tail_asl": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32],
-    "mm_regress_asl": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "mm_regress_asl": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                       _vp],
 }
 
 # host-only helpers (no leading device / stream arguments)

@@ -95,6 +95,19 @@ class CsrOnDevice:
         self.indices = to_device(X.indices, device, np.int32, pinned)
         self.data = to_device(data, device, np.float32, pinned)
         self.nnz = int(self.data.numel())
+        # column indices ascending inside every row and no duplicates (scipy's canonical form; scipy scans the
+        # index arrays once when the flag is not cached): the re-layout then takes its tiled path
+        self.sorted_rows = bool(X.has_canonical_format)
+        # the compression keys hold a count in 24 bits and the moment kernels read the same values: anything but
+        # non-negative integers below 2^24 would make bootstrap tables and moments disagree without an error
+        flags = torch.zeros(1, dtype=torch.int32, device=device)
+        _lib.call("mm_validate_counts", device, self.data, self.nnz, flags)
+        bad = int(flags.item())
+        if bad:
+            what = [m for b, m in ((1, "negative or NaN values"), (2, "non-integer values"), (4, "values >= 2**24"))
+                    if bad & b]
+            raise ValueError("adata.X must hold raw counts (non-negative integers below 2**24) on the device path: "
+                             "found " + ", ".join(what))
 
     def row_sums(self, gene_mask=None, timer=NULL_TIMER):
         out = torch.empty(self.shape[0], dtype=torch.float64, device=self.device)
@@ -211,9 +224,15 @@ class SegMatrix:
         gs = np.asarray([0, n_cells], dtype=np.int64) if group_start is None else np.asarray(group_start, dtype=np.int64)
         R = gs.size - 1
         sizes = np.diff(gs)
-        # chunks of consecutive rows of one group; enough of them to fill the GPU, few enough for the counter array
-        rpc = int(np.clip(n_cells // 8192, 32, 1024))
-        rpc = max(rpc, int(np.ceil(n_cells * float(n_genes) * 4 / 1.5e9)))
+        # chunks of consecutive rows of one group.  Tiled path (sorted rows): up to 256 rows (the height of the
+        # kernel's bit matrix); the generic path: enough chunks to fill the GPU, few enough for the counter array
+        TILE_ROWS = 256         # kTileRows in csrc/relayout.cu
+        tiled = bool(csr.sorted_rows) and n_cells * float(n_genes) * 4 / TILE_ROWS <= 4e9
+        if tiled:
+            rpc = TILE_ROWS
+        else:
+            rpc = int(np.clip(n_cells // 8192, 32, 1024))
+            rpc = max(rpc, int(np.ceil(n_cells * float(n_genes) * 4 / 1.5e9)))
         per_group = (sizes + rpc - 1) // rpc
         group_chunk_lo = np.concatenate([[0], np.cumsum(per_group)]).astype(np.int32)
         n_chunks = int(group_chunk_lo[-1])
@@ -227,15 +246,19 @@ class SegMatrix:
         order_d = None if order is None else d(np.asarray(order, dtype=np.int32))
         cnt = torch.empty(max(n_chunks, 1) * n_genes, dtype=torch.int32, device=dev)
         seg_ptr = torch.zeros(n_genes * R + 1, dtype=torch.int64, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
         ev = timer.start()
         _lib.call("mm_relayout_count", dev, csr.indptr, csr.indices, order_d, crl, cg, gcl, n_chunks, n_genes, R,
-                  cnt, seg_ptr[1:])
+                  cnt, seg_ptr[1:], 1 if tiled else 0, err)
         torch.cumsum(seg_ptr[1:], 0, out=seg_ptr[1:])
         vals = torch.empty(csr.nnz, dtype=torch.float32, device=dev)
         rows = torch.empty(csr.nnz, dtype=torch.int32, device=dev)
         _lib.call("mm_relayout_fill", dev, csr.indptr, csr.indices, csr.data, order_d, crl, cg, n_chunks, n_genes, R,
-                  cnt, seg_ptr, vals, rows)
+                  cnt, seg_ptr, vals, rows, 1 if tiled else 0)
         timer.stop("relayout", ev)
+        if tiled and int(err.item()) != 0:
+            raise _lib.MementoCudaError("adata.X claims canonical format but a row's column indices do not ascend; "
+                                        "call adata.X.sort_indices()")
         return SegMatrix(vals, rows, seg_ptr, n_genes, R, n_cells, gs if group_start is not None else None)
 
     @staticmethod

@@ -68,6 +68,12 @@ class DistContext:
             out = np.rint(out).astype(kind)
         return np.moveaxis(out, 0, axis), sizes
 
+    def all_gather_names(self, names):
+        """Concatenate per-rank lists of strings (gene names) in rank order."""
+        outs = [None] * self.world
+        tdist.all_gather_object(outs, list(names), group=self.group)
+        return [n for part in outs for n in part]
+
     def barrier(self):
         tdist.barrier(group=self.group)
 

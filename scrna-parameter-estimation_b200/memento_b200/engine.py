@@ -15,6 +15,7 @@ from .device import ENTRY_BYTES, NULL_TIMER
 N_TABLE_MAX = 16384      # largest multiplicity with a universal Poisson inversion table
 REGRESS_MIN_CTAS = 592   # mm_regress_asl: CTAs wanted per launch (4 per SM)
 SEG_INFO_BYTES = 48      # sizeof(SegInfo) in csrc/bootstrap.cu
+MIN_ACCEPT = 0.2         # Poissonised sampler: segments below this acceptance rate go to the direct / chain samplers
 _TABLES = {}             # per device: (offsets tensor, pool tensor)
 
 
@@ -112,77 +113,78 @@ def unique_bytes(tab, n_cells):
     return tab["nnz"] * 8 + n_cells * 1 + (tab["n_seg"] + 1) * 8 + total_U * ENTRY_BYTES + tab["n_seg"] * 4
 
 
-def wls_functional(device, covariate, treatment, weights, masks, one_sample, timer=NULL_TIMER, want_basis=False):
-    """masks: (n_mask, R) uint8 numpy.  Returns cmat (n_mask, T, R) on the device; with ``want_basis``
-    also the orthogonalised design (n_mask, R, P + T) and the squared norms (n_mask, P)."""
+def wls_functional(device, covariate, treatment, weights, masks, one_sample, timer=NULL_TIMER, want_basis=False,
+                   col_idx=None):
+    """One regression functional per *design* = validity mask + treatment columns.  masks: (n_mask, R) uint8 numpy;
+    ``col_idx`` (n_mask, T) int numpy: the treatment columns of every design (None: all columns of ``treatment``).
+    ``one_sample``: True forces the weighted-average functional; False lets the kernel decide per design, as the
+    reference decides per gene (hypothesis_test.py:262).  Returns (cmat (n_mask, T, R), one_flag (n_mask,) int32) on
+    the device; with ``want_basis`` also the orthogonalised design (n_mask, R, P + T), the squared norms
+    (n_mask, P) and the weights."""
     R, P = covariate.shape
-    T = treatment.shape[1]
+    T_full = treatment.shape[1]
+    T = T_full if col_idx is None else int(col_idx.shape[1])
     n_mask = masks.shape[0]
     cov_d = torch.as_tensor(np.ascontiguousarray(covariate, dtype=np.float64), device=device)
     tr_d = torch.as_tensor(np.ascontiguousarray(treatment, dtype=np.float64), device=device)
     w_d = torch.as_tensor(np.ascontiguousarray(weights, dtype=np.float64), device=device)
     m_d = torch.as_tensor(np.ascontiguousarray(masks, dtype=np.uint8), device=device)
+    ci_d = None if col_idx is None else torch.as_tensor(np.ascontiguousarray(col_idx, dtype=np.int32), device=device)
     scratch = torch.empty(max(1, n_mask * R * (P + T)), dtype=torch.float64, device=device)
     cmat = torch.empty(n_mask * T * R, dtype=torch.float64, device=device)
     znorm2 = torch.zeros(max(1, n_mask * P), dtype=torch.float64, device=device) if want_basis else None
+    one_flag = torch.empty(max(1, n_mask), dtype=torch.int32, device=device)
     ev = timer.start()
     _lib.call("mm_wls_functional", device, cov_d if P > 0 else None, tr_d, w_d, m_d, R, P, T, n_mask,
-              1 if one_sample else 0, scratch, cmat, znorm2)
+              1 if one_sample else 0, scratch, cmat, znorm2, T_full, ci_d, one_flag)
     timer.stop("wls_functional", ev)
     if want_basis:
-        return cmat.view(n_mask, T, R), scratch, znorm2, w_d
-    return cmat.view(n_mask, T, R)
+        return cmat.view(n_mask, T, R), one_flag, scratch, znorm2, w_d
+    return cmat.view(n_mask, T, R), one_flag
 
 
-def distinct_masks(good):
+def distinct_masks(good, extra=None):
     """Distinct rows of a (n_gene, R) 0/1 uint8 array and, per gene, the index of its row among them (the partition
     ``np.unique(good, axis=0, return_inverse=True)`` gives, in another order): rows are packed to bits and compared as
     byte strings -- np.unique(axis=0) takes 5-10 ms for 4000 x 16 flags, host time the device idles through at the
-    end of the last tile."""
-    packed = np.ascontiguousarray(np.packbits(good, axis=1))
+    end of the last tile.  ``extra`` (n_gene,) int: a second key component (the id of the gene's treatment-column
+    set); returns (first occurrence of every distinct key, inverse)."""
+    packed = np.packbits(good, axis=1)
+    if extra is not None:
+        packed = np.concatenate([packed, np.ascontiguousarray(extra, dtype=np.int32).view(np.uint8).reshape(-1, 4)],
+                                axis=1)
+    packed = np.ascontiguousarray(packed)
     _, first, inverse = np.unique(packed.view(np.dtype((np.void, packed.shape[1]))).ravel(), return_index=True,
                                   return_inverse=True)
-    return np.ascontiguousarray(good[first]), inverse.reshape(-1)
+    return first, inverse.reshape(-1)
 
 
-def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, treatment, weights, one_sample,
-                 approx, want_coef_rows, timer=NULL_TIMER, resample_rep=False, seed=0, gene_id=None,
-                 assignments=None, good_host=None):
-    """Shared tail of the 1D and 2D tests for one tile.  boot*: (n_gene*R, B+1) device tensors,
-    seg_good: (n_gene*R,) uint8 device.  Returns dict of host arrays (n_gene, n_stat, T) + coef rows."""
-    n_gene = seg_good.numel() // R
+def _regress_launch(device, boot0, boot1, seg_good, R, num_boot, approx, want_coef_rows, genes, key_id, cmat,
+                    resampled, basis, P, T, seed, gene_id, assignments, timer):
+    """One launch of mm_regress_asl / mm_regress_resampled over the tile genes ``genes`` (None: all, in order)."""
+    n_gene = seg_good.numel() // R if genes is None else int(genes.size)
     n_stat = 2 if boot1 is not None else 1
-    if good_host is not None:          # (pinned copy, event recorded behind it)
-        good_host[1].synchronize()
-        good_h = good_host[0].numpy().reshape(n_gene, R)
-    else:
-        good_h = seg_good.view(n_gene, R).cpu().numpy()
-    masks, inverse = distinct_masks(good_h)
-    use_resampled = resample_rep and not one_sample      # reference: the one-sample branch ignores it
-    if use_resampled:
-        cmat, zmat, znorm2, w_d = wls_functional(device, covariate, treatment, weights, masks, one_sample, timer,
-                                                 want_basis=True)
-    else:
-        cmat = wls_functional(device, covariate, treatment, weights, masks, one_sample, timer)
-    mask_id = torch.as_tensor(np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32), device=device)
     n_out = n_gene * n_stat * T
     out_coef = torch.empty(n_out, dtype=torch.float64, device=device)
     out_se = torch.empty(n_out, dtype=torch.float64, device=device)
     out_asl = torch.empty(n_out, dtype=torch.float64, device=device)
     out_ext = torch.empty(n_out, dtype=torch.int32, device=device)
     out_nn = torch.empty(n_out, dtype=torch.int32, device=device)
-    n_cols = num_boot if use_resampled else num_boot + 1
+    n_cols = num_boot if resampled else num_boot + 1
     coef_ws = torch.empty(n_out * n_cols, dtype=torch.float64, device=device) if want_coef_rows else None
+    mask_id = torch.as_tensor(np.ascontiguousarray(key_id, dtype=np.int32), device=device)
+    glist = None if genes is None else torch.as_tensor(np.ascontiguousarray(genes, dtype=np.int32), device=device)
     ev = timer.start()
-    if use_resampled:
+    if resampled:
+        zmat, znorm2, w_d = basis
         bad = torch.zeros(1, dtype=torch.int32, device=device)
         rep_a = it_a = None
         if assignments is not None:
             rep_a = torch.as_tensor(np.ascontiguousarray(assignments[0], dtype=np.int32), device=device)
             it_a = torch.as_tensor(np.ascontiguousarray(assignments[1], dtype=np.int32), device=device)
         _lib.call("mm_regress_resampled", device, boot0, boot1, seg_good, mask_id, zmat, znorm2, w_d, n_gene, R,
-                  covariate.shape[1], T, num_boot, 1 if approx else 0, seed, gene_id, rep_a, it_a, coef_ws,
-                  out_coef, out_se, out_asl, out_ext, out_nn, bad)
+                  P, T, num_boot, 1 if approx else 0, seed, gene_id, rep_a, it_a, coef_ws,
+                  out_coef, out_se, out_asl, out_ext, out_nn, bad, glist)
         if int(bad.item()) != 0:
             raise _lib.MementoCudaError("resample_rep: a bootstrap column is non-finite in a valid group; the "
                                         "device path does not drop columns in this mode")
@@ -192,13 +194,80 @@ def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, trea
         n_split = int(min(64, max(1, -(-REGRESS_MIN_CTAS // n_gene)))) if n_gene < REGRESS_MIN_CTAS else 1
         split_ws = torch.empty(n_gene * n_split * n_stat * T * 8, dtype=torch.float64, device=device) if n_split > 1 else None
         _lib.call("mm_regress_asl", device, boot0, boot1, seg_good, mask_id, cmat, n_gene, R, T, num_boot,
-                  1 if approx else 0, coef_ws, out_coef, out_se, out_asl, out_ext, out_nn, n_split, split_ws)
+                  1 if approx else 0, coef_ws, out_coef, out_se, out_asl, out_ext, out_nn, n_split, split_ws, glist)
     timer.stop("regress_asl", ev)
     shp = (n_gene, n_stat, T)
-    return {"coef": out_coef.view(shp), "se": out_se.view(shp), "asl": out_asl.view(shp),
+    return {"genes": genes, "T": T, "coef": out_coef.view(shp), "se": out_se.view(shp), "asl": out_asl.view(shp),
             "extreme": out_ext.view(shp), "n_null": out_nn.view(shp),
-            "coef_rows": coef_ws.view(n_gene, n_stat, T, n_cols) if want_coef_rows else None,
-            "n_masks": masks.shape[0]}
+            "coef_rows": coef_ws.view(n_gene, n_stat, T, n_cols) if want_coef_rows else None}
+
+
+def regress_tile(device, boot0, boot1, seg_good, R, T, num_boot, covariate, treatment, weights, one_sample,
+                 approx, want_coef_rows, timer=NULL_TIMER, resample_rep=False, seed=0, gene_id=None,
+                 assignments=None, good_host=None, colsets=None):
+    """Shared tail of the 1D and 2D tests for one tile.  boot*: (n_gene*R, B+1) device tensors,
+    seg_good: (n_gene*R,) uint8 device.  ``colsets`` = (set_id (n_gene,) int, [column index arrays]): the gene's
+    own treatment columns (treatment_for_gene, reference main.py:368-373, :392); None = every column for every
+    gene.  ``one_sample``: True forces the weighted-average branch, False decides per gene like the reference.
+
+    Genes are regressed in *buckets* of equal column count (and, under resample_rep, equal branch), one launch per
+    bucket; a design (validity mask + column set) is solved once and shared by its genes, so the cost is
+    proportional to the sum of the genes' own column counts.  Returns {"buckets": [bucket dicts of device tensors
+    (n_bucket_genes, n_stat, T_bucket) + "genes" (tile-local indices, None = all in order)], "n_masks"}; with a
+    single bucket over all genes its tensors are also at the top level."""
+    n_gene = seg_good.numel() // R
+    if good_host is not None:          # (pinned copy, event recorded behind it)
+        good_host[1].synchronize()
+        good_h = good_host[0].numpy().reshape(n_gene, R)
+    else:
+        good_h = seg_good.view(n_gene, R).cpu().numpy()
+    P = covariate.shape[1]
+    if colsets is None:
+        set_id, sets = None, [np.arange(treatment.shape[1], dtype=np.int32)]
+    else:
+        set_id, sets = np.asarray(colsets[0], dtype=np.int32), [np.asarray(c, dtype=np.int32) for c in colsets[1]]
+    first, inverse = distinct_masks(good_h, set_id)
+    key_masks = np.ascontiguousarray(good_h[first])
+    key_set = np.zeros(first.size, dtype=np.int32) if set_id is None else set_id[first]
+    set_T = np.array([c.size for c in sets], dtype=np.int64)
+    key_T = set_T[key_set]
+    gene_T = key_T[inverse]
+    buckets = []
+    for Tb in np.unique(key_T):
+        Tb = int(Tb)
+        if Tb == 0:
+            continue
+        keys = np.flatnonzero(key_T == Tb)
+        local = np.full(first.size, -1, dtype=np.int64)
+        local[keys] = np.arange(keys.size)
+        whole = keys.size == first.size
+        genes = None if whole else np.flatnonzero(gene_T == Tb)
+        key_id = local[inverse] if whole else local[inverse[genes]]
+        col_idx = None if colsets is None else np.stack([sets[k] for k in key_set[keys]])
+        if resample_rep and not one_sample:
+            cmat, one_flag, zmat, znorm2, w_d = wls_functional(device, covariate, treatment, weights, key_masks[keys],
+                                                               False, timer, want_basis=True, col_idx=col_idx)
+            # the reference's one-sample branch comes before (and ignores) resample_rep: hypothesis_test.py:262-265
+            flag = one_flag[:keys.size].cpu().numpy() != 0
+            gsel = np.arange(n_gene) if genes is None else genes
+            g_one = flag[key_id]
+            for is_one in ((False, True) if g_one.any() else (False,)):
+                sub = None if (not g_one.any() and genes is None) else gsel[g_one == is_one]
+                if sub is not None and sub.size == 0:
+                    continue
+                kid = key_id if sub is None else key_id[g_one == is_one]
+                buckets.append(_regress_launch(device, boot0, boot1, seg_good, R, num_boot, approx, want_coef_rows, sub,
+                                               kid, cmat, not is_one, (zmat, znorm2, w_d), P, Tb, seed, gene_id,
+                                               assignments, timer))
+        else:
+            cmat, _ = wls_functional(device, covariate, treatment, weights, key_masks[keys], one_sample, timer,
+                                     col_idx=col_idx)
+            buckets.append(_regress_launch(device, boot0, boot1, seg_good, R, num_boot, approx, want_coef_rows, genes,
+                                           key_id, cmat, False, None, P, Tb, seed, gene_id, None, timer))
+    res = {"buckets": buckets, "n_masks": int(first.size), "n_gene": n_gene}
+    if len(buckets) == 1 and buckets[0]["genes"] is None:
+        res.update({k: v for k, v in buckets[0].items() if k not in ("genes", "T")})
+    return res
 
 
 def bootstrap_tile(seg, design, tab, n_genes, estimator, num_boot, seed, seg_skip=None, gene_id=None,
@@ -284,7 +353,7 @@ def ht_1d_tile_boot(seg, design, cell_bin, gene_lo, n_genes, true_mean, true_rv,
 
 
 def ht_1d_tile_regress(ctx, design, R, covariate, treatment, num_boot, seed, approx, one_sample, want_coef_rows,
-                       timer=NULL_TIMER, resample_rep=False):
+                       timer=NULL_TIMER, resample_rep=False, colsets=None):
     """Second half of a gene tile: regression functional per validity mask -> coefficients, SE, ASL.  Waits for
     the tile's first half (it reads the validity flags on the host)."""
     dev = ctx["boot_mean"].device
@@ -307,7 +376,7 @@ def ht_1d_tile_regress(ctx, design, R, covariate, treatment, num_boot, seed, app
     return regress_tile(dev, ctx["boot_mean"], ctx["boot_var"], ctx["seg_good"], R, T, num_boot, covariate, treatment,
                         design.n_cells_host.astype(np.float64), one_sample, approx, want_coef_rows, timer,
                         resample_rep=resample_rep, seed=seed, gene_id=ctx["gene_id"],
-                        good_host=(ctx["good_host"], ctx["good_event"]))
+                        good_host=(ctx["good_host"], ctx["good_event"]), colsets=colsets)
 
 
 def finalize_stats(stats, num_boot, n_cells):

@@ -41,7 +41,8 @@ class DeviceState:
         self.timer = NULL_TIMER
         self.h2d_bytes = 0
         self.codes = None        # host: group code of every cell (original order)
-        self.gene_index = None   # host: original column of every current gene
+        self.gene_index = None   # host: ORIGINAL column (of the matrix given to setup_memento) of every current gene
+        self.x_cols = None       # host: column of every current gene in the adata.X captured by create_groups
         self.bin_inv_sf = None
         self.n_bins_present = None
         self.cell_bin_host = None
@@ -261,13 +262,29 @@ def create_groups(adata, label_columns, label_delimiter="^", inplace=True):
 
     if st.csr is not None:      # hand-written counting transposition of the uploaded CSR (csrc/relayout.cu)
         st.seg = SegMatrix.from_csr_grouped(st.csr, order, st.group_start, timer=st.timer)
-    else:                       # create_groups called again on the same object: regroup the gene-sorted matrix
-        st.seg = st.seg_all.regroup(to_device(codes, st.device, np.int32), R, to_device(rank, st.device, np.int32))
+        st.gene_index = np.arange(adata.shape[1])
+    else:
+        # create_groups called again on the same object: regroup the gene-sorted matrix of all cells.  It still has
+        # every ORIGINAL gene column, while adata may have been column-filtered by compute_1d_moments since (the
+        # reference regroups the filtered adata.X, main.py:128): keep the device matrix in step with adata.var
+        if st.seg_all is None:
+            raise RuntimeError("create_groups: the all-cells matrix was released (host-staged mode); "
+                               "call setup_memento again before regrouping")
+        base = st.seg_all
+        if st.gene_index is not None and (st.gene_index.size != base.G or
+                                          not np.array_equal(st.gene_index, np.arange(base.G))):
+            base = base.select_genes(st.gene_index)
+        assert base.G == adata.shape[1], "device matrix and adata.var disagree"
+        st.seg = base.regroup(to_device(codes, st.device, np.int32), R, to_device(rank, st.device, np.int32))
     st.csr = None
-    st.gene_index = np.arange(adata.shape[1])
+    st.design = None            # group sizes / q / trend belong to the previous grouping
+    for key in ("size_factor", "approx_size_factor", "all_approx_size_factor", "1d_moments", "mv_regressor"):
+        mem.pop(key, None)      # per-group state of the previous grouping
     X = adata.X
-    mem["group_cells"] = {g: LazyGroupCells(X, order[st.group_start[r]:st.group_start[r + 1]], st.gene_index)
+    x_cols = np.arange(adata.shape[1])      # columns of THIS adata.X (already filtered when called again)
+    mem["group_cells"] = {g: LazyGroupCells(X, order[st.group_start[r]:st.group_start[r + 1]], x_cols)
                           for r, g in enumerate(mem["groups"])}
+    st.x_cols = x_cols
     q_sum = np.bincount(codes, weights=mem["q"], minlength=R)
     mem["group_q"] = {g: q_sum[r] / counts[r] for r, g in enumerate(mem["groups"])}
     if not inplace:
@@ -331,8 +348,9 @@ def compute_1d_moments(adata, inplace=True, min_perc_group=0.7, filter_genes=Tru
         keep = np.flatnonzero(overall)
         st.seg = st.seg.select_genes(keep)
         st.gene_index = st.gene_index[keep]
+        st.x_cols = st.x_cols[keep]
         mean, var, rv_filter = mean[keep], var[keep], rv_filter[keep]
-        mem["group_cells"] = {g: mem["group_cells"][g].with_genes(st.gene_index) for g in groups}
+        mem["group_cells"] = {g: mem["group_cells"][g].with_genes(st.x_cols) for g in groups}
         adata._inplace_subset_var(overall)
     mem["gene_rv_filter"] = {g: rv_filter[:, r].copy() for r, g in enumerate(groups)}
 
@@ -359,7 +377,8 @@ def compute_1d_moments(adata, inplace=True, min_perc_group=0.7, filter_genes=Tru
         keep = np.flatnonzero(given)
         st.seg = st.seg.select_genes(keep)
         st.gene_index = st.gene_index[keep]
-        mem["group_cells"] = {g: mem["group_cells"][g].with_genes(st.gene_index) for g in groups}
+        st.x_cols = st.x_cols[keep]
+        mem["group_cells"] = {g: mem["group_cells"][g].with_genes(st.x_cols) for g in groups}
         mem["1d_moments"] = {g: [mem["1d_moments"][g][k][given] for k in range(3)] for g in groups}
         adata._inplace_subset_var(given)
     _refresh_design(adata)
@@ -377,19 +396,44 @@ def _refresh_design(adata):
 
 
 # --------------------------------------------------------------------------- ht_1d_moments
+def _treatment_column_sets(adata, treatment, treatment_for_gene):
+    """Per-gene treatment columns (reference main.py:368-373, :392: ``treatment[treatment_for_gene[gene]]``) as
+    (set_id (G,), [int32 column arrays], T_gene (G,), number of result slots).  Genes that share a column list share
+    a set; the result-array length is the reference's: the sum over ALL entries of the dict (main.py:371-373)."""
+    G = adata.shape[1]
+    if treatment_for_gene is None:
+        T = treatment.shape[1]
+        return None, np.full(G, T, dtype=np.int64), T * G
+    cols = {c: i for i, c in enumerate(treatment.columns)}
+    ids, sets = {}, []
+    set_id = np.empty(G, dtype=np.int32)
+    for i, gname in enumerate(adata.var.index):
+        key = tuple(cols[c] for c in treatment_for_gene[gname])
+        k = ids.get(key)
+        if k is None:
+            k = ids[key] = len(sets)
+            sets.append(np.asarray(key, dtype=np.int32))
+        set_id[i] = k
+    t_gene = np.array([c.size for c in sets], dtype=np.int64)[set_id]
+    return (set_id, sets), t_gene, int(sum(len(v) for v in treatment_for_gene.values()))
+
+
 def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=True, num_boot=10000,
                   verbose=1, num_cpus=1, seed=0, workspace_bytes=None, replay=None, sampler="poisson",
-                  **kwargs):
+                  gather=True, **kwargs):
     """Hypothesis test for the mean and the residual variance.  reference: main.py:341-415.
 
     ``num_cpus`` / ``verbose`` are accepted and ignored (the GPU grid replaces the process pool).
     Test keywords as in the reference: ``resampling='bootstrap'`` (only mode on the device path),
-    ``approx``, ``resample_rep``.  Build-only: ``seed`` (Philox key), ``workspace_bytes`` (bootstrap rows of one
+    ``approx``, ``resample_rep``.  ``treatment_for_gene`` {gene: [treatment columns]} as in the reference: every
+    gene is regressed on its own columns only (cost proportional to the columns used, not to ``treatment.shape[1]``).
+    Build-only: ``seed`` (Philox key), ``workspace_bytes`` (bootstrap rows of one
     gene tile; two tiles are alive at a time; default: 24 GB or a sixth of the free device memory, whichever is less),
     ``replay`` (deterministic parity mode: host-supplied unique tables, resample counts and
     imputation sources for every (gene, group); see engine.ht_1d_replay), ``sampler`` ("poisson":
     Poissonised exact multinomial with the conditional-binomial chain as per-segment fallback;
-    "chain": the chain everywhere)."""
+    "chain": the chain everywhere), ``gather`` (gene-sharded runs only: all-gather every rank's results over NCCL
+    into ``uns['memento']['1d_ht_all']`` -- the reference assembles all genes in one place, main.py:399-412)."""
     if not inplace:
         adata = adata.copy()
     resampling = kwargs.pop("resampling", "bootstrap")
@@ -409,10 +453,6 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
             st.workspace_default = engine.default_workspace(st.device)
         workspace_bytes = st.workspace_default
     genes_per_tile = engine.tile_plan_groups(R, num_boot, workspace_bytes)
-    if os.environ.get("MM_WORKSPACE_GB"):           # tuning hook
-        genes_per_tile = engine.tile_plan_groups(R, num_boot, int(float(os.environ["MM_WORKSPACE_GB"]) * (1 << 30)))
-    if G > genes_per_tile and os.environ.get("MM_TILE_BALANCE", "0") != "0":      # equal tiles instead of full ones + a sliver
-        genes_per_tile = -(-G // -(-G // genes_per_tile))
     # host-staged matrix (end-to-end mode): the second and later gene tiles are uploaded behind the first one's
     # slice, under the first tile's kernels
     st.ensure_resident(split_gene=genes_per_tile if (replay is None and G > genes_per_tile) else None)
@@ -421,25 +461,39 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         _refresh_design(adata)
     cov = np.ascontiguousarray(covariate.values, dtype=np.float64)
     tr_all = np.ascontiguousarray(treatment.values, dtype=np.float64)
-    T = tr_all.shape[1]
-    one_sample = bool((tr_all == 1).mean() == 1)                              # hypothesis_test.py:262
+    colsets, t_gene, num_tests = _treatment_column_sets(adata, treatment, treatment_for_gene)
+    out_ptr = np.concatenate([[0], np.cumsum(t_gene)]).astype(np.int64)       # gene-major, treatment-minor (:399-404)
+    # the one-sample branch (hypothesis_test.py:262) is decided per gene on the device, from the gene's own columns
+    # and valid groups; only a treatment frame of ones forces it up front (it also switches resample_rep off)
+    one_sample = bool((tr_all == 1).mean() == 1)
     true_mean = np.stack([mem["1d_moments"][g][0] for g in groups], axis=1)   # (G, R)
     true_rv = np.stack([mem["1d_moments"][g][2] for g in groups], axis=1)
 
-    out = {k: np.full((G, 2, T), np.nan) for k in ("coef", "se", "asl")}
+    out = {k: np.full((2, num_tests), np.nan) for k in ("coef", "se", "asl")}
     stats_acc = {"want_modes": bool(getattr(st, "count_modes", False))}
     if sampler not in ("poisson", "chain"):
         raise ValueError("sampler must be 'poisson' or 'chain'")
+
+    def store(lo, bucket):          # bucket tensors (n, 2, T) -> the flat result arrays
+        genes = np.arange(lo, lo + bucket["coef"].shape[0]) if bucket["genes"] is None else lo + bucket["genes"]
+        pos = (out_ptr[genes][:, None] + np.arange(bucket["T"])[None, :]).reshape(-1)
+        for k in out:
+            v = bucket[k].cpu().numpy()
+            out[k][0, pos] = v[:, 0, :].reshape(-1)
+            out[k][1, pos] = v[:, 1, :].reshape(-1)
+
     if replay is not None:
+        if colsets is not None:
+            raise NotImplementedError("replay mode takes one treatment frame for all genes")
         dh = {"n_cells": np.diff(st.group_start), "q": [mem["group_q"][g] for g in groups],
               "mv_fit": np.stack([mem["mv_regressor"][g] for g in groups])}
         res = engine.ht_1d_replay(st.device, R, replay, dh, true_mean, true_rv, cov, tr_all, num_boot, estimator,
                                   approx, one_sample, want_coef_rows=not approx, timer=st.timer,
                                   resample_rep=resample_rep)
-        if not approx:
-            gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
-        for k in out:
-            out[k][:] = res[k].cpu().numpy()
+        for bucket in res["buckets"]:
+            if not approx:
+                gev.refine_tail_asl(bucket, st.device, st.timer, stats_acc)
+            store(0, bucket)
         gev.count_tail_tests(stats_acc)
         genes_per_tile = G + 1
         st.last_replay = res
@@ -459,7 +513,7 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         return engine.ht_1d_tile_boot(st.seg, st.design, st.cell_bin, lo, n, true_mean[lo:lo + n], true_rv[lo:lo + n],
                                       num_boot, estimator, seed, timer=st.timer, stats=stats_acc,
                                       gene_id=gene_id[lo:lo + n], sampler=sampler,
-                                      min_accept=getattr(st, "min_accept", 0.2))
+                                      min_accept=getattr(st, "min_accept", engine.MIN_ACCEPT))
 
     ctx = first_half(*tiles[0]) if tiles else None
     st.upload_tail()            # split upload: the later tiles' slice goes out under the first tile's kernels
@@ -470,18 +524,23 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
             main_stream.wait_event(st.tail_event)
             st.tail_event = None
         nxt = first_half(*tiles[i + 1]) if i + 1 < len(tiles) else None
+        tile_sets = None if colsets is None else (colsets[0][lo:lo + n], colsets[1])
         res = engine.ht_1d_tile_regress(ctx, st.design, R, cov, tr_all, num_boot, seed, approx, one_sample,
-                                        want_coef_rows=not approx, timer=st.timer, resample_rep=resample_rep)
+                                        want_coef_rows=not approx, timer=st.timer, resample_rep=resample_rep,
+                                        colsets=tile_sets)
         ctx = nxt
         if side is not None:
             side = st.side_streams[i & 1]       # consecutive tiles' GEV stages (latency-bound) may overlap each other
             side.wait_stream(main_stream)
             with torch.cuda.stream(side):
-                gev.refine_tail_asl(res, st.device, st.timer, stats_acc)
-            for key in ("coef_rows", "asl", "extreme"):
-                res[key].record_stream(side)
-            del res["coef_rows"]            # the allocator keeps the block until the side stream is done with it
-        pending.append((lo, n, {k: res[k] for k in out}))
+                for bucket in res["buckets"]:
+                    gev.refine_tail_asl(bucket, st.device, st.timer, stats_acc)
+            for bucket in res["buckets"]:
+                for key in ("coef_rows", "asl", "extreme"):
+                    bucket[key].record_stream(side)
+                del bucket["coef_rows"]     # the allocator keeps the block until the side stream is done with it
+        pending.append((lo, [{k: b[k] for k in ("genes", "T", "coef", "se", "asl")} for b in res["buckets"]]))
+        res = None
     if side is not None:
         for sd in st.side_streams:
             main_stream.wait_stream(sd)
@@ -489,30 +548,45 @@ def ht_1d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     if st.tail_event is not None:
         main_stream.wait_event(st.tail_event)
         st.tail_event = None
-    for lo, n, res in pending:
-        for k in out:
-            out[k][lo:lo + n] = res[k].cpu().numpy()
+    for lo, buckets in pending:
+        for bucket in buckets:
+            store(lo, bucket)
     gev.count_tail_tests(stats_acc)
     engine.finalize_stats(stats_acc, num_boot, st.design.n_cells_total)
     st.last_stats = stats_acc
 
-    # flat gene-major / treatment-minor outputs (main.py:399-404)
-    if treatment_for_gene is None:
-        sel = None
-        flat = {k: out[k].transpose(1, 0, 2).reshape(2, G * T) for k in out}
-    else:
-        cols = {c: i for i, c in enumerate(treatment.columns)}
-        sel = [np.array([cols[c] for c in treatment_for_gene[gname]], dtype=int) for gname in adata.var.index]
-        flat = {k: np.stack([np.concatenate([out[k][i, s, sel[i]] for i in range(G)]) for s in range(2)])
-                for k in out}
     ht = mem["1d_ht"] = {}
     if treatment_for_gene is not None:
         ht["treatment_for_gene"] = treatment_for_gene
     ht["treatment"], ht["covariate"] = treatment, covariate
-    ht["mean_coef"], ht["mean_se"], ht["mean_asl"] = flat["coef"][0], flat["se"][0], flat["asl"][0]
-    ht["var_coef"], ht["var_se"], ht["var_asl"] = flat["coef"][1], flat["se"][1], flat["asl"][1]
+    ht["mean_coef"], ht["mean_se"], ht["mean_asl"] = out["coef"][0], out["se"][0], out["asl"][0]
+    ht["var_coef"], ht["var_se"], ht["var_asl"] = out["coef"][1], out["se"][1], out["asl"][1]
+    if st.dist is not None and gather:
+        _gather_1d_ht(adata, t_gene)
     if not inplace:
         return adata
+
+
+_HT_KEYS = ("mean_coef", "mean_se", "mean_asl", "var_coef", "var_se", "var_asl")
+
+
+def _gather_1d_ht(adata, t_gene):
+    """Gene-sharded run: every rank gets the results of all ranks' genes, in global gene order (rank blocks are
+    contiguous gene ranges), as ``uns['memento']['1d_ht_all']`` = {"gene": names, "n_tests": per-gene test counts,
+    the six flat arrays of ``1d_ht``}.  One all-gather of 6 * (tests of the rank) doubles over NCCL / NVLink; the
+    rank's own ``1d_ht`` keeps matching its ``adata.var``."""
+    mem = adata.uns["memento"]
+    st = _state(adata)
+    ht = mem["1d_ht"]
+    n_local = int(t_gene.sum())
+    packed = np.stack([ht[k][:n_local] for k in _HT_KEYS], axis=1)                  # (tests, 6)
+    allv, _ = st.dist.all_gather_concat(packed)
+    counts, _ = st.dist.all_gather_concat(t_gene.astype(np.int64))
+    names = st.dist.all_gather_names(adata.var.index.tolist())
+    res = {"gene": names, "n_tests": counts}
+    for j, k in enumerate(_HT_KEYS):
+        res[k] = np.ascontiguousarray(allv[:, j])
+    mem["1d_ht_all"] = res
 
 
 # --------------------------------------------------------------------------- 2D

@@ -1,0 +1,285 @@
+"""GPU tests of the call patterns round 1 left untested ("What's weak" 3): ``treatment_for_gene``
+(the eQTL pattern of reference analysis/lupus/run_memento.py:99-109, main.py:368-373, :392), several treatment
+columns (T = 3, T = 6 > the kernel's 4-column pass), ``estimator_type='mean_only'``, ``inplace=False``,
+``filter_genes=False``, the per-gene one-sample decision (hypothesis_test.py:262), regrouping after a gene filter,
+and the input validation of the count matrix.  Deterministic quantities (coefficients = column 0 of the bootstrap
+arrays) are held to 1e-8 against the oracle; Monte-Carlo quantities by ratio / rank concordance; and plumbing
+identities (same seed => same replicates) to round-off.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+import scipy.stats as stats
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+import memento_b200 as memento            # noqa: E402
+from memento_b200 import synth            # noqa: E402
+from oracle import pipeline as o_pipe     # noqa: E402
+
+LABELS = ["stim", "cell", "donor"]
+HT_KEYS = ("mean_coef", "mean_se", "mean_asl", "var_coef", "var_se", "var_asl")
+
+
+def _dataset(estimator_type="hyper_relative", seed=5):
+    ad = synth.make_counts(2400, 120, n_conditions=2, n_types=2, q=0.07, seed=seed, n_donors=4)
+    ad.X = ad.X.astype(np.float64)       # the reference then computes in float64 throughout
+    return ad
+
+
+def _prepare(mod, ad, estimator_type="hyper_relative", **kw):
+    mod.setup_memento(ad, "q", estimator_type=estimator_type)
+    mod.create_groups(ad, LABELS)
+    mod.compute_1d_moments(ad, min_perc_group=0.7, **kw)
+    return ad
+
+
+def _designs(groups, n_extra=9, seed=1):
+    """covariate = cell-type dummy; treatment = stim indicator + ``n_extra`` genotype-like columns (0/1/2 per
+    donor), as in the eQTL runs."""
+    rows = [g.split("^")[1:] for g in groups]
+    df = pd.DataFrame(rows, columns=LABELS, index=groups)
+    cov = pd.get_dummies(df[["cell"]], drop_first=True).astype(float)
+    rng = np.random.default_rng(seed)
+    tr = pd.DataFrame({"stim": (df["stim"] == "stim").astype(float)}, index=groups)
+    donors = sorted(df["donor"].unique())
+    for k in range(n_extra):
+        geno = dict(zip(donors, rng.permutation(np.arange(len(donors)) % 3)))
+        tr["snp%d" % k] = df["donor"].map(geno).astype(float)
+    return cov, tr
+
+
+@pytest.fixture(scope="module")
+def pair():
+    g = _prepare(memento, _dataset())
+    o = _prepare(o_pipe, _dataset())
+    assert g.var.index.tolist() == o.var.index.tolist()
+    return g, o
+
+
+def _gene_columns(ad, tr, seed=2):
+    rng = np.random.default_rng(seed)
+    cols = tr.columns.tolist()
+    return {g: [cols[j] for j in sorted(rng.choice(len(cols), size=int(rng.integers(1, 4)), replace=False))]
+            for g in ad.var.index}
+
+
+# ----------------------------------------------------------------------------- several treatment columns
+@pytest.mark.parametrize("T", [3, 6])
+def test_multi_treatment_vs_oracle(pair, T):
+    g, o = pair
+    cov, tr = _designs(g.uns["memento"]["groups"])
+    tr = tr.iloc[:, :T]
+    memento.ht_1d_moments(g, cov, tr, num_boot=1500, resampling="bootstrap", approx=True, seed=4)
+    np.random.seed(0)
+    o_pipe.ht_1d_moments(o, cov, tr, num_boot=1500, num_cpus=1, resampling="bootstrap", approx=True)
+    hg, ho = g.uns["memento"]["1d_ht"], o.uns["memento"]["1d_ht"]
+    n = g.shape[1]
+    assert hg["mean_coef"].shape == (n * T,)
+    assert_close(hg["mean_coef"], ho["mean_coef"], 1e-8, atol=1e-10, what="mean_coef T=%d" % T)
+    assert_close(hg["var_coef"], ho["var_coef"], 1e-7, atol=1e-9, what="var_coef T=%d" % T)
+    ok = np.isfinite(ho["mean_se"])
+    ratio = hg["mean_se"][ok] / ho["mean_se"][ok]
+    assert 0.9 < np.median(ratio) < 1.1 and np.percentile(np.abs(np.log(ratio)), 95) < 0.25
+    rho = stats.spearmanr(hg["mean_asl"][ok], ho["mean_asl"][ok]).statistic
+    assert rho > 0.95, rho
+    # marginal slopes: column t of a T-column run == the single-column run of that column (same seed, same replicates)
+    full = {k: hg[k].copy() for k in HT_KEYS}
+    for t in (0, T - 1):
+        memento.ht_1d_moments(g, cov, tr.iloc[:, [t]], num_boot=1500, resampling="bootstrap", approx=True, seed=4)
+        one = g.uns["memento"]["1d_ht"]
+        for k in HT_KEYS:
+            assert_close(full[k].reshape(n, T)[:, t], one[k], 1e-11, atol=1e-13, what="%s column %d" % (k, t))
+
+
+# ----------------------------------------------------------------------------- treatment_for_gene
+@pytest.mark.parametrize("kw", [dict(approx=True), dict(approx=True, resample_rep=True), dict()])
+def test_treatment_for_gene_equals_dense_runs(pair, kw):
+    """Every gene regressed on its own columns only: must equal, gene by gene, the dense run on exactly those
+    columns (same seed => same bootstrap replicates), and the flat layout must be the reference's (gene-major,
+    treatment-minor, main.py:399-404)."""
+    g, _ = pair
+    cov, tr = _designs(g.uns["memento"]["groups"])
+    tfg = _gene_columns(g, tr)
+    memento.ht_1d_moments(g, cov, tr, treatment_for_gene=tfg, num_boot=800, resampling="bootstrap", seed=9, **kw)
+    ht = {k: g.uns["memento"]["1d_ht"][k].copy() for k in HT_KEYS}
+    assert g.uns["memento"]["1d_ht"]["treatment_for_gene"] is tfg
+    names = g.var.index.tolist()
+    nt = np.array([len(tfg[n]) for n in names])
+    ptr = np.concatenate([[0], np.cumsum(nt)])
+    assert ht["mean_coef"].shape == (ptr[-1],)
+    for cols in sorted({tuple(v) for v in tfg.values()})[:6]:
+        memento.ht_1d_moments(g, cov, tr[list(cols)], num_boot=800, resampling="bootstrap", seed=9, **kw)
+        dense = g.uns["memento"]["1d_ht"]
+        for i, n in enumerate(names):
+            if tuple(tfg[n]) != cols:
+                continue
+            for k in HT_KEYS:
+                assert_close(ht[k][ptr[i]:ptr[i + 1]], dense[k][i * len(cols):(i + 1) * len(cols)], 1e-11, atol=1e-13,
+                             what="%s gene %s cols %s" % (k, n, cols))
+
+
+def test_treatment_for_gene_vs_oracle(pair):
+    g, o = pair
+    cov, tr = _designs(g.uns["memento"]["groups"])
+    tfg = _gene_columns(g, tr, seed=3)
+    memento.ht_1d_moments(g, cov, tr, treatment_for_gene=tfg, num_boot=1500, resampling="bootstrap", approx=True, seed=2)
+    np.random.seed(0)
+    o_pipe.ht_1d_moments(o, cov, tr, treatment_for_gene=tfg, num_boot=1500, num_cpus=1, resampling="bootstrap",
+                         approx=True)
+    hg, ho = g.uns["memento"]["1d_ht"], o.uns["memento"]["1d_ht"]
+    assert hg["mean_coef"].shape == ho["mean_coef"].shape
+    assert_close(hg["mean_coef"], ho["mean_coef"], 1e-8, atol=1e-10, what="mean_coef")
+    assert_close(hg["var_coef"], ho["var_coef"], 1e-7, atol=1e-9, what="var_coef")
+    ok = np.isfinite(ho["mean_asl"])
+    assert stats.spearmanr(hg["mean_asl"][ok], ho["mean_asl"][ok]).statistic > 0.95
+    ratio = hg["var_se"][ok] / ho["var_se"][ok]
+    assert 0.9 < np.median(ratio) < 1.1
+
+
+def test_one_sample_is_decided_per_gene(pair):
+    """reference hypothesis_test.py:262: a gene whose OWN treatment columns are all ones gets the Nc-weighted
+    average over groups, whatever the other columns of the frame hold."""
+    g, o = pair
+    cov, tr = _designs(g.uns["memento"]["groups"], n_extra=2)
+    tr = tr.copy()
+    tr["ones"] = 1.0
+    names = g.var.index.tolist()
+    tfg = {n: (["ones"] if i % 3 == 0 else ["stim"]) for i, n in enumerate(names)}
+    for kw in (dict(approx=True), dict(approx=True, resample_rep=True)):
+        memento.ht_1d_moments(g, cov, tr, treatment_for_gene=tfg, num_boot=600, resampling="bootstrap", seed=1, **kw)
+        np.random.seed(0)
+        o_pipe.ht_1d_moments(o, cov, tr, treatment_for_gene=tfg, num_boot=600, num_cpus=1, resampling="bootstrap", **kw)
+        hg, ho = g.uns["memento"]["1d_ht"], o.uns["memento"]["1d_ht"]
+        assert_close(hg["mean_coef"], ho["mean_coef"], 1e-8, atol=1e-10, what="mean_coef %s" % kw)
+        one = np.array([i % 3 == 0 for i in range(len(names))])
+        ok = np.isfinite(ho["mean_se"]) & one
+        ratio = hg["mean_se"][ok] / ho["mean_se"][ok]
+        assert 0.85 < np.median(ratio) < 1.15
+
+
+# ----------------------------------------------------------------------------- mean_only estimator
+def test_mean_only_estimator_vs_oracle():
+    """estimator_type='mean_only' (reference estimator.py:188-204, genetics tutorial): mean + 1 and a constant 10."""
+    g = _prepare(memento, _dataset(), "mean_only")
+    o = _prepare(o_pipe, _dataset(), "mean_only")
+    assert g.var.index.tolist() == o.var.index.tolist()
+    for grp in g.uns["memento"]["groups"]:
+        for k in range(3):
+            assert_close(g.uns["memento"]["1d_moments"][grp][k], o.uns["memento"]["1d_moments"][grp][k], 1e-9,
+                         what="1d_moments[%d]" % k)
+    cov, tr = _designs(g.uns["memento"]["groups"], n_extra=0)
+    memento.ht_1d_moments(g, cov, tr, num_boot=2000, resampling="bootstrap", approx=True, seed=3)
+    np.random.seed(0)
+    o_pipe.ht_1d_moments(o, cov, tr, num_boot=2000, num_cpus=1, resampling="bootstrap", approx=True)
+    hg, ho = g.uns["memento"]["1d_ht"], o.uns["memento"]["1d_ht"]
+    assert_close(hg["mean_coef"], ho["mean_coef"], 1e-8, atol=1e-10, what="mean_coef")
+    ok = np.isfinite(ho["mean_asl"])
+    assert ok.sum() > 50
+    ratio = hg["mean_se"][ok] / ho["mean_se"][ok]
+    assert 0.9 < np.median(ratio) < 1.1
+    assert stats.spearmanr(hg["mean_asl"][ok], ho["mean_asl"][ok]).statistic > 0.95
+    # the variance statistic is a constant under this estimator: its coefficient is 0 and its null is degenerate
+    assert np.array_equal(np.isnan(hg["var_asl"]), np.isnan(ho["var_asl"]))
+
+
+# ----------------------------------------------------------------------------- inplace / filter_genes
+def test_inplace_false_returns_copies_and_leaves_the_input_alone():
+    ad = _dataset()
+    memento.setup_memento(ad, "q")
+    ad2 = memento.create_groups(ad, LABELS, inplace=False)
+    assert "groups" not in ad.uns["memento"] and "groups" in ad2.uns["memento"]
+    n_before = ad2.shape[1]
+    ad3 = memento.compute_1d_moments(ad2, inplace=False, min_perc_group=0.7)
+    assert "1d_moments" not in ad2.uns["memento"] and ad2.shape[1] == n_before
+    assert ad3.shape[1] < n_before
+    cov, tr = _designs(ad3.uns["memento"]["groups"], n_extra=0)
+    ad4 = memento.ht_1d_moments(ad3, cov, tr, inplace=False, num_boot=300, resampling="bootstrap", approx=True, seed=1)
+    assert "1d_ht" not in ad3.uns["memento"] and "1d_ht" in ad4.uns["memento"]
+    # the copies give what the in-place calls give
+    ref = _prepare(memento, _dataset())
+    memento.ht_1d_moments(ref, cov, tr, num_boot=300, resampling="bootstrap", approx=True, seed=1)
+    for k in HT_KEYS:
+        assert_close(ad4.uns["memento"]["1d_ht"][k], ref.uns["memento"]["1d_ht"][k], 1e-12, atol=1e-14, what=k)
+
+
+def test_filter_genes_false_vs_oracle():
+    g = _prepare(memento, _dataset(), filter_genes=False)
+    o = _prepare(o_pipe, _dataset(), filter_genes=False)
+    assert g.shape[1] == 120 and o.shape[1] == 120
+    assert np.array_equal(g.uns["memento"]["overall_gene_filter"], o.uns["memento"]["overall_gene_filter"])
+    for grp in g.uns["memento"]["groups"]:
+        for k in range(3):
+            assert_close(g.uns["memento"]["1d_moments"][grp][k], o.uns["memento"]["1d_moments"][grp][k], 1e-9,
+                         atol=1e-14, what="1d_moments[%d]" % k)
+    cov, tr = _designs(g.uns["memento"]["groups"], n_extra=0)
+    memento.ht_1d_moments(g, cov, tr, num_boot=500, resampling="bootstrap", approx=True, seed=3)
+    np.random.seed(0)
+    o_pipe.ht_1d_moments(o, cov, tr, num_boot=500, num_cpus=1, resampling="bootstrap", approx=True)
+    hg, ho = g.uns["memento"]["1d_ht"], o.uns["memento"]["1d_ht"]
+    # unfiltered genes include all-zero / invalid ones: same NaN pattern, same coefficients
+    assert_close(hg["mean_coef"], ho["mean_coef"], 1e-8, atol=1e-10, what="mean_coef")
+
+
+# ----------------------------------------------------------------------------- regrouping after a gene filter
+def test_create_groups_again_after_gene_filter():
+    """A second create_groups on an AnnData that compute_1d_moments has column-filtered must regroup the FILTERED
+    genes (the reference rebuilds group_cells from the filtered adata.X, main.py:128)."""
+    ad = _prepare(memento, _dataset())
+    n_kept = ad.shape[1]
+    assert n_kept < 120
+    memento.create_groups(ad, ["stim", "cell"])
+    memento.compute_1d_moments(ad, min_perc_group=0.7, filter_genes=False)
+    fresh = _dataset()
+    keep = np.isin(fresh.var.index.values, ad.var.index.values)
+    o = _dataset()
+    o_pipe.setup_memento(o, "q")
+    o._inplace_subset_var(keep)
+    o_pipe.create_groups(o, ["stim", "cell"])
+    o_pipe.compute_1d_moments(o, min_perc_group=0.7, filter_genes=False)
+    assert ad.shape[1] == n_kept == o.shape[1]
+    assert ad.uns["memento"]["groups"] == o.uns["memento"]["groups"]
+    for grp in ad.uns["memento"]["groups"]:
+        assert ad.uns["memento"]["group_cells"][grp].shape == o.uns["memento"]["group_cells"][grp].shape
+        for k in range(2):
+            assert_close(ad.uns["memento"]["1d_moments"][grp][k], o.uns["memento"]["1d_moments"][grp][k], 1e-9,
+                         atol=1e-14, what="1d_moments[%d] %s" % (k, grp))
+    cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+    memento.ht_1d_moments(ad, cov, tr, num_boot=300, resampling="bootstrap", approx=True, seed=1)
+    assert np.isfinite(ad.uns["memento"]["1d_ht"]["mean_coef"]).sum() > 0.8 * n_kept
+
+
+# ----------------------------------------------------------------------------- input validation
+@pytest.mark.parametrize("bad,what", [(0.5, "non-integer"), (-1.0, "negative"), (float(1 << 24), "2\\*\\*24")])
+def test_count_matrix_is_validated(bad, what):
+    ad = synth.make_counts(200, 30, seed=1)
+    X = ad.X.copy().astype(np.float64)
+    X.data[7] = bad
+    ad.X = sp.csr_matrix(X)
+    with pytest.raises(ValueError, match=what):
+        memento.setup_memento(ad, "q")
+
+
+def test_unsorted_rows_take_the_generic_relayout():
+    """Rows whose column indices do not ascend are legal CSR: the re-layout must not take its tiled path."""
+    ad = synth.make_counts(300, 40, n_types=2, seed=2)
+    ref = ad.copy()
+    X = ad.X.copy()
+    for r in range(0, X.shape[0], 3):       # reverse every third row
+        lo, hi = X.indptr[r], X.indptr[r + 1]
+        X.indices[lo:hi] = X.indices[lo:hi][::-1].copy()
+        X.data[lo:hi] = X.data[lo:hi][::-1].copy()
+    X = sp.csr_matrix((X.data, X.indices, X.indptr), shape=X.shape)
+    assert not X.has_sorted_indices
+    ad.X = X
+    for a in (ad, ref):
+        memento.setup_memento(a, "q")
+        memento.create_groups(a, ["stim", "cell"])
+        memento.compute_1d_moments(a, min_perc_group=0.7)
+    for grp in ref.uns["memento"]["groups"]:
+        for k in range(3):
+            assert_close(ad.uns["memento"]["1d_moments"][grp][k], ref.uns["memento"]["1d_moments"][grp][k], 1e-12,
+                         what="1d_moments[%d]" % k)

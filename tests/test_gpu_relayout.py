@@ -23,13 +23,37 @@ def _case(n_cells, n_genes, n_groups, density, seed, empty_groups=()):
     return X, codes
 
 
-@pytest.mark.parametrize("shape", [(700, 90, 5, 0.2, ()), (5000, 300, 16, 0.05, (3, 15)), (64, 10, 1, 0.5, ()),
-                                   (3000, 40, 400, 0.3, (7,)), (40000, 64, 3, 0.1, ())])
-def test_relayout_equals_stable_sort(shape):
+def _shuffle_rows(X, seed):
+    """Same matrix with the entries of every row in random order (legal, non-canonical CSR)."""
+    rng = np.random.default_rng(seed)
+    indices, data = X.indices.copy(), X.data.copy()
+    for r in range(X.shape[0]):
+        lo, hi = X.indptr[r], X.indptr[r + 1]
+        p = rng.permutation(hi - lo)
+        indices[lo:hi], data[lo:hi] = indices[lo:hi][p], data[lo:hi][p]
+    return sp.csr_matrix((data, indices, X.indptr.copy()), shape=X.shape)
+
+
+# (cells, genes, groups, density, empty groups): the tiled path (sorted rows; csrc/relayout.cu relayout_tile_kernel)
+# sees gene counts below / across / far above its 256-gene blocks, chunks of exactly 256 rows and ragged ones, blocks
+# denser than its 12288-element staging buffer (several passes), groups smaller than a chunk, one group
+SHAPES = [(700, 90, 5, 0.2, ()), (5000, 300, 16, 0.05, (3, 15)), (64, 10, 1, 0.5, ()),
+          (3000, 40, 400, 0.3, (7,)), (40000, 64, 3, 0.1, ()), (1024, 256, 1, 0.97, ()), (2100, 1300, 4, 0.6, (2,)),
+          (513, 2050, 2, 0.02, ()), (9000, 700, 7, 0.25, ())]
+
+
+@pytest.mark.parametrize("canonical", [True, False])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_relayout_equals_stable_sort(shape, canonical):
     n_cells, n_genes, R, density, empty = shape
     X, codes = _case(n_cells, n_genes, R, density, seed=n_cells, empty_groups=empty)
+    if not canonical:
+        if n_cells > 5000:
+            pytest.skip("host-side row shuffle of the large case")
+        X = _shuffle_rows(X, seed=1)
     d = torch.device("cuda", 0)
     csr = dev_mod.CsrOnDevice(X, d)
+    assert csr.sorted_rows == canonical
     order = np.argsort(codes, kind="stable")
     rank = np.empty_like(order); rank[order] = np.arange(order.size)
     gs = np.concatenate([[0], np.cumsum(np.bincount(codes, minlength=R))]).astype(np.int64)

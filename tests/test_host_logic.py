@@ -19,7 +19,8 @@ def test_distinct_masks_is_the_partition_of_np_unique(n, R, p):
     least-squares functional)."""
     rng = np.random.default_rng(n * 1000 + R)
     good = (rng.random((n, R)) < p).astype(np.uint8)
-    masks, inv = engine.distinct_masks(good)
+    first, inv = engine.distinct_masks(good)
+    masks = good[first]
     want_masks, want_inv = np.unique(good, axis=0, return_inverse=True)
     assert masks.shape == want_masks.shape and masks.dtype == np.uint8
     assert inv.shape == (n,)
@@ -28,6 +29,19 @@ def test_distinct_masks_is_the_partition_of_np_unique(n, R, p):
     # same partition: genes share a mask here iff they share one there
     pairs = set(zip(inv.tolist(), np.asarray(want_inv).reshape(-1).tolist()))
     assert len(pairs) == masks.shape[0]
+
+
+def test_distinct_masks_with_a_second_key_component():
+    """With treatment_for_gene a design is (validity mask, id of the gene's treatment-column set): genes share a
+    design iff both agree (reference main.py:368-373, :392 slices the treatment frame per gene)."""
+    rng = np.random.default_rng(3)
+    good = (rng.random((400, 6)) < 0.8).astype(np.uint8)
+    extra = rng.integers(0, 5, size=400)
+    first, inv = engine.distinct_masks(good, extra)
+    np.testing.assert_array_equal(good[first][inv], good)
+    np.testing.assert_array_equal(extra[first][inv], extra)
+    keys = {(good[i].tobytes(), int(extra[i])) for i in range(400)}
+    assert len(keys) == first.size
 
 
 def test_tile_plan_respects_grid_and_workspace_limits():
