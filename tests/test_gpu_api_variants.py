@@ -182,8 +182,10 @@ def test_mean_only_estimator_vs_oracle():
     ratio = hg["mean_se"][ok] / ho["mean_se"][ok]
     assert 0.9 < np.median(ratio) < 1.1
     assert stats.spearmanr(hg["mean_asl"][ok], ho["mean_asl"][ok]).statistic > 0.95
-    # the variance statistic is a constant under this estimator: its coefficient is 0 and its null is degenerate
-    assert np.array_equal(np.isnan(hg["var_asl"]), np.isnan(ho["var_asl"]))
+    # the variance statistic is a constant (10) under this estimator: log residual variance = round-off around 0 on
+    # both sides, so its coefficient is 0 to round-off and its p-value is decided by noise (the reference returns NaN
+    # only when every replicate is bit-equal, hypothesis_test.py:62-64) -- nothing to compare beyond the coefficient
+    assert np.nanmax(np.abs(hg["var_coef"])) < 1e-9 and np.nanmax(np.abs(ho["var_coef"])) < 1e-9
 
 
 # ----------------------------------------------------------------------------- inplace / filter_genes
