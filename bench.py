@@ -72,11 +72,6 @@ def ncu_traffic(nnz):
     return tot, "profiles/r01_seg_moments_stream.json (ncu --set full, same matrix, stream + edge kernels)"
 
 
-def engine_tile_genes(seg, num_boot):
-    from memento_b200 import engine
-    return engine.tile_plan(seg, num_boot, engine.default_workspace(seg.device))
-
-
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -94,11 +89,16 @@ def parse():
 
 
 def config_dict(a, n_groups, n_tested, extra=None):
+    """Workload description; identical in both arms (the driver compares the two lines' ``config``)."""
     c = {"workload": "configs[1] IFN-beta PBMC-shaped 1D DE: %d cells x %d genes, %d groups (stim x %d cell "
                      "types), num_boot=%d, resampling=bootstrap, approx=%s" %
                      (a.cells, a.genes, n_groups, a.types, a.num_boot, bool(a.approx)),
          "cells": a.cells, "genes": a.genes, "genes_tested": n_tested, "groups": n_groups,
-         "num_boot": a.num_boot, "approx": bool(a.approx), "q": 0.07}
+         "num_boot": a.num_boot, "approx": bool(a.approx), "q": 0.07,
+         "parallelism": "gene-sharded x%d (a %d-gene block of the same cells per GPU; all-reduce of UMI totals + "
+                        "all-gather of moment vectors in setup only, none in the timed step)" % (a.gpus, a.genes),
+         "l2": "inputs larger than L2, no explicit flush: the group-sorted count matrix (8 B per nonzero, ~0.47 GB "
+               "at 25k x 10k) is streamed every step and ~10 GB of bootstrap rows are written and re-read per gene tile"}
     if extra:
         c.update(extra)
     return c
@@ -172,79 +172,220 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------------- reference arm
+class ReferenceSession:
+    """The reference's own CPU path for this workload: the UNMODIFIED package under ``oracle/_ref`` (recipe:
+    oracle/build_ref.py; ``kind: "reference"``) through its public API -- setup_memento -> create_groups ->
+    compute_1d_moments once on the full matrix, then ``ht_1d_moments(num_cpus=<all host cores>)`` on bounded gene
+    samples.  Falls back to the oracle port (``kind: "port"``) only when ``oracle/_ref`` was not built.
+
+    Fairness: one BLAS/OpenMP thread per worker process (the reference parallelises over genes with a
+    joblib process pool, main.py:397; library threads on top of it oversubscribe the cores), the pool is joblib's
+    reusable loky executor -- started by the warm-up steps, alive across the timed ones -- and a timed step holds
+    several genes per core."""
+
+    def __init__(self, a, ad):
+        from oracle import reference as o_ref
+        from memento_b200 import synth
+        o_ref.pin_worker_threads()
+        self.a, self.cores = a, os.cpu_count()
+        if o_ref.available():
+            self.kind, self.api = "reference", o_ref.load().main
+        else:
+            from oracle import pipeline as o_pipe
+            self.kind, self.api = "port", o_pipe
+        ad.X = ad.X.astype(np.float64)      # the reference then computes in float64 throughout (its own dtype rule)
+        t0 = time.perf_counter()
+        self.api.setup_memento(ad, "q")
+        self.api.create_groups(ad, ["stim", "cell"])
+        self.api.compute_1d_moments(ad, min_perc_group=0.7)
+        self.t_moments = time.perf_counter() - t0
+        self.ad = ad
+        self.groups = ad.uns["memento"]["groups"]
+        self.cov, self.tr = synth.design_from_groups(self.groups, ["stim", "cell"])
+        self.G = ad.shape[1]
+
+    def gene_view(self, idx):
+        """The data set restricted to the genes ``idx`` -- what the reference's own ``gene_list`` branch leaves
+        behind (main.py:258-271), without re-running the moment stage for every sample."""
+        from memento_b200.anndata_lite import AnnDataLite
+        mem = dict(self.ad.uns["memento"])
+        mem["group_cells"] = {g: mem["group_cells"][g][:, idx] for g in self.groups}
+        mem["1d_moments"] = {g: [m[idx] for m in mem["1d_moments"][g]] for g in self.groups}
+        view = AnnDataLite(_ShapeOnly(self.ad.shape[0], len(idx)), self.ad.obs, self.ad.var.iloc[idx], {"memento": mem})
+        return view, mem
+
+    def ht_1d(self, idx):
+        """One timed call of the reference's ht_1d_moments on the genes ``idx``; returns (seconds, 1d_ht dict)."""
+        view, mem = self.gene_view(idx)
+        kw = dict(num_boot=self.a.num_boot, num_cpus=self.cores, resampling="bootstrap", approx=bool(self.a.approx))
+        if self.kind == "reference":
+            kw["verbose"] = 0
+        t0 = time.perf_counter()
+        self.api.ht_1d_moments(view, self.cov, self.tr, **kw)
+        return time.perf_counter() - t0, mem["1d_ht"]
+
+
+class _ShapeOnly:
+    """ht_1d_moments reads ``adata.shape`` only (reference main.py:359); the count matrix of a gene view is never
+    touched, so none is materialised."""
+
+    def __init__(self, n, g):
+        self.shape = (n, g)
+
+
 def run_reference(a):
-    """The reference's CPU path (oracle port, numpy/scipy/sklearn as the reference calls them; the
-    Python reference itself cannot travel to the GPU box) on a bounded gene sample, all cores."""
+    """``--impl reference``: the reference's CPU implementation of the path on this box's host cores, on our arm's
+    config / metric / unit; each step = one ``ht_1d_moments(num_cpus=cores)`` call on a bounded random gene sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle import pipeline as o_pipe
-    from memento_b200 import synth
     dev = "cuda" if torch.cuda.is_available() else None
-    ad = make_data(a, 0, dev)
-    o_pipe.setup_memento(ad, "q")
-    o_pipe.create_groups(ad, ["stim", "cell"])
-    o_pipe.compute_1d_moments(ad, min_perc_group=0.7)
-    groups = ad.uns["memento"]["groups"]
-    cov, tr = synth.design_from_groups(groups, ["stim", "cell"])
-    cores = os.cpu_count()
-    n_sample = a.cpu_sample or max(8, 2 * cores)
-    G = ad.shape[1]
+    ses = ReferenceSession(a, make_data(a, 0, dev))
+    cores, G = ses.cores, ses.G
     rng = np.random.default_rng(0)
-    kw = dict(resampling="bootstrap", approx=bool(a.approx))
-    times = []
+    # warm-up steps start the worker pool and page the libraries in: one gene per core is enough for that.  Timed
+    # steps: 8 genes per core when the run is short, fewer when the driver asks for many steps, so that the timed
+    # region stays around 200 s (rate taken from the last warm-up step), never below 3 genes per core.
+    rate = None
+    times, sizes = [], []
     for it in range(a.warmup + a.steps):
-        sub = np.sort(rng.choice(G, size=min(n_sample, G), replace=False))
-        t0 = time.perf_counter()
-        o_pipe.ht_1d_moments(ad, cov, tr, num_boot=a.num_boot, num_cpus=cores, gene_subset=sub, **kw)
-        dt = time.perf_counter() - t0
-        if it >= a.warmup:
-            times.append(dt)
+        if it < a.warmup:
+            n = min(G, cores * (1 if it + 1 < a.warmup else 2))
+        elif a.cpu_sample:
+            n = min(G, a.cpu_sample)
+        else:
+            n = 8 * cores if rate is None else int(np.clip(rate * 200.0 / a.steps, 3 * cores, 8 * cores))
+            n = min(G, n)
+        sub = np.sort(rng.choice(G, size=n, replace=False))
+        dt, _ = ses.ht_1d(sub)
+        print("reference step %d: %d genes in %.1f s" % (it, n, dt), file=sys.stderr)
+        if it < a.warmup:
+            rate = n / dt
+        else:
+            times.append(dt); sizes.append(n)
     ms = 1e3 * float(np.mean(times))
-    value = min(n_sample, G) / (ms / 1e3)
-    sample = "%d random genes of %d per step, all %d groups, num_boot=%d" % (min(n_sample, G), G, len(groups), a.num_boot)
+    value = float(np.sum(sizes) / np.sum(times))
+    sample = ("%d random genes of %d per step (%.1f per core), all %d groups, num_boot=%d; unmodified reference "
+              "package, joblib pool of %d single-threaded workers kept alive across steps"
+              % (sizes[0], G, sizes[0] / cores, len(ses.groups), a.num_boot, cores)) if ses.kind == "reference" else \
+             ("%d random genes of %d per step, all %d groups, num_boot=%d (oracle port; oracle/_ref absent)"
+              % (sizes[0], G, len(ses.groups), a.num_boot))
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": config_dict(a, len(groups), G),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f64", "data": "synthetic", "config": config_dict(a, len(ses.groups), G),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ses.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
-def cpu_baseline(a, ad_host):
-    """Oracle port on the host cores, bounded sample (rank 0, N == 1 only)."""
-    from oracle import pipeline as o_pipe
-    from memento_b200 import synth
-    t0 = time.perf_counter()
-    oad = ad_host
-    o_pipe.setup_memento(oad, "q")
-    o_pipe.create_groups(oad, ["stim", "cell"])
-    o_pipe.compute_1d_moments(oad, min_perc_group=0.7)
-    t_moments = time.perf_counter() - t0
-    groups = oad.uns["memento"]["groups"]
-    cov, tr = synth.design_from_groups(groups, ["stim", "cell"])
-    cores = os.cpu_count()
-    n_sample = a.cpu_sample or max(8, 2 * cores)
-    G = oad.shape[1]
-    sub = np.sort(np.random.default_rng(0).choice(G, size=min(n_sample, G), replace=False))
-    t0 = time.perf_counter()
-    o_pipe.ht_1d_moments(oad, cov, tr, num_boot=a.num_boot, num_cpus=cores, gene_subset=sub,
-                         resampling="bootstrap", approx=bool(a.approx))
-    dt = time.perf_counter() - t0
-    return {"value": len(sub) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d random genes of %d, all %d groups, num_boot=%d (%.1f s); moment stage "
-                      "setup+groups+1d_moments on the full matrix: %.1f s" %
-                      (len(sub), G, len(groups), a.num_boot, dt, t_moments)}
+def cpu_baseline(a, ad_host, gpu_names, gpu_ht):
+    """The reference on the host cores, bounded sample (rank 0, N == 1 only), and -- the same genes having just been
+    tested on the GPU -- the parity of the two on the bench configuration itself: coefficients (deterministic) to
+    1e-6 relative, standard errors by ratio, p-values by rank concordance (Monte Carlo error on both sides)."""
+    import scipy.stats as stats
+    ses = ReferenceSession(a, ad_host)
+    cores, G = ses.cores, ses.G
+    names = ses.ad.var.index.tolist()
+    same_genes = names == list(gpu_names)
+    n_sample = a.cpu_sample or 4 * cores
+    rng = np.random.default_rng(0)
+    ses.ht_1d(np.sort(rng.choice(G, size=min(G, cores), replace=False)))        # starts the worker pool (untimed)
+    sub = np.sort(rng.choice(G, size=min(n_sample, G), replace=False))
+    dt, ht = ses.ht_1d(sub)
+    out = {"value": len(sub) / dt, "unit": UNIT, "cores": cores, "kind": ses.kind,
+           "sample": "%d random genes of %d (%.1f per core), all %d groups, num_boot=%d (%.1f s); pool of %d "
+                     "single-threaded workers started beforehand; moment stage setup+groups+1d_moments on the full "
+                     "matrix: %.1f s" % (len(sub), G, len(sub) / cores, len(ses.groups), a.num_boot, dt, cores,
+                                          ses.t_moments)}
+    parity = {"genes": int(len(sub)), "same_gene_filter": bool(same_genes)}
+    if same_genes:
+        T = ses.tr.shape[1]
+        pos = (sub[:, None] * T + np.arange(T)[None, :]).reshape(-1)
+        ok_all = True
+        for stat in ("mean", "var"):
+            cg, cr = gpu_ht[stat + "_coef"][pos], ht[stat + "_coef"]
+            sg, sr = gpu_ht[stat + "_se"][pos], ht[stat + "_se"]
+            pg, pr = gpu_ht[stat + "_asl"][pos], ht[stat + "_asl"]
+            fin = np.isfinite(cr)
+            nan_same = bool(np.array_equal(np.isfinite(cg), fin))
+            rel = float(np.max(np.abs(cg[fin] - cr[fin]) / np.maximum(np.abs(cr[fin]), 1e-3))) if fin.any() else 0.0
+            okp = fin & np.isfinite(pr) & np.isfinite(pg) & np.isfinite(sr) & (sr > 0)
+            ratio = sg[okp] / sr[okp]
+            lg, lr = -np.log10(np.maximum(pg[okp], 1e-300)), -np.log10(np.maximum(pr[okp], 1e-300))
+            rho = float(stats.spearmanr(lg, lr).statistic) if okp.sum() > 2 else None
+            parity[stat] = {"n": int(fin.sum()), "nan_pattern_equal": nan_same, "coef_max_rel_err": rel,
+                            "se_ratio_median": float(np.median(ratio)) if okp.any() else None,
+                            "se_ratio_p05_p95": [float(np.percentile(ratio, 5)), float(np.percentile(ratio, 95))]
+                            if okp.any() else None,
+                            "spearman_neglog10_p": rho,
+                            "median_abs_dlog10_p": float(np.median(np.abs(lg - lr))) if okp.any() else None}
+            tol = 1e-6 if stat == "mean" else 1e-5
+            ok_all &= nan_same and rel < tol and (rho is None or rho > 0.9) and \
+                (not okp.any() or 0.9 < float(np.median(ratio)) < 1.1)
+        parity["tolerances"] = "coef rel 1e-6 (mean) / 1e-5 (var, through the fitted trend); median SE ratio in " \
+                               "[0.9, 1.1]; Spearman of -log10 p > 0.9"
+        parity["ok"] = bool(ok_all)
+    else:
+        parity["ok"] = False
+    return out, parity
 
 
 # ----------------------------------------------------------------------------------- our arm
+def sharded_parity(ctx, dev, rank, world):
+    """N > 1, after the timed region: a fixed 6000-cell x 400-gene data set is tested gene-SHARDED over the N ranks
+    (work-balanced contiguous gene blocks, NCCL all-reduce / all-gather in setup, results all-gathered) and, on rank
+    0, unsharded on one GPU; the two must agree -- same gene filter, coefficients to 1e-9, p-values to 1e-6 (global
+    Philox stream ids: a sharded run draws the replicates the single-GPU run draws).  Every driver run at N > 1
+    thereby proves the sharded path's results, not only that it executes."""
+    import memento_b200 as memento
+    from memento_b200 import synth
+    from memento_b200.dist import shard_plan
+
+    def pipeline(ad, dist_ctx, lo):
+        memento.setup_memento(ad, "q", dist=dist_ctx, gene_offset=lo)
+        memento.create_groups(ad, ["stim", "cell"])
+        memento.compute_1d_moments(ad, min_perc_group=0.7)
+        cov, tr = synth.design_from_groups(ad.uns["memento"]["groups"], ["stim", "cell"])
+        memento.ht_1d_moments(ad, cov, tr, num_boot=2000, resampling="bootstrap", approx=False, seed=3)
+        return ad.uns["memento"]
+
+    full = synth.make_counts(6000, 400, n_conditions=2, n_types=2, q=0.07, seed=11)
+    bounds = shard_plan(np.diff(full.X.tocsc().indptr), world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    part = full.copy()
+    keep = np.zeros(full.shape[1], dtype=bool)
+    keep[lo:hi] = True
+    part._inplace_subset_var(keep)
+    part.X = part.X.tocsr()
+    got = pipeline(part, ctx, lo)["1d_ht_all"]
+    if rank != 0:
+        return None
+    mem = pipeline(full, None, 0)
+    ht = mem["1d_ht"]
+    names = full.var.index.tolist()
+    res = {"genes": len(names), "ranks": world, "same_genes": got["gene"] == names, "num_boot": 2000}
+    ok = res["same_genes"] and int(got["n_tests"].sum()) == ht["mean_coef"].size
+    if ok:
+        for k, tol in (("mean_coef", 1e-9), ("var_coef", 1e-9), ("mean_se", 1e-9), ("var_se", 1e-9),
+                       ("mean_asl", 1e-6), ("var_asl", 1e-6)):
+            a_, b_ = got[k], ht[k]
+            same_nan = bool(np.array_equal(np.isnan(a_), np.isnan(b_)))
+            f = ~np.isnan(b_)
+            err = float(np.max(np.abs(a_[f] - b_[f]) / np.maximum(np.abs(b_[f]), 1e-12))) if (same_nan and f.any()) else None
+            res[k + "_max_rel_err"] = err
+            ok = ok and same_nan and (err is None or err <= tol)
+    res["tolerances"] = "coef / se 1e-9, asl 1e-6 (relative)"
+    res["ok"] = bool(ok)
+    return res
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
     import memento_b200 as memento
-    from memento_b200 import synth
+    from memento_b200 import synth, _lib
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,16 +440,17 @@ def run_ours(a):
         clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    launches = 0
+    launches = -_lib.launch_count()      # kernels launched by libmemento_b200.so, counted at its launch sites
     for i in range(a.steps):
         t0 = time.perf_counter()
         memento.ht_1d_moments(ad, cov, tr, seed=100 + i, **kw)      # returns after its device-to-host result copies
-        launches += st.last_stats.get("launches", 0)
         if rank == 0:
             print("timed step %.1f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
     e1.record()
+    launches += _lib.launch_count()
     barrier()
     gc.enable()
+    gpu_ht = {k: np.array(v) for k, v in mem["1d_ht"].items() if k.endswith(("_coef", "_se", "_asl"))}
     ms_total = e0.elapsed_time(e1)
     clk = clocks.stop() if clocks else None
     stage_ms = st.timer.collect()
@@ -381,26 +523,27 @@ def run_ours(a):
     e2e = {"value": genes_total / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te[0]) * 1e3}
 
-    cpu = None
+    cpu = parity = None
     if ad_host is not None:
-        cpu = cpu_baseline(a, ad_host)
+        cpu, parity = cpu_baseline(a, ad_host, ad.var.index.tolist(), gpu_ht)
+    shard_check = sharded_parity(ctx, dev, rank, world) if world > 1 else None
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
-               "config": config_dict(a, len(groups), G, {
-                   "parallelism": "gene-sharded x%d (10k-gene block of the same cells per GPU; all-reduce of UMI "
-                                  "totals + all-gather of moment vectors in setup only, none in the timed step)" % world,
-                   "l2": "inputs larger than L2: group-sorted matrix %.0f MB streamed per step, plus ~%.1f GB of "
-                         "bootstrap rows written and re-read per gene tile"
-                         % (seg.nnz * 8 / 1e6 if seg is not None else 0,
-                            min(G, engine_tile_genes(seg, a.num_boot)) * seg.R * (a.num_boot + 1) * 16 / 1e9)}),
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+               "config": config_dict(a, len(groups), G),
+               "roofline": roofline, "cpu_baseline": cpu, "parity_on_bench_config": parity, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clk}
         out.update(extra)
+        if shard_check is not None:
+            out["sharded_parity"] = shard_check
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and ((shard_check is not None and not shard_check["ok"]) or (parity is not None and not parity["ok"])):
+        print("PARITY FAILURE: %s" % json.dumps({"sharded_parity": shard_check, "parity_on_bench_config": parity}),
+              file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

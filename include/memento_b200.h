@@ -25,6 +25,9 @@ extern "C" {
 #endif
 
 int mm_version(void);
+/* Number of kernels this library has launched in the process so far (every launch site is counted): the bench line's
+ * "gpu_launches" is the difference of two readings around the timed region. */
+int64_t mm_launch_count(void);
 const char* mm_last_error(void);
 
 /* Per-cell UMI totals of a CSR matrix, optionally restricted to the genes with gene_mask[g] != 0

@@ -742,7 +742,7 @@ MM_EXPORT int mm_boot_prepare(int device, void* stream, void* entries, const int
     P.R = R; P.seg_U = seg_U; P.group_ncells = group_ncells; P.n_table_max = n_table_max; P.tab_off = tab_off;
     P.acc_slot = (const long long*)acc_slot; P.acc_stride = acc_stride; P.acc_pool = acc_pool;
     P.info = (SegInfo*)seg_info; P.min_accept = min_accept;
-    P.allow_direct = !(getenv("MM_BOOT_DIRECT") && !atoi(getenv("MM_BOOT_DIRECT")));      // A/B hook
+    P.allow_direct = tuning().boot_direct != 0;      // A/B hook
     long long blocks = (n_seg + 7) / 8;
     MM_REQUIRE(blocks < 2147483647LL, "too many segments");
     MM_CUDA(cudaMemsetAsync(seg_lists(seg_info, n_seg).count, 0, 4 * sizeof(int), (cudaStream_t)stream));
@@ -771,8 +771,9 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     P.log_rows = log_rows; P.n_invalid = n_invalid; P.seg_order = seg_order;
     MM_REQUIRE(!log_rows || n_invalid, "log_rows needs the n_invalid counters (zero-initialised)");
     P.info = (const SegInfo*)seg_info; P.tab_pool = (const uint2*)tab_pool; P.acc_pool = acc_pool;
-    const int variant = getenv("MM_BOOT_VARIANT") ? atoi(getenv("MM_BOOT_VARIANT")) : 1;     // A/B hooks
-    const int slots = getenv("MM_BOOT_SLOTS") ? atoi(getenv("MM_BOOT_SLOTS")) : 2;
+    const Tuning& tune = tuning();
+    const int variant = tune.boot_variant >= 0 ? tune.boot_variant : 1;     // A/B hooks
+    const int slots = tune.boot_slots >= 0 ? tune.boot_slots : 2;
     const int n_slots = (variant == 0 || slots <= 1) ? 1 : (slots >= 4 ? 4 : slots);
     // replicates per block: lanes claim replicates from the block's counter, so only the block's last pass has idle
     // lanes -- one block per segment when there are enough segments to fill the GPU (C2: 40 passes 165 ms, 20 passes
@@ -780,7 +781,7 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
     const long long want_blocks = (148 * 6 * 2 + n_seg - 1) / n_seg;
     int passes = (int)((num_boot + (long long)kBootThreads * n_slots * want_blocks - 1) / ((long long)kBootThreads * n_slots * want_blocks));
     if (passes > 40) passes = 40;
-    if (getenv("MM_BOOT_PASSES")) passes = atoi(getenv("MM_BOOT_PASSES"));      // A/B hook
+    if (tune.boot_passes >= 0) passes = tune.boot_passes;      // A/B hook
     if (passes < 1) passes = 1;
     P.reps_per_block = kBootThreads * passes * n_slots;
     MM_REQUIRE(!seg_info || (tab_pool && acc_pool), "seg_info needs tab_pool and acc_pool");
@@ -804,8 +805,9 @@ MM_EXPORT int mm_bootstrap_1d(int device, void* stream, const void* entries, con
         MM_CUDA(cudaFuncSetAttribute(bootstrap_1d_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid3((num_boot + kDirectReps - 1) / kDirectReps, (unsigned)(n_seg < 1024 ? n_seg : 1024));
         bootstrap_1d_direct_kernel<<<grid3, kBootThreads, smem, st>>>(P);
+        return check_launch("mm_bootstrap_1d (direct)");
     }
-    return check_launch("mm_bootstrap_1d");
+    return 0;
 }
 
 MM_EXPORT int mm_bootstrap_1d_replay(int device, void* stream, const double* x, const double* inv_sf,

@@ -16,6 +16,25 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);      // cudaGetLastError -> status
 int enter(int device);                   // cudaSetDevice + clear error; returns status
 
+// A/B and tuning switches (MM_* environment variables), read ONCE per process at the first C-ABI call -- never on
+// the per-call path.  -1 / 0 = "not set" (the built-in choice applies).
+struct Tuning {
+    int moments_notile;     // MM_MOMENTS_NOTILE: set -> generic W-lane kernels
+    int moments_kernel;     // MM_MOMENTS_KERNEL: 0 auto, 1 tile, 2 stream, 3 stream_l1
+    int moments_threads;    // MM_MOMENTS_THREADS (stream kernel): 512 / 640 / 768 / 896
+    int moments_prefetch;   // MM_MOMENTS_PREFETCH: -1 unset
+    int moments_chunk;      // MM_MOMENTS_CHUNK: spans per chunk, 1 / 4 / 8
+    int moments_cfg;        // MM_MOMENTS_CFG (tile kernel): -1 unset
+    int moments_regime;     // MM_MOMENTS_REGIME
+    int moments_w;          // MM_MOMENTS_W: lanes per segment of the generic kernel
+    int boot_direct;        // MM_BOOT_DIRECT: -1 unset, 0 = no direct sampler
+    int boot_variant;       // MM_BOOT_VARIANT: -1 unset
+    int boot_slots;         // MM_BOOT_SLOTS: -1 unset
+    int boot_passes;        // MM_BOOT_PASSES: -1 unset
+    int pair_slots;         // MM_PAIR_SLOTS: -1 unset
+};
+const Tuning& tuning();
+
 #define MM_CUDA(call)                                                              \
     do {                                                                           \
         cudaError_t e_ = (call);                                                   \

@@ -15,6 +15,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 
 namespace mm {
 
@@ -814,7 +815,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<long long> g_launches{0};      // kernels launched by this library (every launch is followed by check_launch)
 int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -832,13 +835,42 @@ int enter(int device) {
     return 0;
 }
 const char* last_error() { return g_err; }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+static int env_int(const char* name, int unset) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : unset;
+}
+const Tuning& tuning() {
+    static const Tuning t = [] {
+        Tuning u;
+        u.moments_notile = getenv("MM_MOMENTS_NOTILE") ? 1 : 0;
+        const char* k = getenv("MM_MOMENTS_KERNEL");
+        u.moments_kernel = !k ? 0 : !strcmp(k, "tile") ? 1 : !strcmp(k, "stream") ? 2 : !strcmp(k, "stream_l1") ? 3 : 0;
+        u.moments_threads = env_int("MM_MOMENTS_THREADS", 0);
+        u.moments_prefetch = env_int("MM_MOMENTS_PREFETCH", -1);
+        u.moments_chunk = env_int("MM_MOMENTS_CHUNK", 0);
+        u.moments_cfg = env_int("MM_MOMENTS_CFG", -1);
+        u.moments_regime = env_int("MM_MOMENTS_REGIME", 0);
+        u.moments_w = env_int("MM_MOMENTS_W", 0);
+        u.boot_direct = env_int("MM_BOOT_DIRECT", -1);
+        u.boot_variant = env_int("MM_BOOT_VARIANT", -1);
+        u.boot_slots = env_int("MM_BOOT_SLOTS", -1);
+        u.boot_passes = env_int("MM_BOOT_PASSES", -1);
+        u.pair_slots = env_int("MM_PAIR_SLOTS", -1);
+        return u;
+    }();
+    return t;
+}
 
 }  // namespace mm
 
 using namespace mm;
 
 MM_EXPORT const char* mm_last_error(void) { return mm::last_error(); }
-MM_EXPORT int mm_version(void) { return 100; }
+MM_EXPORT int mm_version(void) { return 101; }
+namespace mm { long long launch_count(); }
+MM_EXPORT int64_t mm_launch_count(void) { return (int64_t)mm::launch_count(); }
 
 MM_EXPORT int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                               const float* data, int64_t n_rows, const uint8_t* gene_mask, double* out) {
@@ -920,25 +952,22 @@ MM_EXPORT int mm_seg_moments(int device, void* stream, const float* vals, const 
     const long long* sp = (const long long*)seg_ptr;
     const long long mean_len = nnz / n_seg;
     const bool aligned = (((uintptr_t)vals | (uintptr_t)rows | (uintptr_t)inv_sf) & 15) == 0;
-    if (chunk_seg && edge && aligned && n_seg < 2147483647LL && !getenv("MM_MOMENTS_NOTILE")) {
+    const Tuning& tune = tuning();
+    if (chunk_seg && edge && aligned && n_seg < 2147483647LL && !tune.moments_notile) {
         const int n_sm = sm_count(device);
         // Tuning hooks: MM_MOMENTS_KERNEL = stream | stream_l1 | tile overrides the choice below;
         // MM_MOMENTS_CFG (tile kernel) 0 = 3 stages x 2 CTAs/SM, 1 = 2 stages x 3 CTAs/SM, 2 = 4 stages x 1 CTA/SM.
-        const char* kern = getenv("MM_MOMENTS_KERNEL");
         bool use_stream = mean_len >= kStreamMinMean;
         bool smem_table = n_cells > 0 && n_cells * 8 <= 227 * 1024 - 1024;
-        if (kern) {
-            if (!strcmp(kern, "tile")) use_stream = false;
-            else if (!strcmp(kern, "stream")) use_stream = true;
-            else if (!strcmp(kern, "stream_l1")) { use_stream = true; smem_table = false; }
-        }
+        if (tune.moments_kernel == 1) use_stream = false;
+        else if (tune.moments_kernel == 2) use_stream = true;
+        else if (tune.moments_kernel == 3) { use_stream = true; smem_table = false; }
         if (use_stream) {
             int threads = 640;
             bool pf = true;
-            if (const char* ov = getenv("MM_MOMENTS_THREADS")) threads = atoi(ov);      // tuning hooks
-            if (const char* ov = getenv("MM_MOMENTS_PREFETCH")) pf = atoi(ov) != 0;
-            int chunk_spans = 4;
-            if (const char* ov = getenv("MM_MOMENTS_CHUNK")) { int c = atoi(ov); chunk_spans = (c == 1 || c == 8) ? c : 4; }   // 8: 256-nonzero spans
+            if (tune.moments_threads) threads = tune.moments_threads;      // tuning hooks
+            if (tune.moments_prefetch >= 0) pf = tune.moments_prefetch != 0;
+            const int chunk_spans = (tune.moments_chunk == 1 || tune.moments_chunk == 8) ? tune.moments_chunk : 4;   // 8: 256-nonzero spans
 #define MM_STREAM(T, PF) (chunk_spans == 1 ? launch_stream<T, PF, 1, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
                         : chunk_spans == 8 ? launch_stream<T, PF, 8, 2>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
                                            : launch_stream<T, PF, 4, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table))
@@ -949,14 +978,14 @@ MM_EXPORT int mm_seg_moments(int device, void* stream, const float* vals, const 
 #undef MM_STREAM
         }
         int cfg = 1, regime = 0;
-        if (const char* ov = getenv("MM_MOMENTS_CFG")) cfg = atoi(ov);
-        if (const char* ov = getenv("MM_MOMENTS_REGIME")) regime = atoi(ov);
+        if (tune.moments_cfg >= 0) cfg = tune.moments_cfg;
+        regime = tune.moments_regime;
         if (cfg == 0) return launch_tile<3, 2>(st, n_sm, regime, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, out, edge);
         if (cfg == 2) return launch_tile<4, 1>(st, n_sm, regime, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, out, edge);
         return launch_tile<2, 3>(st, n_sm, regime, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, out, edge);
     }
     int W = mean_len < 48 ? 8 : (mean_len < 1024 ? 16 : 32);
-    if (const char* ov = getenv("MM_MOMENTS_W")) { int w = atoi(ov); if (w == 8 || w == 16 || w == 32) W = w; }   // tuning hook
+    if (tune.moments_w == 8 || tune.moments_w == 16 || tune.moments_w == 32) W = tune.moments_w;   // tuning hook
     // Without the tile index (or with unaligned arrays): W lanes per segment straight from global memory;
     // segments far above the mean are deferred to the CTA kernel through big_list.
     MM_REQUIRE(big_list, "null pointer (big_list)");

@@ -547,12 +547,13 @@ MM_EXPORT int mm_pair_bootstrap(int device, void* stream, const void* entries, c
     P.entries = (const PairEntry*)entries; P.item_ptr = (const long long*)item_ptr; P.n_items = n_items; P.R = R;
     P.info = (const PairInfo*)info; P.group_ncells = group_ncells; P.true_corr = true_corr;
     P.tab_pool = (const uint2*)tab_pool; P.acc_pool = acc_pool; P.B = num_boot; P.seed = seed;
-    const int slots = getenv("MM_PAIR_SLOTS") ? atoi(getenv("MM_PAIR_SLOTS")) : 2;      // A/B hook
+    const Tuning& tune = tuning();
+    const int slots = tune.pair_slots >= 0 ? tune.pair_slots : 2;      // A/B hook
     const int n_slots = slots <= 1 ? 1 : (slots >= 3 ? 3 : 2);
     const long long want_blocks = (148 * 4 * 2 + n_items - 1) / n_items;     // see mm_bootstrap_1d
     int passes = (int)((num_boot + (long long)kPairThreads * n_slots * want_blocks - 1) / ((long long)kPairThreads * n_slots * want_blocks));
     if (passes > 40) passes = 40;
-    if (getenv("MM_BOOT_PASSES")) passes = atoi(getenv("MM_BOOT_PASSES"));      // A/B hook
+    if (tune.boot_passes >= 0) passes = tune.boot_passes;      // A/B hook
     if (passes < 1) passes = 1;
     P.item_id = (const long long*)item_id; P.reps_per_block = kPairThreads * passes * n_slots;
     P.boot_corr = boot_corr; P.item_good = item_good; P.item_order = item_order;

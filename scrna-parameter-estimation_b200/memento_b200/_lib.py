@@ -46,7 +46,7 @@ SIGNATURES = {
 }
 
 # host-only helpers (no leading device / stream arguments)
-HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp]}
+HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp], "mm_launch_count": []}
 
 _lib = None
 
@@ -73,7 +73,7 @@ def load():
         fn.argtypes = [C.c_int, _vp] + args
     for name, args in HOST_SIGNATURES.items():
         fn = getattr(lib, name)
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name == "mm_launch_count" else C.c_int
         fn.argtypes = args
     _lib = lib
     return lib
@@ -97,6 +97,11 @@ def call(name, device, *args):
     status = getattr(lib, name)(idx, stream, *conv)
     if status != 0:
         raise MementoCudaError("%s failed (status %d): %s" % (name, status, lib.mm_last_error().decode()))
+
+
+def launch_count():
+    """Kernels launched by the library in this process so far (counted at every launch site in csrc/)."""
+    return int(load().mm_launch_count())
 
 
 def poisson_table_offsets(n_max):

@@ -573,17 +573,26 @@ _HT_KEYS = ("mean_coef", "mean_se", "mean_asl", "var_coef", "var_se", "var_asl")
 def _gather_1d_ht(adata, t_gene):
     """Gene-sharded run: every rank gets the results of all ranks' genes, in global gene order (rank blocks are
     contiguous gene ranges), as ``uns['memento']['1d_ht_all']`` = {"gene": names, "n_tests": per-gene test counts,
-    the six flat arrays of ``1d_ht``}.  One all-gather of 6 * (tests of the rank) doubles over NCCL / NVLink; the
-    rank's own ``1d_ht`` keeps matching its ``adata.var``."""
+    the six flat arrays of ``1d_ht``}.  One variable-length all-gather of (tests of the rank) x 7 doubles over
+    NCCL / NVLink: the six statistics plus the gene's position in the gathered name list; the names themselves are
+    exchanged once per gene set (they change only when compute_1d_moments filters).  The rank's own ``1d_ht`` keeps
+    matching its ``adata.var``."""
     mem = adata.uns["memento"]
     st = _state(adata)
     ht = mem["1d_ht"]
+    names_local = adata.var.index
+    key = (len(names_local), hash(tuple(names_local[:: max(1, len(names_local) // 64)])))
+    if getattr(st, "all_names_key", None) != key:
+        counts, _ = st.dist.all_gather_concat(np.array([len(names_local)], dtype=np.int64))
+        st.all_names = st.dist.all_gather_names(names_local.tolist())
+        st.all_names_lo = int(counts[:st.dist.rank].sum())
+        st.all_names_key = key
     n_local = int(t_gene.sum())
-    packed = np.stack([ht[k][:n_local] for k in _HT_KEYS], axis=1)                  # (tests, 6)
+    gene_pos = np.repeat(st.all_names_lo + np.arange(t_gene.size), t_gene).astype(np.float64)
+    packed = np.stack([ht[k][:n_local] for k in _HT_KEYS] + [gene_pos], axis=1)     # (tests, 7)
     allv, _ = st.dist.all_gather_concat(packed)
-    counts, _ = st.dist.all_gather_concat(t_gene.astype(np.int64))
-    names = st.dist.all_gather_names(adata.var.index.tolist())
-    res = {"gene": names, "n_tests": counts}
+    pos = np.rint(allv[:, 6]).astype(np.int64)
+    res = {"gene": st.all_names, "n_tests": np.bincount(pos, minlength=len(st.all_names)).astype(np.int64)}
     for j, k in enumerate(_HT_KEYS):
         res[k] = np.ascontiguousarray(allv[:, j])
     mem["1d_ht_all"] = res

@@ -91,3 +91,50 @@ def test_shard_plan_balances_work():
         assert loads.max() <= w.sum() / world + w.max() + 1
     assert mdist.shard_plan(np.zeros(0), 4).tolist() == [0, 0, 0, 0, 0]
     assert mdist.shard_plan(np.ones(3), 8)[-1] == 3
+
+
+# ----------------------------------------------------------------------------- result gather of ht_1d_moments
+def _gather_worker(rank, world, port, out_dir):
+    """Every rank holds the results of its own (ragged) gene block; ``main._gather_1d_ht`` must leave ALL genes'
+    results, in global gene order, on every rank (reference main.py:399-412 assembles all genes in one place)."""
+    import types
+    import pandas as pd
+    from memento_b200 import main as mmain
+    from memento_b200.anndata_lite import AnnDataLite
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_genes = [5, 3][rank]
+        lo = [0, 5][rank]
+        t_gene = np.array([[2, 1, 0, 3, 1], [1, 2, 2]][rank])          # tests per gene (treatment_for_gene pattern)
+        n_tests = int(t_gene.sum())
+        ht = {k: 100.0 * j + 10.0 * rank + np.arange(n_tests, dtype=np.float64)
+              for j, k in enumerate(mmain._HT_KEYS)}
+        ht["mean_asl"][0] = np.nan
+        st = types.SimpleNamespace(dist=mdist.DistContext())
+        var = pd.DataFrame(index=pd.Index(["g%d" % (lo + i) for i in range(n_genes)]))
+        import scipy.sparse as sp
+        ad = AnnDataLite(sp.csr_matrix((4, n_genes)), var=var, uns={"memento": {"_b200": st, "1d_ht": ht}})
+        for _ in range(2):                      # the second call reuses the cached name list
+            mmain._gather_1d_ht(ad, t_gene)
+        res = ad.uns["memento"]["1d_ht_all"]
+        np.savez(os.path.join(out_dir, "g%d.npz" % rank), gene=np.asarray(res["gene"], dtype="U"),
+                 n_tests=res["n_tests"], **{k: res[k] for k in mmain._HT_KEYS})
+    finally:
+        tdist.destroy_process_group()
+
+
+def test_result_gather_of_ragged_gene_blocks(tmp_path):
+    from memento_b200 import main as mmain
+    mp.spawn(_gather_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "g0.npz"), np.load(tmp_path / "g1.npz")
+    for key in r0.files:
+        assert np.array_equal(r0[key], r1[key], equal_nan=(r0[key].dtype.kind == "f")), key
+    assert r0["gene"].tolist() == ["g%d" % i for i in range(8)]
+    assert r0["n_tests"].tolist() == [2, 1, 0, 3, 1, 1, 2, 2]
+    for j, k in enumerate(mmain._HT_KEYS):
+        want = np.concatenate([100.0 * j + np.arange(7.0), 100.0 * j + 10.0 + np.arange(5.0)])
+        if k == "mean_asl":
+            want[[0, 7]] = np.nan            # every rank's first test
+        assert np.array_equal(r0[k], want, equal_nan=True), k
