@@ -72,6 +72,28 @@ def ncu_traffic(nnz):
     return tot, "profiles/r01_seg_moments_stream.json (ncu --set full, same matrix, stream + edge kernels)"
 
 
+# BASELINE.json shapes beyond the headline configuration.  ``labels`` = create_groups columns of
+# the synthetic obs frame (stim: condition, cell: cell type / guide, donor: donor / well).
+WORKLOADS = {
+    "northstar": dict(
+        desc="north-star: 1M cells x 20k genes, 2 conditions x 20 cell types = 40 groups, num_boot=10000, "
+             "approx=False; covariate = cell-type dummies, treatment = stim",
+        cells=1_000_000, genes=20_000, conditions=2, types=20, donors=1, q=0.07, labels=["stim", "cell"],
+        kw=dict(approx=False), design="stim"),
+    "c4": dict(
+        desc="configs[3] Perturb-seq K562-shaped: 250k cells x 8k genes, 1000 guides x 2 wells = 2000 groups, "
+             "num_boot=10000, approx=True; covariate = well dummy, treatment = targeting vs the 100 control guides",
+        cells=250_000, genes=8_000, conditions=1, types=1000, donors=2, q=0.15, labels=["cell", "donor"],
+        kw=dict(approx=True), design="guide"),
+    "c5": dict(
+        desc="configs[4] lupus-scale eQTL: 1.2M cells x 20k genes, 2 conditions x 20 cell types x 100 donors = 4000 "
+             "groups, num_boot=10000, approx=True, resample_rep=True, treatment_for_gene = 5 of 500 genotype columns "
+             "per gene; covariate = cell-type dummies + stim",
+        cells=1_200_000, genes=20_000, conditions=2, types=20, donors=100, q=0.1, labels=["stim", "cell", "donor"],
+        kw=dict(approx=True, resample_rep=True), design="eqtl"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -85,6 +107,10 @@ def parse():
     ap.add_argument("--approx", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="genes in the CPU sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2"] + sorted(WORKLOADS),
+                    help="c2 (default): the headline metric's configuration; the others time the whole API "
+                         "pipeline of a larger BASELINE shape, gene-sharded over the ranks (strong scaling)")
+    ap.add_argument("--genes-total", type=int, default=0, help="workload runs: genes over ALL ranks (0 = the shape's)")
     return ap.parse_args()
 
 
@@ -546,10 +572,160 @@ def run_ours(a):
         sys.exit(3)
 
 
+def workload_design(name, groups, labels, genes):
+    """Group-level covariate / treatment frames (and treatment_for_gene) of a WORKLOADS entry."""
+    import pandas as pd
+    rows = [g.split("^")[1:] for g in groups]
+    df = pd.DataFrame(rows, columns=labels, index=groups)
+    tfg = None
+    if name == "stim":
+        cov = pd.get_dummies(df[["cell"]], drop_first=True).astype(float)
+        tr = pd.DataFrame({"stim": (df["stim"] == "stim").astype(float)}, index=groups)
+    elif name == "guide":
+        cov = pd.get_dummies(df[["donor"]], drop_first=True).astype(float)                # well
+        tr = pd.DataFrame({"targeting": (df["cell"].str[2:].astype(int) >= 100).astype(float)}, index=groups)
+    else:   # eqtl: reference analysis/lupus/run_memento.py:99-109
+        cov = pd.get_dummies(df[["cell"]], drop_first=True).astype(float)
+        cov["stim"] = (df["stim"] == "stim").astype(float)
+        rng = np.random.default_rng(5)
+        donors = sorted(df["donor"].unique())
+        geno = rng.integers(0, 3, size=(len(donors), 500)).astype(float)
+        tr = pd.DataFrame(geno[pd.Categorical(df["donor"], categories=donors).codes],
+                          columns=["snp%d" % k for k in range(500)], index=groups)
+        cols = tr.columns.to_numpy()
+        tfg = {g: cols[np.sort(rng.choice(500, size=5, replace=False))].tolist() for g in genes}
+    return cov, tr, tfg
+
+
+def run_workload(a):
+    """``--workload northstar|c4|c5``: the whole public-API pipeline of a larger BASELINE shape, the genes sharded
+    over the ranks (strong scaling; ``--genes-total`` shrinks the gene axis for runs on fewer GPUs).  Every stage is
+    timed by the wall clock between barriers + device synchronisation (max over ranks); ``ht_1d_moments`` includes the
+    NCCL all-gather of the results.  One JSON line: value = seconds of one ht_1d_moments call over all genes."""
+    import torch
+    import torch.distributed as dist
+    import memento_b200 as memento
+    from memento_b200 import synth, _lib
+
+    w = WORKLOADS[a.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = None
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+        from memento_b200.dist import DistContext
+        ctx = DistContext(device=dev)
+    genes_total = a.genes_total or w["genes"]
+    per_rank = genes_total // world
+    num_boot = a.num_boot
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    stages = {}
+
+    def timed(name, fn):
+        sync()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stages.setdefault(name, []).append(float(t[0]))
+        if rank == 0:
+            print("%-28s %.3f s" % (name, float(t[0])), file=sys.stderr, flush=True)
+        return out
+
+    # warm the context (CUDA / NCCL initialisation, the Poisson tables, library load) on a toy data set
+    toy = synth.make_counts(2000, 64 * world, n_conditions=2, n_types=2, q=0.07, seed=3)
+    keep = np.zeros(toy.shape[1], dtype=bool); keep[rank * 64:(rank + 1) * 64] = True
+    toy._inplace_subset_var(keep); toy.X = toy.X.tocsr()
+    memento.setup_memento(toy, "q", dist=ctx, gene_offset=rank * 64)
+    memento.create_groups(toy, ["stim", "cell"])
+    memento.compute_1d_moments(toy, min_perc_group=0.5)
+    tcov, ttr = synth.design_from_groups(toy.uns["memento"]["groups"], ["stim", "cell"])
+    memento.ht_1d_moments(toy, tcov, ttr, num_boot=200, resampling="bootstrap", approx=True)
+    del toy
+
+    t0 = time.perf_counter()
+    ad = synth.make_counts_fast(w["cells"], per_rank, n_conditions=w["conditions"], n_types=w["types"], q=w["q"],
+                                seed=7, n_donors=w["donors"], device=dev, shard=rank)
+    t_synth = time.perf_counter() - t0
+    nnz_host = int(ad.X.nnz)
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    timed("setup_memento", lambda: memento.setup_memento(ad, "q", profile=True, dist=ctx, gene_offset=rank * per_rank))
+    timed("create_groups", lambda: memento.create_groups(ad, w["labels"]))
+    timed("compute_1d_moments", lambda: memento.compute_1d_moments(ad, min_perc_group=0.7))
+    mem = ad.uns["memento"]
+    st = mem["_b200"]
+    groups = mem["groups"]
+    cov, tr, tfg = workload_design(w["design"], groups, w["labels"], ad.var.index.tolist())
+    kw = dict(num_boot=num_boot, resampling="bootstrap", treatment_for_gene=tfg, **w["kw"])
+    if clocks:
+        clocks.wait_ready()
+    for i in range(a.warmup):
+        timed("ht_1d_moments (warm-up)", lambda: memento.ht_1d_moments(ad, cov, tr, seed=1 + i, **kw))
+    st.timer.collect(); st.timer.ms.clear(); st.timer.calls.clear()
+    if clocks:
+        clocks.mark()
+    l0 = _lib.launch_count()
+    for i in range(a.steps):
+        timed("ht_1d_moments", lambda: memento.ht_1d_moments(ad, cov, tr, seed=100 + i, **kw))
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop() if clocks else None
+    stage_ms = {k: v / a.steps for k, v in st.timer.collect().items()}
+    G = ad.shape[1]
+    tot = torch.tensor([float(G), float(nnz_host), float(st.seg.nnz)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ht_s = float(np.mean(stages["ht_1d_moments"]))
+    first = {k: v[0] for k, v in stages.items() if k not in ("ht_1d_moments", "ht_1d_moments (warm-up)")}
+    pipeline_s = sum(first.values()) + ht_s
+    n_tests = int(mem["1d_ht"]["mean_coef"].size)
+    gathered = mem.get("1d_ht_all")
+    if rank == 0:
+        out = {"metric": "seconds per ht_1d_moments call over all genes (num_boot=%d), %s" % (num_boot, a.workload),
+               "value": ht_s, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ht_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": w["desc"], "cells": w["cells"], "genes_total": genes_total,
+                          "genes_per_rank": per_rank, "genes_tested": int(tot[0]), "groups": len(groups),
+                          "num_boot": num_boot, "treatment_columns": int(tr.shape[1]),
+                          "tests_rank0": n_tests, "nnz_total": int(tot[1]), **w["kw"],
+                          "l2": "inputs larger than L2 (%.1f GB group-sorted matrix per rank)" % (st.seg.nnz * 8 / 1e9)},
+               "genes_per_s": float(tot[0]) / ht_s,
+               "pipeline_s": pipeline_s,
+               "stage_s": {**first, "ht_1d_moments": ht_s,
+                           "ht_1d_moments (first call)": (stages.get("ht_1d_moments (warm-up)") or [None])[0]},
+               "ht_1d_kernel_ms_rank0": stage_ms,
+               "synth_s_rank0": t_synth,
+               "results_gathered": None if gathered is None else
+               {"genes": len(gathered["gene"]), "tests": int(gathered["mean_coef"].size),
+                "finite_mean_asl": int(np.isfinite(gathered["mean_asl"]).sum())},
+               "finite_mean_asl_rank0": int(np.isfinite(mem["1d_ht"]["mean_asl"]).sum()),
+               "gpu_launches": int(launches), "launches_setup_to_moments": int(l0 - launches0),
+               "max_mem_gb_rank0": torch.cuda.max_memory_allocated(dev) / 1e9, "clocks": clk,
+               "host_profile_rank0": getattr(st, "host_profile", None)}
+        emit(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     guard_stdout()
-    if args.impl == "reference":
+    if args.workload != "c2":
+        run_workload(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

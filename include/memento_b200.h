@@ -222,6 +222,9 @@ int mm_wls_functional(int device, void* stream, const double* covariate, const d
  * bad_flag is set when a non-finite bootstrap column is met (the caller raises).
  * gene_list (nullable) [n_gene]: launched gene i reads the row block gene_list[i] of boot / seg_good /
  * gene_id / the replay assignments; mask_id and every output are indexed by i (NULL: identity).
+ * variant 0: replay mode runs one CTA per gene; the RNG mode runs column-parallel over (gene, replicate block) --
+ * residualise, slopes (every pick drawn once for all statistics and columns), finish -- and then REQUIRES coef_ws.
+ * variant 1: the one-CTA-per-gene kernel in the RNG mode too (same Philox counters: equal results to round-off).
  * Replaces: memento/hypothesis_test.py:231-239 (_cross_coef_resampled), :273-286. */
 int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
                          const uint8_t* seg_good, const int32_t* mask_id, const double* zmat,
@@ -230,7 +233,7 @@ int mm_regress_resampled(int device, void* stream, double* boot0, double* boot1,
                          const int64_t* gene_id, const int32_t* rep_assign, const int32_t* iter_assign,
                          double* coef_ws, double* out_coef, double* out_se, double* out_asl,
                          int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag,
-                         const int32_t* gene_list);
+                         const int32_t* gene_list, int32_t variant);
 
 /* Per gene: coefficient of every bootstrap column, SE (population std of columns 1..), and the ASL:
  * approx != 0 -> two-sided normal tail; else extreme count c and (c+1)/(n+1) (out_extreme carries c

@@ -701,6 +701,215 @@ regress_resampled_kernel(ResampParams P) {
     }
 }
 
+// ------------------------------------------------------------------ resample_rep, column-parallel path (RNG mode)
+// regress_resampled_kernel above is one CTA per gene and redraws every pick for every (statistic, treatment column):
+// fine for the replay mode's handful of small cases, hopeless at eQTL scale (R = 4000 groups, T = 5: 0.56 s per gene
+// measured).  The RNG mode therefore runs as three grid-wide kernels over (gene, column block):
+//   1. residualise    y <- y - mean_W(y) - sum_c <Z_c, y>_W / |Z_c|^2 Z_c : the Z_c are W-orthogonal to each other
+//                     and to 1, so all coefficients come from ONE sweep over the column (classical Gram-Schmidt on an
+//                     orthogonal basis = the modified form the legacy kernel uses), then one update pass;
+//   2. slopes         one thread per output column j: every (slot, column) pick is drawn ONCE (same Philox counters
+//                     as the legacy kernel) and feeds the running sums of all statistics and treatment columns;
+//                     slope = (S_way - S_wa S_wy / S_w) / (S_waa - S_wa^2 / S_w), the reference's centred form
+//                     expanded (residualised operands: no cancellation to speak of);
+//   3. finish         SE / ASL per (gene, statistic, treatment column) from the stored coefficient rows.
+constexpr int kRsCov = 24;      // covariate directions per residualisation sweep
+
+__device__ __forceinline__ int build_good_list(const unsigned char* good, int R, int* s_good, int* s_n) {
+    if (threadIdx.x < 32) {     // ordered compaction by warp 0
+        const int lane = threadIdx.x;
+        int base = 0;
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            const int r = r0 + lane;
+            const bool ok = r < R && good[r];
+            const unsigned m = __ballot_sync(kFull, ok);
+            if (ok) s_good[base + __popc(m & ((1u << lane) - 1u))] = r;
+            base += __popc(m);
+        }
+        if (lane == 0) *s_n = base;
+    }
+    __syncthreads();
+    return *s_n;
+}
+
+__global__ void __launch_bounds__(kRegThreads)
+resample_residualise_kernel(ResampParams P) {
+    extern __shared__ int s_good[];
+    __shared__ double sred[kRegThreads / 32];
+    __shared__ int s_ngood;
+    const int gi = blockIdx.x, tid = threadIdx.x;
+    const int g = P.gene_list ? P.gene_list[gi] : gi;
+    const int R = P.R, Pc = P.Pc, B1 = P.B + 1, K = Pc + P.T;
+    const int ng = build_good_list(P.seg_good + (long long)g * R, R, s_good, &s_ngood);
+    if (ng == 0) return;
+    const double* Z = P.zmat + (long long)P.mask_id[gi] * R * K;
+    const double* zn = P.znorm2 + (long long)P.mask_id[gi] * Pc;
+    double wl = 0.0;
+    for (int i = tid; i < ng; i += kRegThreads) wl += P.weights[s_good[i]];
+    const double wsum = block_sum(wl, sred);
+    const int b = blockIdx.y * kRegThreads + tid;
+    if (b >= B1) return;
+    for (int s = 0; s < P.n_stat; ++s) {
+        double* col = P.boot[s] + (long long)g * R * B1 + b;
+        for (int c0 = 0; c0 == 0 || c0 < Pc; c0 += kRsCov) {
+            const int nc = min(kRsCov, Pc - c0);
+            double acc[kRsCov], mu = 0.0;
+#pragma unroll
+            for (int k = 0; k < kRsCov; ++k) acc[k] = 0.0;
+            bool finite = true;
+            for (int i = 0; i < ng; ++i) {
+                const int r = s_good[i];
+                const double y = col[(long long)r * B1];
+                const double wy = P.weights[r] * y;
+                finite = finite && isfinite(y);
+                mu += wy;
+                const double* zr = Z + (long long)r * K + c0;
+#pragma unroll
+                for (int k = 0; k < kRsCov; ++k) if (k < nc) acc[k] = fma(wy, zr[k], acc[k]);
+            }
+            if (!finite) *P.bad_flag = 1;
+            mu = c0 == 0 ? mu / wsum : 0.0;         // later chunks: the column is centred already
+#pragma unroll
+            for (int k = 0; k < kRsCov; ++k) acc[k] = (k < nc && zn[c0 + k] > 0.0) ? acc[k] / zn[c0 + k] : 0.0;
+            for (int i = 0; i < ng; ++i) {
+                const int r = s_good[i];
+                const double* zr = Z + (long long)r * K + c0;
+                double y = col[(long long)r * B1] - mu;
+#pragma unroll
+                for (int k = 0; k < kRsCov; ++k) if (k < nc) y = fma(-acc[k], zr[k], y);
+                col[(long long)r * B1] = y;
+            }
+        }
+    }
+}
+
+template <int TT>
+__global__ void __launch_bounds__(kRegThreads)
+resample_slopes_kernel(ResampParams P) {
+    extern __shared__ int s_good[];
+    __shared__ int s_ngood;
+    const int gi = blockIdx.x, tid = threadIdx.x;
+    const int g = P.gene_list ? P.gene_list[gi] : gi;
+    const int R = P.R, Pc = P.Pc, T = P.T, B = P.B, B1 = B + 1, K = Pc + T, NS = P.n_stat;
+    const int ng = build_good_list(P.seg_good + (long long)g * R, R, s_good, &s_ngood);
+    const int j = blockIdx.y * kRegThreads + tid;
+    if (ng == 0 || j >= B) return;
+    const double* Z = P.zmat + (long long)P.mask_id[gi] * R * K + Pc;
+    const double* bt0 = P.boot[0] + (long long)g * R * B1;
+    const double* bt1 = NS > 1 ? P.boot[1] + (long long)g * R * B1 : bt0;
+    const long long sid_base = (P.gene_id ? P.gene_id[g] : (long long)g) * R;
+    for (int t0 = 0; t0 < T; t0 += TT) {
+        const int tn = min(TT, T - t0);
+        double sw = 0.0, swy0 = 0.0, swy1 = 0.0, swa[TT], swaa[TT], sway0[TT], sway1[TT], a0[TT];
+        unsigned differs = 0u;
+#pragma unroll
+        for (int t = 0; t < TT; ++t) swa[t] = swaa[t] = sway0[t] = sway1[t] = a0[t] = 0.0;
+        for (int i = 0; i < ng; ++i) {
+            int ra = i, bi = 0;                 // column 0: the observed arrangement
+            if (j > 0) {
+                const long long sid = sid_base + i;
+                const uint4 r4 = Philox::round10(make_uint4((uint32_t)j, (uint32_t)sid, (uint32_t)(sid >> 32), 0x4E5Au),
+                                                 (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                ra = (int)(((unsigned long long)r4.x * (unsigned)ng) >> 32);
+                bi = 1 + (int)(((unsigned long long)r4.y * (unsigned)B) >> 32);
+            }
+            const int r = s_good[ra];
+            const double w = P.weights[r];
+            const double y0 = bt0[(long long)r * B1 + bi], y1 = bt1[(long long)r * B1 + bi];
+            const double* zr = Z + (long long)r * K + t0;
+            sw += w;
+            swy0 = fma(w, y0, swy0);
+            swy1 = fma(w, y1, swy1);
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                if (t < tn) {
+                    const double a = zr[t], wa = w * a;
+                    if (i == 0) a0[t] = a;
+                    else differs |= (a != a0[t]) ? (1u << t) : 0u;
+                    swa[t] += wa;
+                    swaa[t] = fma(wa, a, swaa[t]);
+                    sway0[t] = fma(wa, y0, sway0[t]);
+                    sway1[t] = fma(wa, y1, sway1[t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+            if (t < tn) {
+                // every pick has the same treatment value: 0/0 (see the legacy kernel)
+                const bool degenerate = !((differs >> t) & 1u);
+                const double ss = swaa[t] - swa[t] * swa[t] / sw;
+                const double c0 = degenerate ? nan("") : (sway0[t] - swa[t] * swy0 / sw) / ss;
+                P.coef_ws[(((long long)gi * NS + 0) * T + t0 + t) * B + j] = c0;
+                if (NS > 1) {
+                    const double c1 = degenerate ? nan("") : (sway1[t] - swa[t] * swy1 / sw) / ss;
+                    P.coef_ws[(((long long)gi * NS + 1) * T + t0 + t) * B + j] = c1;
+                }
+            }
+        }
+    }
+}
+
+// one CTA per (gene, statistic, treatment column): SE and ASL of the stored coefficient row
+__global__ void __launch_bounds__(kRegThreads)
+resample_finish_kernel(ResampParams P) {
+    __shared__ double sred[kRegThreads / 32];
+    __shared__ double s_mn[kRegThreads / 32], s_mx[kRegThreads / 32];
+    const int NS = P.n_stat, T = P.T, B = P.B, tid = threadIdx.x;
+    const long long o = blockIdx.x;                       // (gi * NS + s) * T + t
+    const int gi = (int)(o / (NS * T));
+    const int g = P.gene_list ? P.gene_list[gi] : gi;
+    const unsigned char* good = P.seg_good + (long long)g * P.R;
+    double ngl = 0.0;
+    for (int r = tid; r < P.R; r += kRegThreads) ngl += good[r] ? 1.0 : 0.0;
+    if (block_sum(ngl, sred) == 0.0) {
+        if (tid == 0) {
+            P.out_coef[o] = nan(""); P.out_se[o] = nan(""); P.out_asl[o] = nan("");
+            P.out_extreme[o] = -1; P.out_nnull[o] = 0;
+        }
+        return;
+    }
+    const double* row = P.coef_ws + o * B;
+    const double stat = row[0], astat = fabs(stat);
+    double sum = 0, sq = 0, vmin = INFINITY, vmax = -INFINITY;
+    int hi = 0, lo = 0, cnt = 0;
+    for (int j = tid; j < B; j += kRegThreads) {
+        const double c = row[j];
+        if (!isfinite(c)) continue;        // degenerate resample (reference: dropped by isfinite / nanstd)
+        vmin = fmin(vmin, c); vmax = fmax(vmax, c);
+        if (j > 0) {
+            const double d = c - stat;
+            sum += d; sq = fma(d, d, sq); hi += (d > astat); lo += (d < -astat); ++cnt;
+        }
+    }
+    sum = block_sum(sum, sred);
+    sq = block_sum(sq, sred);
+    const int ext = (int)(block_sum((double)(hi + lo), sred) + 0.5);
+    const int n = (int)(block_sum((double)cnt, sred) + 0.5);
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        vmin = fmin(vmin, __shfl_xor_sync(kFull, vmin, w));
+        vmax = fmax(vmax, __shfl_xor_sync(kFull, vmax, w));
+    }
+    if ((tid & 31) == 0) { s_mn[tid >> 5] = vmin; s_mx[tid >> 5] = vmax; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kRegThreads / 32; ++w) { vmin = fmin(vmin, s_mn[w]); vmax = fmax(vmax, s_mx[w]); }
+        double mu = sum / n, var = sq / n - mu * mu;
+        if (var < 0) var = 0;
+        const double sd = sqrt(var);
+        double asl;
+        int extreme = -1;
+        if (!(vmin < vmax)) asl = nan("");
+        else if (P.approx) {
+            const double k2 = 1.0 / (sd * 1.4142135623730951);
+            asl = 0.5 * erfc((astat - mu) * k2) + 0.5 * erfc((astat + mu) * k2);
+        } else { extreme = ext; asl = (double)(ext + 1) / (double)(n + 1); }
+        P.out_coef[o] = stat; P.out_se[o] = sd; P.out_asl[o] = asl;
+        P.out_extreme[o] = extreme; P.out_nnull[o] = n;
+    }
+}
+
 }  // namespace mm
 
 using namespace mm;
@@ -806,7 +1015,7 @@ MM_EXPORT int mm_regress_resampled(int device, void* stream, double* boot0, doub
                                    const int64_t* gene_id, const int32_t* rep_assign, const int32_t* iter_assign,
                                    double* coef_ws, double* out_coef, double* out_se, double* out_asl,
                                    int32_t* out_extreme, int32_t* out_nnull, int32_t* bad_flag,
-                                   const int32_t* gene_list) {
+                                   const int32_t* gene_list, int32_t variant) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_gene >= 0 && R > 0 && T > 0 && num_boot > 1 && n_cov >= 0, "n_gene/R/T/num_boot/n_cov");
     if (n_gene == 0) return 0;
@@ -822,8 +1031,27 @@ MM_EXPORT int mm_regress_resampled(int device, void* stream, double* boot0, doub
     P.iter_assign = iter_assign; P.coef_ws = coef_ws; P.out_coef = out_coef; P.out_se = out_se; P.out_asl = out_asl;
     P.out_extreme = out_extreme; P.out_nnull = out_nnull; P.bad_flag = bad_flag;
     size_t smem = (size_t)R * sizeof(int);
-    if (smem > 48 * 1024)
-        MM_CUDA(cudaFuncSetAttribute(regress_resampled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    regress_resampled_kernel<<<n_gene, kRegThreads, smem, (cudaStream_t)stream>>>(P);
-    return check_launch("mm_regress_resampled");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool legacy = rep_assign != nullptr || variant == 1;
+    if (legacy) {       // replay mode (explicit assignments) and A/B checks: one CTA per gene
+        if (smem > 48 * 1024)
+            MM_CUDA(cudaFuncSetAttribute(regress_resampled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        regress_resampled_kernel<<<n_gene, kRegThreads, smem, st>>>(P);
+        return check_launch("mm_regress_resampled");
+    }
+    MM_REQUIRE(coef_ws, "the column-parallel path needs coef_ws [n_gene][n_stat][T][num_boot]");
+    MM_REQUIRE(n_gene <= 65535 * 32, "n_gene");
+#define MM_SMEM_ATTR(k) if (smem > 48 * 1024) MM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+    MM_SMEM_ATTR(resample_residualise_kernel);
+    resample_residualise_kernel<<<dim3(n_gene, (num_boot + 1 + kRegThreads - 1) / kRegThreads), kRegThreads, smem, st>>>(P);
+    if (int s = check_launch("resample_residualise")) return s;
+    const dim3 grid2(n_gene, (num_boot + kRegThreads - 1) / kRegThreads);
+    if (T == 1) { MM_SMEM_ATTR(resample_slopes_kernel<1>); resample_slopes_kernel<1><<<grid2, kRegThreads, smem, st>>>(P); }
+    else if (T == 2) { MM_SMEM_ATTR(resample_slopes_kernel<2>); resample_slopes_kernel<2><<<grid2, kRegThreads, smem, st>>>(P); }
+    else if (T <= 4) { MM_SMEM_ATTR(resample_slopes_kernel<4>); resample_slopes_kernel<4><<<grid2, kRegThreads, smem, st>>>(P); }
+    else { MM_SMEM_ATTR(resample_slopes_kernel<8>); resample_slopes_kernel<8><<<grid2, kRegThreads, smem, st>>>(P); }
+#undef MM_SMEM_ATTR
+    if (int s = check_launch("resample_slopes")) return s;
+    resample_finish_kernel<<<(unsigned)((long long)n_gene * P.n_stat * T), kRegThreads, 0, st>>>(P);
+    return check_launch("resample_finish");
 }

@@ -34,7 +34,7 @@ SIGNATURES = {
     "mm_fill_log": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _u64, _vp, _vp, _vp, _vp, _vp],
     "mm_wls_functional": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "mm_regress_resampled": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _u64, _vp, _vp,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32],
     "mm_pair_unique": [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp],
     "mm_pair_prepare": [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],

@@ -15,6 +15,7 @@ from .device import ENTRY_BYTES, NULL_TIMER
 N_TABLE_MAX = 16384      # largest multiplicity with a universal Poisson inversion table
 REGRESS_MIN_CTAS = 592   # mm_regress_asl: CTAs wanted per launch (4 per SM)
 SEG_INFO_BYTES = 48      # sizeof(SegInfo) in csrc/bootstrap.cu
+RESAMPLED_VARIANT = 0    # mm_regress_resampled: 0 = column-parallel kernels in the RNG mode, 1 = one CTA per gene (A/B tests)
 MIN_ACCEPT = 0.2         # Poissonised sampler: segments below this acceptance rate go to the direct / chain samplers
 _TABLES = {}             # per device: (offsets tensor, pool tensor)
 
@@ -171,7 +172,8 @@ def _regress_launch(device, boot0, boot1, seg_good, R, num_boot, approx, want_co
     out_ext = torch.empty(n_out, dtype=torch.int32, device=device)
     out_nn = torch.empty(n_out, dtype=torch.int32, device=device)
     n_cols = num_boot if resampled else num_boot + 1
-    coef_ws = torch.empty(n_out * n_cols, dtype=torch.float64, device=device) if want_coef_rows else None
+    # the column-parallel resample_rep path keeps its coefficient rows in this workspace whatever the caller wants
+    coef_ws = torch.empty(n_out * n_cols, dtype=torch.float64, device=device) if (want_coef_rows or resampled) else None
     mask_id = torch.as_tensor(np.ascontiguousarray(key_id, dtype=np.int32), device=device)
     glist = None if genes is None else torch.as_tensor(np.ascontiguousarray(genes, dtype=np.int32), device=device)
     ev = timer.start()
@@ -184,7 +186,7 @@ def _regress_launch(device, boot0, boot1, seg_good, R, num_boot, approx, want_co
             it_a = torch.as_tensor(np.ascontiguousarray(assignments[1], dtype=np.int32), device=device)
         _lib.call("mm_regress_resampled", device, boot0, boot1, seg_good, mask_id, zmat, znorm2, w_d, n_gene, R,
                   P, T, num_boot, 1 if approx else 0, seed, gene_id, rep_a, it_a, coef_ws,
-                  out_coef, out_se, out_asl, out_ext, out_nn, bad, glist)
+                  out_coef, out_se, out_asl, out_ext, out_nn, bad, glist, RESAMPLED_VARIANT)
         if int(bad.item()) != 0:
             raise _lib.MementoCudaError("resample_rep: a bootstrap column is non-finite in a valid group; the "
                                         "device path does not drop columns in this mode")

@@ -285,3 +285,27 @@ def test_unsorted_rows_take_the_generic_relayout():
         for k in range(3):
             assert_close(ad.uns["memento"]["1d_moments"][grp][k], ref.uns["memento"]["1d_moments"][grp][k], 1e-12,
                          what="1d_moments[%d]" % k)
+
+
+# ----------------------------------------------------------------------------- resample_rep: the two kernel paths
+@pytest.mark.parametrize("T", [1, 3, 6])
+def test_resample_rep_column_parallel_equals_one_cta_per_gene(pair, T):
+    """mm_regress_resampled in the RNG mode: the column-parallel path (residualise / slopes / finish kernels, every
+    pick drawn once for all statistics and treatment columns; the path large designs need) draws from the same Philox
+    counters as the one-CTA-per-gene kernel that the replay tests pin on the reference, so the two agree to
+    round-off (classical vs modified Gram-Schmidt on an orthogonal basis, expanded vs centred slope sums)."""
+    from memento_b200 import engine
+    g, _ = pair
+    cov, tr = _designs(g.uns["memento"]["groups"])
+    tr = tr.iloc[:, :T]
+    out = {}
+    for variant in (0, 1):
+        engine.RESAMPLED_VARIANT = variant
+        try:
+            memento.ht_1d_moments(g, cov, tr, num_boot=700, resampling="bootstrap", approx=True, resample_rep=True, seed=6)
+        finally:
+            engine.RESAMPLED_VARIANT = 0
+        out[variant] = {k: g.uns["memento"]["1d_ht"][k].copy() for k in HT_KEYS}
+    assert np.isfinite(out[1]["mean_asl"]).sum() > 50 * T
+    for k in HT_KEYS:
+        assert_close(out[0][k], out[1][k], 1e-8, atol=1e-10, what="%s T=%d" % (k, T))
