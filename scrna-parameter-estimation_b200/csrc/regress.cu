@@ -749,35 +749,60 @@ resample_residualise_kernel(ResampParams P) {
     const double wsum = block_sum(wl, sred);
     const int b = blockIdx.y * kRegThreads + tid;
     if (b >= B1) return;
+    // A thread walks its column down the rows (stride B1: coalesced across the warp).  The walk is latency bound
+    // unless several rows are in flight per thread, so rows go in batches of kRsBatch independent loads.
+    constexpr int kRsBatch = 8;
+    const double* __restrict__ wts = P.weights;
     for (int s = 0; s < P.n_stat; ++s) {
-        double* col = P.boot[s] + (long long)g * R * B1 + b;
+        double* __restrict__ col = P.boot[s] + (long long)g * R * B1 + b;
         for (int c0 = 0; c0 == 0 || c0 < Pc; c0 += kRsCov) {
             const int nc = min(kRsCov, Pc - c0);
             double acc[kRsCov], mu = 0.0;
 #pragma unroll
             for (int k = 0; k < kRsCov; ++k) acc[k] = 0.0;
             bool finite = true;
-            for (int i = 0; i < ng; ++i) {
-                const int r = s_good[i];
-                const double y = col[(long long)r * B1];
-                const double wy = P.weights[r] * y;
-                finite = finite && isfinite(y);
-                mu += wy;
-                const double* zr = Z + (long long)r * K + c0;
+            for (int i0 = 0; i0 < ng; i0 += kRsBatch) {
+                double y[kRsBatch];
+                int rr[kRsBatch];
 #pragma unroll
-                for (int k = 0; k < kRsCov; ++k) if (k < nc) acc[k] = fma(wy, zr[k], acc[k]);
+                for (int u = 0; u < kRsBatch; ++u) {
+                    rr[u] = s_good[min(i0 + u, ng - 1)];
+                    y[u] = col[(long long)rr[u] * B1];
+                }
+#pragma unroll
+                for (int u = 0; u < kRsBatch; ++u) {
+                    if (i0 + u < ng) {
+                        const double wy = wts[rr[u]] * y[u];
+                        finite = finite && isfinite(y[u]);
+                        mu += wy;
+                        const double* __restrict__ zr = Z + (long long)rr[u] * K + c0;
+#pragma unroll
+                        for (int k = 0; k < kRsCov; ++k) if (k < nc) acc[k] = fma(wy, zr[k], acc[k]);
+                    }
+                }
             }
             if (!finite) *P.bad_flag = 1;
             mu = c0 == 0 ? mu / wsum : 0.0;         // later chunks: the column is centred already
 #pragma unroll
             for (int k = 0; k < kRsCov; ++k) acc[k] = (k < nc && zn[c0 + k] > 0.0) ? acc[k] / zn[c0 + k] : 0.0;
-            for (int i = 0; i < ng; ++i) {
-                const int r = s_good[i];
-                const double* zr = Z + (long long)r * K + c0;
-                double y = col[(long long)r * B1] - mu;
+            for (int i0 = 0; i0 < ng; i0 += kRsBatch) {
+                double y[kRsBatch];
+                int rr[kRsBatch];
 #pragma unroll
-                for (int k = 0; k < kRsCov; ++k) if (k < nc) y = fma(-acc[k], zr[k], y);
-                col[(long long)r * B1] = y;
+                for (int u = 0; u < kRsBatch; ++u) {
+                    rr[u] = s_good[min(i0 + u, ng - 1)];
+                    y[u] = col[(long long)rr[u] * B1];
+                }
+#pragma unroll
+                for (int u = 0; u < kRsBatch; ++u) {
+                    if (i0 + u < ng) {
+                        const double* __restrict__ zr = Z + (long long)rr[u] * K + c0;
+                        double v = y[u] - mu;
+#pragma unroll
+                        for (int k = 0; k < kRsCov; ++k) if (k < nc) v = fma(-acc[k], zr[k], v);
+                        col[(long long)rr[u] * B1] = v;
+                    }
+                }
             }
         }
     }
@@ -804,32 +829,48 @@ resample_slopes_kernel(ResampParams P) {
         unsigned differs = 0u;
 #pragma unroll
         for (int t = 0; t < TT; ++t) swa[t] = swaa[t] = sway0[t] = sway1[t] = a0[t] = 0.0;
-        for (int i = 0; i < ng; ++i) {
-            int ra = i, bi = 0;                 // column 0: the observed arrangement
-            if (j > 0) {
-                const long long sid = sid_base + i;
-                const uint4 r4 = Philox::round10(make_uint4((uint32_t)j, (uint32_t)sid, (uint32_t)(sid >> 32), 0x4E5Au),
-                                                 (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-                ra = (int)(((unsigned long long)r4.x * (unsigned)ng) >> 32);
-                bi = 1 + (int)(((unsigned long long)r4.y * (unsigned)B) >> 32);
-            }
-            const int r = s_good[ra];
-            const double w = P.weights[r];
-            const double y0 = bt0[(long long)r * B1 + bi], y1 = bt1[(long long)r * B1 + bi];
-            const double* zr = Z + (long long)r * K + t0;
-            sw += w;
-            swy0 = fma(w, y0, swy0);
-            swy1 = fma(w, y1, swy1);
+        // picks go in batches: the Philox blocks and the two random gathers of a batch are independent, which keeps
+        // several DRAM sectors in flight per thread (the loop is otherwise one dependent chain per pick)
+        constexpr int kPickBatch = 4;
+        for (int i0 = 0; i0 < ng; i0 += kPickBatch) {
+            int rr[kPickBatch];
+            double y0[kPickBatch], y1[kPickBatch], wv[kPickBatch];
 #pragma unroll
-            for (int t = 0; t < TT; ++t) {
-                if (t < tn) {
-                    const double a = zr[t], wa = w * a;
-                    if (i == 0) a0[t] = a;
-                    else differs |= (a != a0[t]) ? (1u << t) : 0u;
-                    swa[t] += wa;
-                    swaa[t] = fma(wa, a, swaa[t]);
-                    sway0[t] = fma(wa, y0, sway0[t]);
-                    sway1[t] = fma(wa, y1, sway1[t]);
+            for (int u = 0; u < kPickBatch; ++u) {
+                const int i = min(i0 + u, ng - 1);
+                int ra = i, bi = 0;             // column 0: the observed arrangement
+                if (j > 0) {
+                    const long long sid = sid_base + i;
+                    const uint4 r4 = Philox::round10(make_uint4((uint32_t)j, (uint32_t)sid, (uint32_t)(sid >> 32), 0x4E5Au),
+                                                     (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                    ra = (int)(((unsigned long long)r4.x * (unsigned)ng) >> 32);
+                    bi = 1 + (int)(((unsigned long long)r4.y * (unsigned)B) >> 32);
+                }
+                rr[u] = s_good[ra];
+                y0[u] = bt0[(long long)rr[u] * B1 + bi];
+                y1[u] = bt1[(long long)rr[u] * B1 + bi];
+                wv[u] = P.weights[rr[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < kPickBatch; ++u) {
+                if (i0 + u < ng) {
+                    const double w = wv[u];
+                    const double* zr = Z + (long long)rr[u] * K + t0;
+                    sw += w;
+                    swy0 = fma(w, y0[u], swy0);
+                    swy1 = fma(w, y1[u], swy1);
+#pragma unroll
+                    for (int t = 0; t < TT; ++t) {
+                        if (t < tn) {
+                            const double a = zr[t], wa = w * a;
+                            if (i0 + u == 0) a0[t] = a;
+                            else differs |= (a != a0[t]) ? (1u << t) : 0u;
+                            swa[t] += wa;
+                            swaa[t] = fma(wa, a, swaa[t]);
+                            sway0[t] = fma(wa, y0[u], sway0[t]);
+                            sway1[t] = fma(wa, y1[u], sway1[t]);
+                        }
+                    }
                 }
             }
         }

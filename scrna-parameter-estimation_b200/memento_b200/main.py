@@ -304,8 +304,12 @@ def _bin_size_factor(adata):
     approx_sf[is_max] = max_sf
     mem["all_approx_size_factor"] = approx_sf
     codes = st.codes
-    mem["approx_size_factor"] = {g: approx_sf[codes == r] for r, g in enumerate(mem["groups"])}
-    mem["size_factor"] = {g: size_factor[codes == r] for r, g in enumerate(mem["groups"])}
+    # per-group views through the group-sorted order (stable: a group's cells keep their original order, so
+    # approx_sf[order[lo:hi]] == approx_sf[codes == r]) -- R boolean scans of all cells cost seconds at R = 4000
+    gs = st.group_start
+    approx_sorted, sf_sorted = approx_sf[st.order], size_factor[st.order]
+    mem["approx_size_factor"] = {g: approx_sorted[gs[r]:gs[r + 1]] for r, g in enumerate(mem["groups"])}
+    mem["size_factor"] = {g: sf_sorted[gs[r]:gs[r + 1]] for r, g in enumerate(mem["groups"])}
     # device side: bin id per cell (the max cells get their own id) + 1/approx_sf per bin id
     nb = binned[0].shape[0]
     cell_bin = (bin_idx - 1).astype(np.int64)
@@ -316,7 +320,9 @@ def _bin_size_factor(adata):
     st.cell_bin = to_device(cell_bin[st.order].astype(np.uint8), st.device)
     st.inv_sf_sorted = to_device(1.0 / size_factor[st.order], st.device, np.float64)
     R = len(mem["groups"])
-    st.n_bins_present = np.array([np.unique(cell_bin[codes == r]).size for r in range(R)], dtype=np.int32)
+    present = np.zeros((R, nb + 1), dtype=bool)
+    present[codes, cell_bin] = True
+    st.n_bins_present = present.sum(axis=1).astype(np.int32)
 
 
 # --------------------------------------------------------------------------- compute_1d_moments
@@ -361,16 +367,15 @@ def compute_1d_moments(adata, inplace=True, min_perc_group=0.7, filter_genes=Tru
         g_mean = st.dist.all_gather_concat(mean)[0]
         g_var = st.dist.all_gather_concat(var)[0]
         g_rvf = st.dist.all_gather_concat(rv_filter)[0]
-    mean_cat = np.concatenate([g_mean[g_rvf[:, r], r] for r in range(R)])
-    var_cat = np.concatenate([g_var[g_rvf[:, r], r] for r in range(R)])
+    mean_cat = g_mean.T[g_rvf.T]          # group-major, genes ascending inside a group: the reference's concatenation
+    var_cat = g_var.T[g_rvf.T]
     pooled = _fit_mv(mean_cat, var_cat)
     mem["mv_regressor"] = {"all": pooled}
     for g in groups:
         mem["mv_regressor"][g] = pooled.copy()
-    mem["1d_moments"] = {}
-    for r, g in enumerate(groups):                                            # :248-255
-        m, v = mean[:, r].copy(), var[:, r].copy()
-        mem["1d_moments"][g] = [m, v, _residual_variance(m, v, mem["mv_regressor"][g])]
+    mean_t, var_t = np.ascontiguousarray(mean.T), np.ascontiguousarray(var.T)           # (R, G)
+    rv_t = _residual_variance(mean_t, var_t, pooled)                          # :248-255, every group has the pooled fit
+    mem["1d_moments"] = {g: [mean_t[r], var_t[r], rv_t[r]] for r, g in enumerate(groups)}
     if gene_list is not None:                                                 # :258-271
         assert type(gene_list) == list
         given = np.isin(adata.var.index.values, gene_list)
