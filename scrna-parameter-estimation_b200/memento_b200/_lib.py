@@ -18,6 +18,7 @@ _i32, _i64, _u64, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 SIGNATURES = {
     "mm_csr_row_sums": [_vp, _vp, _vp, _i64, _vp, _vp],
     "mm_seg_moments": [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
+    "mm_seg_moments_windows": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "mm_validate_counts": [_vp, _i64, _vp],
     "mm_relayout_count": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "mm_relayout_fill": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32],
@@ -46,7 +47,7 @@ SIGNATURES = {
 }
 
 # host-only helpers (no leading device / stream arguments)
-HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp], "mm_launch_count": []}
+HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp], "mm_launch_count": [], "mm_reload_tuning": []}
 
 _lib = None
 
@@ -102,6 +103,11 @@ def call(name, device, *args):
 def launch_count():
     """Kernels launched by the library in this process so far (counted at every launch site in csrc/)."""
     return int(load().mm_launch_count())
+
+
+def reload_tuning():
+    """Re-read the MM_* tuning variables (they are otherwise read once, at library load).  Tests / tuning scripts."""
+    load().mm_reload_tuning()
 
 
 def poisson_table_offsets(n_max):

@@ -19,3 +19,19 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def tuning(monkeypatch):
+    """``tuning(MM_MOMENTS_KERNEL="tile", ...)``: set MM_* variables and make the library re-read them (they are
+    read once at load); the library goes back to the plain environment when the test ends."""
+    from memento_b200 import _lib
+
+    def apply(**env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, str(v))
+        _lib.reload_tuning()
+
+    yield apply
+    monkeypatch.undo()
+    _lib.reload_tuning()

@@ -41,22 +41,28 @@ def test_relayout_checksums_full_size(full):
     np.testing.assert_array_equal(col.cpu().numpy(), np.asarray(X.sum(axis=0)).ravel().astype(np.float64))
 
 
-def test_moment_kernels_agree_full_size(full, monkeypatch):
+def test_moment_kernels_agree_full_size(full, tuning, monkeypatch):
     ad, X, seg = full
     st = ad.uns["memento"]["_b200"]
     outs = {}
     for kern in ("stream", "stream_l1", "tile"):
-        monkeypatch.setenv("MM_MOMENTS_KERNEL", kern)
+        tuning(MM_MOMENTS_KERNEL=kern)
         a = seg.moments(st.inv_sf_sorted).cpu().numpy()
         b = seg.moments(st.inv_sf_sorted).cpu().numpy()
         np.testing.assert_array_equal(a, b)                  # deterministic
         outs[kern] = a
     monkeypatch.delenv("MM_MOMENTS_KERNEL")
+    dev_mod._lib.reload_tuning()
     big = torch.zeros(seg.nnz // 4096 + 2, dtype=torch.int32, device=seg.device)
     out = torch.empty(5 * seg.n_seg, dtype=torch.float64, device=seg.device)
     dev_mod._lib.call("mm_seg_moments", seg.device, seg.vals, seg.rows, seg.seg_ptr, seg.n_seg, seg.nnz,
                       st.inv_sf_sorted, int(st.inv_sf_sorted.numel()), out, big, None, None)
     outs["per_segment"] = out.view(5, seg.G, seg.R).cpu().numpy()
+    dev_mod.MOMENTS_KERNEL = "windows"          # the row-window kernel (a group's 1/sf slice in shared memory)
+    try:
+        outs["windows"] = seg.moments(st.inv_sf_sorted).cpu().numpy()
+    finally:
+        dev_mod.MOMENTS_KERNEL = "auto"
     ref = outs["per_segment"]
     assert ref[0].sum() == float(X.data.astype(np.float64).sum())      # checksum of checksums (exact: integers)
     for kern, a in outs.items():

@@ -84,46 +84,102 @@ def test_seg_moments_fallback_kernel(name):
 
 @pytest.mark.parametrize("kernel", ["stream", "stream_l1", "tile"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_seg_moments_every_kernel(kernel, name, monkeypatch):
+def test_seg_moments_every_kernel(kernel, name, tuning):
     """Each streaming kernel on every structure, whatever the size-based choice would have been."""
-    monkeypatch.setenv("MM_MOMENTS_KERNEL", kernel)
+    tuning(MM_MOMENTS_KERNEL=kernel)
     _run(CASES[name], seed=5)
 
 
 @pytest.mark.parametrize("regime", ["0", "1"])
-def test_seg_moments_tile_regimes(regime, monkeypatch):
-    monkeypatch.setenv("MM_MOMENTS_KERNEL", "tile")
-    monkeypatch.setenv("MM_MOMENTS_REGIME", regime)
+def test_seg_moments_tile_regimes(regime, tuning):
+    tuning(MM_MOMENTS_KERNEL="tile", MM_MOMENTS_REGIME=regime)
     for name in ("mixed", "exact_tile_edges", "multi_tile_segments", "many_small"):
         _run(CASES[name], seed=6)
 
 
 @pytest.mark.parametrize("name", ["exact_span_edges", "window_of_31", "multi_tile_segments", "ragged_end3", "mixed"])
-def test_seg_moments_stream_single_span_chunks(name, monkeypatch):
-    monkeypatch.setenv("MM_MOMENTS_KERNEL", "stream")
-    monkeypatch.setenv("MM_MOMENTS_CHUNK", "1")
+def test_seg_moments_stream_single_span_chunks(name, tuning):
+    tuning(MM_MOMENTS_KERNEL="stream", MM_MOMENTS_CHUNK=1)
     _run(CASES[name], seed=8)
 
 
 @pytest.mark.parametrize("name", ["exact_span_edges", "exact_chunk_edges", "window_of_31", "ragged_end3", "mixed"])
-def test_seg_moments_stream_short_spans(name, monkeypatch):
-    monkeypatch.setenv("MM_MOMENTS_KERNEL", "stream")
-    monkeypatch.setenv("MM_MOMENTS_CHUNK", "8")
-    monkeypatch.setenv("MM_MOMENTS_THREADS", "896")
+def test_seg_moments_stream_short_spans(name, tuning):
+    tuning(MM_MOMENTS_KERNEL="stream", MM_MOMENTS_CHUNK=8, MM_MOMENTS_THREADS=896)
     _run(CASES[name], seed=9)
 
 
-def test_seg_moments_table_too_large_for_smem(monkeypatch):
-    monkeypatch.setenv("MM_MOMENTS_KERNEL", "stream")
+def test_seg_moments_table_too_large_for_smem(tuning):
+    tuning(MM_MOMENTS_KERNEL="stream")
     _run(CASES["mixed"], n_cells=40000, seed=7)
 
 
 @pytest.mark.parametrize("w", ["8", "16", "32"])
-def test_seg_moments_lane_widths(w, monkeypatch):
-    monkeypatch.setenv("MM_MOMENTS_W", w)
+def test_seg_moments_lane_widths(w, tuning):
+    tuning(MM_MOMENTS_W=w)
     _run(CASES["mixed"], seed=5, use_tiles=False)
 
 
 def test_seg_moments_empty_matrix():
     got = _run([0, 0, 0, 0])
     assert not got.any()
+
+
+# ----------------------------------------------------------------------------- row-window kernel
+def _grouped_case(n_cells, n_genes, sizes, density, seed):
+    """A group-sorted matrix with the given group sizes: rows of segment (g, r) lie in the group's row range."""
+    rng = np.random.default_rng(seed)
+    gs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    assert gs[-1] == n_cells
+    R = len(sizes)
+    lens, rows = [], []
+    for g in range(n_genes):
+        dens = density * rng.uniform(0.0, 2.0) if g % 7 else 0.0          # some empty genes
+        for r in range(R):
+            n = int(sizes[r])
+            k = int(rng.binomial(n, min(1.0, dens))) if n else 0
+            if g == 3 and n:
+                k = n                                                      # a full segment
+            lens.append(k)
+            rows.append(gs[r] + np.sort(rng.choice(n, k, replace=False)) if k else np.zeros(0, np.int64))
+    lens = np.asarray(lens, dtype=np.int64)
+    seg_ptr = np.concatenate([[0], np.cumsum(lens)])
+    rows = np.concatenate(rows).astype(np.int32)
+    vals = rng.integers(1, 40, rows.size).astype(np.float32)
+    inv_sf = 1.0 / rng.uniform(0.3, 3.0, n_cells)
+    return vals, rows, seg_ptr, inv_sf, gs
+
+
+@pytest.mark.parametrize("case", [
+    dict(n_cells=3000, n_genes=40, sizes=[1000, 0, 1500, 500], density=0.3),          # an empty group
+    dict(n_cells=20000, n_genes=25, sizes=[20000], density=0.2),                      # one group, one large window
+    dict(n_cells=70001, n_genes=12, sizes=[70001], density=0.1),                      # one group cut into 3 windows
+    dict(n_cells=65000, n_genes=10, sizes=[30000, 5, 34995], density=0.15),           # cut groups next to a tiny one
+    dict(n_cells=5000, n_genes=300, sizes=[313] * 15 + [305], density=0.25),          # C2-like: many genes, 16 groups
+    dict(n_cells=64, n_genes=3, sizes=[1, 63], density=0.9),
+])
+def test_seg_moments_window_kernel(case):
+    """mm_seg_moments_windows (a group's 1/sf slice in shared memory, one warp per (gene, window) piece) against the
+    numpy restatement and against the span / tile kernels (same sums, another order)."""
+    vals, rows, seg_ptr, inv_sf, gs = _grouped_case(seed=11, **case)
+    d = torch.device("cuda", 0)
+    R = len(case["sizes"])
+    seg = dev_mod.SegMatrix(torch.as_tensor(vals, device=d), torch.as_tensor(rows, device=d),
+                            torch.as_tensor(seg_ptr, device=d), case["n_genes"], R, case["n_cells"], gs)
+    w = torch.as_tensor(inv_sf, device=d)
+    want = _reference(vals, rows, seg_ptr, inv_sf)
+    got = {}
+    for kern in ("windows", "legacy"):
+        dev_mod.MOMENTS_KERNEL = kern
+        try:
+            a = seg.moments(w).cpu().numpy().reshape(5, -1)
+            b = seg.moments(w).cpu().numpy().reshape(5, -1)
+        finally:
+            dev_mod.MOMENTS_KERNEL = "auto"
+        np.testing.assert_array_equal(a, b)                  # deterministic
+        np.testing.assert_array_equal(a[0], want[0])
+        np.testing.assert_array_equal(a[1], want[1])
+        np.testing.assert_allclose(a[2:], want[2:], rtol=1e-12, atol=0)
+        got[kern] = a
+    plan = seg.window_plan()
+    assert plan["n_win"] >= R and plan["max_rows"] <= dev_mod.SegMatrix.WINDOW_MAX_ROWS

@@ -360,7 +360,7 @@ def test_samplers_agree_exact_moments(gpu_prepared):
     assert np.abs(ratio - 1).max() < 0.06, np.abs(ratio - 1).max()
 
 
-def test_poisson_sampler_slots_and_log_rows(gpu_prepared, monkeypatch):
+def test_poisson_sampler_slots_and_log_rows(gpu_prepared, tuning):
     """The Poissonised kernel runs several replicates per lane in lockstep (MM_BOOT_SLOTS); a replicate's random
     numbers depend on (seed, replicate, segment, attempt) only, so every slot count must give bit-identical rows.
     The log rows it writes directly (table-driven log, log rv = log var - trend) must agree with the logs of the
@@ -374,7 +374,7 @@ def test_poisson_sampler_slots_and_log_rows(gpu_prepared, monkeypatch):
     tab = engine.unique_tables(seg, dstate.design, dstate.cell_bin, 0, G, 0)
     raw = {}
     for slots in ("1", "2", "3", "4"):
-        monkeypatch.setenv("MM_BOOT_SLOTS", slots)
+        tuning(MM_BOOT_SLOTS=slots)
         m, v, _ = engine.bootstrap_tile(seg, dstate.design, tab, G, 0, B, 4321)
         torch.cuda.synchronize()
         raw[slots] = (m.cpu().numpy().reshape(n_seg, B), v.cpu().numpy().reshape(n_seg, B))
@@ -383,7 +383,7 @@ def test_poisson_sampler_slots_and_log_rows(gpu_prepared, monkeypatch):
         np.testing.assert_array_equal(raw["1"][1], raw[slots][1])
     logs = {}
     for slots in ("1", "2"):
-        monkeypatch.setenv("MM_BOOT_SLOTS", slots)
+        tuning(MM_BOOT_SLOTS=slots)
         bm = torch.full((n_seg * (B + 1),), -7.0, dtype=torch.float64, device=seg.device)
         bv = torch.full((n_seg * (B + 1),), -7.0, dtype=torch.float64, device=seg.device)
         ninv = torch.zeros(2 * n_seg, dtype=torch.int32, device=seg.device)
