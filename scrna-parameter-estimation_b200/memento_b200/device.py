@@ -122,8 +122,12 @@ MOMENTS_KERNEL = "auto"      # "auto" | "windows" | "legacy": which mm_seg_momen
 
 
 def WINDOWS_AUTO(seg, plan):
-    """auto rule of SegMatrix.use_windows beyond the piece-length test (filled in from measurements)."""
-    return seg.n_cells * 8 > 226 * 1024
+    """auto rule of SegMatrix.use_windows beyond the piece-length test.  Measured on B200
+    (profiles/r02_moments_shapes.json): the row-window kernel ties with the span kernel where the 1/sf table does not
+    fit shared memory (1 M cells x 40 groups: 3.60 vs 3.66 TB/s) and loses where it does (25 k cells x 16 groups:
+    1.5 vs 3.3 TB/s) -- the gather's shared-memory wavefronts, not its source, are the cost -- so auto never picks
+    it; it stays reachable through MOMENTS_KERNEL = "windows" for A/B runs."""
+    return False
 
 
 class SegMatrix:
