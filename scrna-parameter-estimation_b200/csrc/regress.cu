@@ -732,75 +732,108 @@ __device__ __forceinline__ int build_good_list(const unsigned char* good, int R,
     return *s_n;
 }
 
-__global__ void __launch_bounds__(kRegThreads)
+constexpr int kRsRows = 32;     // valid groups staged per tile of the residualisation
+constexpr int kRsBatch = 8;     // rows a thread keeps in flight
+
+__global__ void __launch_bounds__(kRegThreads, 2)
 resample_residualise_kernel(ResampParams P) {
     extern __shared__ int s_good[];
     __shared__ double sred[kRegThreads / 32];
     __shared__ int s_ngood;
+    // one tile of the design, shared by all columns of the CTA: weighted (sweep) or plain (update) covariate
+    // directions, zero-padded to kRsCov so that the inner loops carry no predicates, the group weights and row ids
+    __shared__ __align__(16) double s_z[kRsRows][kRsCov];
+    __shared__ double s_w[kRsRows];
+    __shared__ int s_r[kRsRows];
     const int gi = blockIdx.x, tid = threadIdx.x;
     const int g = P.gene_list ? P.gene_list[gi] : gi;
     const int R = P.R, Pc = P.Pc, B1 = P.B + 1, K = Pc + P.T;
     const int ng = build_good_list(P.seg_good + (long long)g * R, R, s_good, &s_ngood);
     if (ng == 0) return;
-    const double* Z = P.zmat + (long long)P.mask_id[gi] * R * K;
-    const double* zn = P.znorm2 + (long long)P.mask_id[gi] * Pc;
+    const double* __restrict__ Z = P.zmat + (long long)P.mask_id[gi] * R * K;
+    const double* __restrict__ zn = P.znorm2 + (long long)P.mask_id[gi] * Pc;
+    const double* __restrict__ wts = P.weights;
     double wl = 0.0;
-    for (int i = tid; i < ng; i += kRegThreads) wl += P.weights[s_good[i]];
+    for (int i = tid; i < ng; i += kRegThreads) wl += wts[s_good[i]];
     const double wsum = block_sum(wl, sred);
     const int b = blockIdx.y * kRegThreads + tid;
-    if (b >= B1) return;
-    // A thread walks its column down the rows (stride B1: coalesced across the warp).  The walk is latency bound
-    // unless several rows are in flight per thread, so rows go in batches of kRsBatch independent loads.
-    constexpr int kRsBatch = 8;
-    const double* __restrict__ wts = P.weights;
+    const bool active = b < B1;
+    // stage rows [i0, i0 + kRsRows) of the valid-group list; weighted: w_r * z_rk (for the projections) else z_rk
+    auto stage = [&](int i0, int c0, int nc, bool weighted) {
+        __syncthreads();
+        for (int idx = tid; idx < kRsRows * kRsCov; idx += kRegThreads) {
+            const int row = idx / kRsCov, k = idx % kRsCov, i = i0 + row;
+            double v = 0.0;
+            if (i < ng && k < nc) {
+                const int r = s_good[i];
+                v = Z[(long long)r * K + c0 + k];
+                if (weighted) v *= wts[r];
+            }
+            s_z[row][k] = v;
+        }
+        if (tid < kRsRows) {
+            const int i = i0 + tid;
+            s_r[tid] = s_good[i < ng ? i : ng - 1];
+            s_w[tid] = i < ng ? wts[s_r[tid]] : 0.0;
+        }
+        __syncthreads();
+    };
     for (int s = 0; s < P.n_stat; ++s) {
-        double* __restrict__ col = P.boot[s] + (long long)g * R * B1 + b;
+        double* __restrict__ col = P.boot[s] + (long long)g * R * B1 + (active ? b : 0);
         for (int c0 = 0; c0 == 0 || c0 < Pc; c0 += kRsCov) {
             const int nc = min(kRsCov, Pc - c0);
             double acc[kRsCov], mu = 0.0;
 #pragma unroll
             for (int k = 0; k < kRsCov; ++k) acc[k] = 0.0;
             bool finite = true;
-            for (int i0 = 0; i0 < ng; i0 += kRsBatch) {
-                double y[kRsBatch];
-                int rr[kRsBatch];
+            // ---- sweep: mu = <1, y>_W, acc_k = <z_k, y>_W
+            for (int i0 = 0; i0 < ng; i0 += kRsRows) {
+                stage(i0, c0, nc, true);
+                if (!active) continue;
+#pragma unroll 1
+                for (int u0 = 0; u0 < kRsRows; u0 += kRsBatch) {
+                    double y[kRsBatch];
 #pragma unroll
-                for (int u = 0; u < kRsBatch; ++u) {
-                    rr[u] = s_good[min(i0 + u, ng - 1)];
-                    y[u] = col[(long long)rr[u] * B1];
-                }
+                    for (int u = 0; u < kRsBatch; ++u) y[u] = col[(long long)s_r[u0 + u] * B1];
 #pragma unroll
-                for (int u = 0; u < kRsBatch; ++u) {
-                    if (i0 + u < ng) {
-                        const double wy = wts[rr[u]] * y[u];
-                        finite = finite && isfinite(y[u]);
-                        mu += wy;
-                        const double* __restrict__ zr = Z + (long long)rr[u] * K + c0;
+                    for (int u = 0; u < kRsBatch; ++u) {
+                        finite = finite && (isfinite(y[u]) || s_w[u0 + u] == 0.0);
+                        const double yy = s_w[u0 + u] == 0.0 ? 0.0 : y[u];       // padding rows repeat the last valid one
+                        mu = fma(s_w[u0 + u], yy, mu);
+                        const double2* zr = reinterpret_cast<const double2*>(s_z[u0 + u]);
 #pragma unroll
-                        for (int k = 0; k < kRsCov; ++k) if (k < nc) acc[k] = fma(wy, zr[k], acc[k]);
+                        for (int k = 0; k < kRsCov / 2; ++k) {
+                            const double2 z2 = zr[k];
+                            acc[2 * k] = fma(z2.x, yy, acc[2 * k]);
+                            acc[2 * k + 1] = fma(z2.y, yy, acc[2 * k + 1]);
+                        }
                     }
                 }
             }
-            if (!finite) *P.bad_flag = 1;
+            if (active && !finite) *P.bad_flag = 1;
             mu = c0 == 0 ? mu / wsum : 0.0;         // later chunks: the column is centred already
 #pragma unroll
             for (int k = 0; k < kRsCov; ++k) acc[k] = (k < nc && zn[c0 + k] > 0.0) ? acc[k] / zn[c0 + k] : 0.0;
-            for (int i0 = 0; i0 < ng; i0 += kRsBatch) {
-                double y[kRsBatch];
-                int rr[kRsBatch];
+            // ---- update: y <- y - mu - sum_k acc_k z_k
+            for (int i0 = 0; i0 < ng; i0 += kRsRows) {
+                stage(i0, c0, nc, false);
+                if (!active) continue;
+#pragma unroll 1
+                for (int u0 = 0; u0 < kRsRows; u0 += kRsBatch) {
+                    double y[kRsBatch];
 #pragma unroll
-                for (int u = 0; u < kRsBatch; ++u) {
-                    rr[u] = s_good[min(i0 + u, ng - 1)];
-                    y[u] = col[(long long)rr[u] * B1];
-                }
+                    for (int u = 0; u < kRsBatch; ++u) y[u] = col[(long long)s_r[u0 + u] * B1];
 #pragma unroll
-                for (int u = 0; u < kRsBatch; ++u) {
-                    if (i0 + u < ng) {
-                        const double* __restrict__ zr = Z + (long long)rr[u] * K + c0;
-                        double v = y[u] - mu;
+                    for (int u = 0; u < kRsBatch; ++u) {
+                        const double2* zr = reinterpret_cast<const double2*>(s_z[u0 + u]);
+                        double v0 = y[u] - mu, v1 = 0.0;
 #pragma unroll
-                        for (int k = 0; k < kRsCov; ++k) if (k < nc) v = fma(-acc[k], zr[k], v);
-                        col[(long long)rr[u] * B1] = v;
+                        for (int k = 0; k < kRsCov / 2; ++k) {
+                            const double2 z2 = zr[k];
+                            v0 = fma(-acc[2 * k], z2.x, v0);
+                            v1 = fma(-acc[2 * k + 1], z2.y, v1);
+                        }
+                        if (i0 + u0 + u < ng) col[(long long)s_r[u0 + u] * B1] = v0 + v1;
                     }
                 }
             }
@@ -810,31 +843,44 @@ resample_residualise_kernel(ResampParams P) {
 
 template <int TT>
 __global__ void __launch_bounds__(kRegThreads)
-resample_slopes_kernel(ResampParams P) {
-    extern __shared__ int s_good[];
+resample_slopes_kernel(ResampParams P, int use_tab) {
+    extern __shared__ __align__(16) int s_good[];
     __shared__ int s_ngood;
     const int gi = blockIdx.x, tid = threadIdx.x;
     const int g = P.gene_list ? P.gene_list[gi] : gi;
     const int R = P.R, Pc = P.Pc, T = P.T, B = P.B, B1 = B + 1, K = Pc + T, NS = P.n_stat;
     const int ng = build_good_list(P.seg_good + (long long)g * R, R, s_good, &s_ngood);
     const int j = blockIdx.y * kRegThreads + tid;
-    if (ng == 0 || j >= B) return;
+    if (ng == 0) return;
+    const bool active = j < B;
     const double* Z = P.zmat + (long long)P.mask_id[gi] * R * K + Pc;
     const double* bt0 = P.boot[0] + (long long)g * R * B1;
     const double* bt1 = NS > 1 ? P.boot[1] + (long long)g * R * B1 : bt0;
     const long long sid_base = (P.gene_id ? P.gene_id[g] : (long long)g) * R;
+    // per valid slot {w, a_t0 .. a_t0+tn-1}: the picks' weights and residualised treatment values come from shared
+    // memory when the table fits (they were two more DRAM sectors per pick: the bootstrap rows stream through L2)
+    double* s_tab = reinterpret_cast<double*>(s_good + ((R + 3) & ~3));
     for (int t0 = 0; t0 < T; t0 += TT) {
         const int tn = min(TT, T - t0);
+        const int ts = tn + 1;
+        if (use_tab) {
+            __syncthreads();
+            for (int idx = tid; idx < ng * ts; idx += kRegThreads) {
+                const int i = idx / ts, c = idx % ts, r = s_good[i];
+                s_tab[idx] = c == 0 ? P.weights[r] : Z[(long long)r * K + t0 + c - 1];
+            }
+            __syncthreads();
+        }
+        if (!active) continue;
         double sw = 0.0, swy0 = 0.0, swy1 = 0.0, swa[TT], swaa[TT], sway0[TT], sway1[TT], a0[TT];
         unsigned differs = 0u;
 #pragma unroll
         for (int t = 0; t < TT; ++t) swa[t] = swaa[t] = sway0[t] = sway1[t] = a0[t] = 0.0;
-        // picks go in batches: the Philox blocks and the two random gathers of a batch are independent, which keeps
+        // picks go in batches: the Philox blocks and the random gathers of a batch are independent, which keeps
         // several DRAM sectors in flight per thread (the loop is otherwise one dependent chain per pick)
         constexpr int kPickBatch = 4;
         for (int i0 = 0; i0 < ng; i0 += kPickBatch) {
-            int rr[kPickBatch];
-            double y0[kPickBatch], y1[kPickBatch], wv[kPickBatch];
+            double y0[kPickBatch], y1[kPickBatch], wv[kPickBatch], av[kPickBatch][TT];
 #pragma unroll
             for (int u = 0; u < kPickBatch; ++u) {
                 const int i = min(i0 + u, ng - 1);
@@ -846,30 +892,37 @@ resample_slopes_kernel(ResampParams P) {
                     ra = (int)(((unsigned long long)r4.x * (unsigned)ng) >> 32);
                     bi = 1 + (int)(((unsigned long long)r4.y * (unsigned)B) >> 32);
                 }
-                rr[u] = s_good[ra];
-                y0[u] = bt0[(long long)rr[u] * B1 + bi];
-                y1[u] = bt1[(long long)rr[u] * B1 + bi];
-                wv[u] = P.weights[rr[u]];
+                const int r = s_good[ra];
+                y0[u] = bt0[(long long)r * B1 + bi];
+                y1[u] = bt1[(long long)r * B1 + bi];
+                if (use_tab) {
+                    const double* tr = s_tab + ra * ts;
+                    wv[u] = tr[0];
+#pragma unroll
+                    for (int t = 0; t < TT; ++t) av[u][t] = t < tn ? tr[1 + t] : 0.0;
+                } else {
+                    wv[u] = __ldg(P.weights + r);
+                    const double* zr = Z + (long long)r * K + t0;
+#pragma unroll
+                    for (int t = 0; t < TT; ++t) av[u][t] = t < tn ? __ldg(zr + t) : 0.0;
+                }
             }
 #pragma unroll
             for (int u = 0; u < kPickBatch; ++u) {
                 if (i0 + u < ng) {
                     const double w = wv[u];
-                    const double* zr = Z + (long long)rr[u] * K + t0;
                     sw += w;
                     swy0 = fma(w, y0[u], swy0);
                     swy1 = fma(w, y1[u], swy1);
 #pragma unroll
                     for (int t = 0; t < TT; ++t) {
-                        if (t < tn) {
-                            const double a = zr[t], wa = w * a;
-                            if (i0 + u == 0) a0[t] = a;
-                            else differs |= (a != a0[t]) ? (1u << t) : 0u;
-                            swa[t] += wa;
-                            swaa[t] = fma(wa, a, swaa[t]);
-                            sway0[t] = fma(wa, y0[u], sway0[t]);
-                            sway1[t] = fma(wa, y1[u], sway1[t]);
-                        }
+                        const double a = av[u][t], wa = w * a;
+                        if (i0 + u == 0) a0[t] = a;
+                        else differs |= (a != a0[t]) ? (1u << t) : 0u;
+                        swa[t] += wa;
+                        swaa[t] = fma(wa, a, swaa[t]);
+                        sway0[t] = fma(wa, y0[u], sway0[t]);
+                        sway1[t] = fma(wa, y1[u], sway1[t]);
                     }
                 }
             }
@@ -1087,10 +1140,25 @@ MM_EXPORT int mm_regress_resampled(int device, void* stream, double* boot0, doub
     resample_residualise_kernel<<<dim3(n_gene, (num_boot + 1 + kRegThreads - 1) / kRegThreads), kRegThreads, smem, st>>>(P);
     if (int s = check_launch("resample_residualise")) return s;
     const dim3 grid2(n_gene, (num_boot + kRegThreads - 1) / kRegThreads);
-    if (T == 1) { MM_SMEM_ATTR(resample_slopes_kernel<1>); resample_slopes_kernel<1><<<grid2, kRegThreads, smem, st>>>(P); }
-    else if (T == 2) { MM_SMEM_ATTR(resample_slopes_kernel<2>); resample_slopes_kernel<2><<<grid2, kRegThreads, smem, st>>>(P); }
-    else if (T <= 4) { MM_SMEM_ATTR(resample_slopes_kernel<4>); resample_slopes_kernel<4><<<grid2, kRegThreads, smem, st>>>(P); }
-    else { MM_SMEM_ATTR(resample_slopes_kernel<8>); resample_slopes_kernel<8><<<grid2, kRegThreads, smem, st>>>(P); }
+    {
+        const int tt = T == 1 ? 1 : T == 2 ? 2 : T <= 4 ? 4 : 8;
+        const size_t list = (size_t)((R + 3) & ~3) * sizeof(int);
+        const size_t tab = (size_t)R * ((T < tt ? T : tt) + 1) * sizeof(double);
+        // measured on the 4000-group eQTL shape (T = 5): with the table the kernel is bound by the shared-memory
+        // gathers (6 conflicting LDS.64 per pick: 35 ms per 16 genes), without it by DRAM sectors (167 GB per launch at
+        // 6 TB/s: 28 ms) -- so the table is only used where it is small enough to leave several CTAs per SM
+        const int use_tab = list + tab <= 32 * 1024;
+        const size_t smem2 = use_tab ? list + tab : smem;
+#define MM_SLOPES(TTV)                                                                                                  \
+        do {                                                                                                            \
+            if (smem2 > 48 * 1024)                                                                                      \
+                MM_CUDA(cudaFuncSetAttribute(resample_slopes_kernel<TTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                             (int)smem2));                                                              \
+            resample_slopes_kernel<TTV><<<grid2, kRegThreads, smem2, st>>>(P, use_tab);                                 \
+        } while (0)
+        if (tt == 1) MM_SLOPES(1); else if (tt == 2) MM_SLOPES(2); else if (tt == 4) MM_SLOPES(4); else MM_SLOPES(8);
+#undef MM_SLOPES
+    }
 #undef MM_SMEM_ATTR
     if (int s = check_launch("resample_slopes")) return s;
     resample_finish_kernel<<<(unsigned)((long long)n_gene * P.n_stat * T), kRegThreads, 0, st>>>(P);
