@@ -9,6 +9,7 @@ per-(gene, group) moments, compression, bootstrap, regression, ASL) runs in the 
 There is no CPU fallback: without a CUDA device or the built library every call raises.
 """
 import os
+import time
 
 import numpy as np
 import pandas as pd
@@ -51,6 +52,7 @@ class DeviceState:
         self.pending_tail = None # second part of a split upload, not issued yet
         self.tail_event = None   # ... issued, to be waited for before it is read
         self.dist = None         # DistContext when the genes are sharded over ranks
+        self.host_profile = None # {section: seconds} when profiling (setup_memento(profile=True))
         self.gene_offset = 0     # global index of this rank's first gene column
 
     def __deepcopy__(self, memo):
@@ -114,6 +116,25 @@ class LazyGroupCells:
         return getattr(self.materialize(), name)
 
 
+class _Section:
+    """``with _Section(st, name):`` accumulates the wall time of a host-side section (device synchronised on both
+    sides) in ``st.host_profile`` when setup_memento was called with ``profile=True``; free otherwise."""
+
+    def __init__(self, st, name):
+        self.st, self.name = st, name
+
+    def __enter__(self):
+        if self.st.host_profile is not None:
+            torch.cuda.synchronize(self.st.device)
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if self.st.host_profile is not None:
+            torch.cuda.synchronize(self.st.device)
+            self.st.host_profile[self.name] = self.st.host_profile.get(self.name, 0.0) + time.perf_counter() - self.t0
+        return False
+
+
 def _state(adata):
     st = adata.uns["memento"].get("_b200")
     if st is None:
@@ -144,6 +165,36 @@ def _moments_from_sums(sums, n_obs, q, estimator):
 def _fit_mv(mean, var):
     keep = (mean > 0) & (var > 0)                                   # reference estimator.py:89-92
     return np.polyfit(np.log(mean[keep]), np.log(var[keep]), 2)
+
+
+FIT_BY_SUMS_MIN = 4_000_000     # (mean, var) pairs above which the trend is fitted from power sums
+
+
+def _fit_mv_sums(mean, var, dist=None):
+    """The same quadratic least-squares fit of log var on log mean as :func:`_fit_mv` (reference estimator.py:84-93),
+    from power sums instead of the design matrix: with the genes sharded over ranks every rank adds up its own
+    (mean, var) pairs and 3 + 8 numbers are all-reduced -- an all-gather of the pairs is G x R values per rank
+    (1.3 GB at 20k genes x 4000 groups: 9 s of host staging) and np.polyfit's SVD of the gathered matrix seconds
+    more.  x is centred and scaled with the global mean / spread first, so the 3 x 3 normal equations are
+    well-conditioned (agreement with np.polyfit to ~1e-12 relative on the test matrices)."""
+    keep = (mean > 0) & (var > 0)
+    x, y = np.log(mean[keep]), np.log(var[keep])
+    first = np.array([x.size, x.sum(), (x * x).sum()], dtype=np.float64)
+    if dist is not None:
+        first = dist.all_reduce_sum(first)
+    n, xbar = first[0], first[1] / first[0]
+    scale = np.sqrt(max(first[2] / n - xbar * xbar, 1e-300))
+    z = (x - xbar) / scale
+    z2 = z * z
+    sums = np.array([z.sum(), z2.sum(), (z2 * z).sum(), (z2 * z2).sum(), y.sum(), (y * z).sum(), (y * z2).sum()],
+                    dtype=np.float64)
+    if dist is not None:
+        sums = dist.all_reduce_sum(sums)
+    s1, s2, s3, s4, t0, t1, t2 = sums
+    a, b, c = np.linalg.solve(np.array([[s4, s3, s2], [s3, s2, s1], [s2, s1, n]]), np.array([t2, t1, t0]))
+    # a z^2 + b z + c with z = (x - xbar) / scale, expanded in x (highest power first, as np.polyfit)
+    a, b = a / (scale * scale), b / scale
+    return np.array([a, b - 2.0 * a * xbar, c - b * xbar + a * xbar * xbar])
 
 
 def _residual_variance(mean, var, fit):
@@ -185,6 +236,7 @@ def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_p
     mem["num_bins"] = num_bins
     st = DeviceState(dev)
     st.timer = StageTimer(dev) if profile else NULL_TIMER
+    st.host_profile = {} if profile else None
     st.dist = dist
     st.gene_offset = int(gene_offset)
     mem["_b200"] = st
@@ -193,21 +245,22 @@ def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_p
     n_cells, n_genes = X.shape
     # no need for sorted column indices: the re-layout below is a stable sort by (gene, group) over the row-major
     # nonzeros, and the row sums add integers (exact in float64 in any order)
-    st.csr = CsrOnDevice(X, dev, pinned)
-    st.h2d_bytes += st.csr.h2d_bytes
-    st.seg_all = SegMatrix.from_csr_grouped(st.csr, timer=st.timer)
+    with _Section(st, "setup_memento: upload + validate the CSR"):
+        st.csr = CsrOnDevice(X, dev, pinned)
+        st.h2d_bytes += st.csr.h2d_bytes
+    with _Section(st, "setup_memento: re-layout (all cells)"):
+        st.seg_all = SegMatrix.from_csr_grouped(st.csr, timer=st.timer)
 
     # naive size factor = raw UMI totals (main.py:55-59); moments over all cells (:62-66)
-    naive = st.csr.row_sums(None, st.timer)
-    if dist is not None:
-        naive = dist.all_reduce_sum(naive)
-    sums = st.seg_all.moments(1.0 / naive, st.timer).cpu().numpy()[:, :, 0]
+    with _Section(st, "setup_memento: row sums, moments, all-reduce"):
+        naive = st.csr.row_sums(None, st.timer)
+        if dist is not None:
+            naive = dist.all_reduce_sum(naive)
+        sums = st.seg_all.moments(1.0 / naive, st.timer).cpu().numpy()[:, :, 0]
+    t_host = time.perf_counter()
     all_m, all_v = _moments_from_sums(sums, n_cells, mem["all_q"], 0)
     all_m[sums[0] / n_cells < filter_mean_thresh] = 0                                      # :67
-    if dist is None:
-        fit = _fit_mv(all_m, all_v)
-    else:
-        fit = _fit_mv(dist.all_gather_concat(all_m)[0], dist.all_gather_concat(all_v)[0])
+    fit = _fit_mv(all_m, all_v) if dist is None else _fit_mv_sums(all_m, all_v, dist)
     rv = _residual_variance(all_m, all_v, fit)                                             # :68
     rv_all = rv if dist is None else dist.all_gather_concat(rv)[0]
     rv_ulim = np.quantile(rv_all[np.isfinite(rv_all)], trim_percent)                       # :71
@@ -216,17 +269,21 @@ def setup_memento(adata, q_column, inplace=True, filter_mean_thresh=0.07, trim_p
     mem["least_variable_genes"] = adata.var.index[mask].tolist()
 
     # size factor from the least variable genes (main.py:78-82 -> estimator.py:73-76)
-    mask_d = to_device(mask.astype(np.uint8), dev)
-    totals = st.csr.row_sums(mask_d, st.timer)
-    if dist is not None:
-        totals = dist.all_reduce_sum(totals)
-    totals = totals.cpu().numpy()
-    totals = totals + np.quantile(totals, shrinkage)
-    size_factor = totals / totals.mean()
-    adata.obs["memento_size_factor"] = size_factor
-
-    inv_sf = to_device(1.0 / size_factor, dev, np.float64)
-    sums = st.seg_all.moments(inv_sf, st.timer).cpu().numpy()[:, :, 0]
+    if st.host_profile is not None:
+        st.host_profile["setup_memento: host (trend fit, trim quantile, names)"] = time.perf_counter() - t_host
+    with _Section(st, "setup_memento: row sums, moments, all-reduce"):
+        mask_d = to_device(mask.astype(np.uint8), dev)
+        totals = st.csr.row_sums(mask_d, st.timer)
+        if dist is not None:
+            totals = dist.all_reduce_sum(totals)
+        totals = totals.cpu().numpy()
+    with _Section(st, "setup_memento: host (size-factor quantile, obs column)"):
+        totals = totals + np.quantile(totals, shrinkage)
+        size_factor = totals / totals.mean()
+        adata.obs["memento_size_factor"] = size_factor
+    with _Section(st, "setup_memento: row sums, moments, all-reduce"):
+        inv_sf = to_device(1.0 / size_factor, dev, np.float64)
+        sums = st.seg_all.moments(inv_sf, st.timer).cpu().numpy()[:, :, 0]
     all_m, all_v = _moments_from_sums(sums, n_cells, mem["all_q"], estimator)              # :86-91
     mem["all_1d_moments"] = [all_m, all_v]
     # reference quirk kept: with inplace=False the copy is not returned (main.py:39-40)
@@ -239,16 +296,31 @@ def create_groups(adata, label_columns, label_delimiter="^", inplace=True):
         adata = adata.copy()
     mem = adata.uns["memento"]
     st = _state(adata)
-    label = "sg" + label_delimiter
-    for idx, col in enumerate(label_columns):
-        label = label + adata.obs[col].astype(str)
-        if idx != len(label_columns) - 1:
-            label = label + label_delimiter
-    adata.obs["memento_group"] = label
+    t_host = time.perf_counter()
+    # 'sg' + delimiter + the label columns joined by the delimiter (reference main.py:115-119), built per GROUP, not
+    # per cell: every column is factorised on its own, the per-cell group code is the mixed-radix number of the column
+    # codes, and the strings exist once per distinct group (a million-row string concatenation + string hashing was
+    # the largest host term of create_groups).  obs['memento_group'] becomes a categorical of those strings.
+    combined = np.zeros(adata.shape[0], dtype=np.int64)
+    col_uniques = []
+    for col in label_columns:
+        c, u = pd.factorize(adata.obs[col], sort=False)
+        if (c < 0).any():
+            raise ValueError("create_groups: missing values in obs[%r]" % col)
+        combined = combined * len(u) + c
+        col_uniques.append([str(v) for v in u])
+    codes, uniq_combined = pd.factorize(combined, sort=False)               # first-appearance order (:124)
+    names = []
+    for v in uniq_combined:
+        parts = []
+        for u in reversed(col_uniques):
+            parts.append(u[int(v % len(u))])
+            v //= len(u)
+        names.append("sg" + label_delimiter + label_delimiter.join(reversed(parts)))
+    adata.obs["memento_group"] = pd.Categorical.from_codes(codes, categories=names)
     mem["label_columns"] = label_columns
     mem["label_delimiter"] = label_delimiter
-    codes, uniques = pd.factorize(adata.obs["memento_group"], sort=False)   # first-appearance order (:124)
-    mem["groups"] = [str(u) for u in uniques]
+    mem["groups"] = names
     mem["q"] = adata.obs[mem["q_column"]].values
     R = len(mem["groups"])
     codes = codes.astype(np.int32)
@@ -259,9 +331,12 @@ def create_groups(adata, label_columns, label_delimiter="^", inplace=True):
     st.order = order
     st.group_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     st.codes = codes
+    if st.host_profile is not None:
+        st.host_profile["create_groups: host (labels, factorize, stable argsort)"] = time.perf_counter() - t_host
 
     if st.csr is not None:      # hand-written counting transposition of the uploaded CSR (csrc/relayout.cu)
-        st.seg = SegMatrix.from_csr_grouped(st.csr, order, st.group_start, timer=st.timer)
+        with _Section(st, "create_groups: re-layout (grouped)"):
+            st.seg = SegMatrix.from_csr_grouped(st.csr, order, st.group_start, timer=st.timer)
         st.gene_index = np.arange(adata.shape[1])
     else:
         # create_groups called again on the same object: regroup the gene-sorted matrix of all cells.  It still has
@@ -334,14 +409,17 @@ def compute_1d_moments(adata, inplace=True, min_perc_group=0.7, filter_genes=Tru
     mem = adata.uns["memento"]
     st = _state(adata)
     if "size_factor" not in mem:
-        _bin_size_factor(adata)
+        with _Section(st, "compute_1d_moments: bin size factors"):
+            _bin_size_factor(adata)
     groups = mem["groups"]
     R = len(groups)
     estimator = _estimator_code(mem["estimator_type"])
     n_cells = np.diff(st.group_start).astype(np.float64)
     group_q = np.array([mem["group_q"][g] for g in groups])
 
-    sums = st.seg.moments(st.inv_sf_sorted, st.timer).cpu().numpy()          # (5, G, R)
+    with _Section(st, "compute_1d_moments: moment kernel + read-back"):
+        sums = st.seg.moments(st.inv_sf_sorted, st.timer).cpu().numpy()          # (5, G, R)
+    t_host = time.perf_counter()
     mean, var = _moments_from_sums(sums, n_cells[None, :], group_q[None, :], estimator)
     obs_mean = sums[0] / n_cells[None, :]
     gene_filter = (obs_mean > mem["filter_mean_thresh"]) & (var > 0)         # main.py:201-204
@@ -361,15 +439,15 @@ def compute_1d_moments(adata, inplace=True, min_perc_group=0.7, filter_genes=Tru
     mem["gene_rv_filter"] = {g: rv_filter[:, r].copy() for r, g in enumerate(groups)}
 
     # pooled mean-variance trend over the groups' (mean, var), concatenated in group order (:232-245)
-    if st.dist is None:
-        g_mean, g_var, g_rvf = mean, var, rv_filter
-    else:   # the trend is fitted on all ranks' genes, concatenated in global gene order
-        g_mean = st.dist.all_gather_concat(mean)[0]
-        g_var = st.dist.all_gather_concat(var)[0]
-        g_rvf = st.dist.all_gather_concat(rv_filter)[0]
-    mean_cat = g_mean.T[g_rvf.T]          # group-major, genes ascending inside a group: the reference's concatenation
-    var_cat = g_var.T[g_rvf.T]
-    pooled = _fit_mv(mean_cat, var_cat)
+    if st.host_profile is not None:
+        st.host_profile["compute_1d_moments: host (filters, gene selection, dicts)"] = time.perf_counter() - t_host
+    with _Section(st, "compute_1d_moments: trend fit"):
+        mean_cat = mean.T[rv_filter.T]    # group-major, genes ascending inside a group: the reference's concatenation
+        var_cat = var.T[rv_filter.T]
+        if st.dist is None and mean_cat.size < FIT_BY_SUMS_MIN:
+            pooled = _fit_mv(mean_cat, var_cat)
+        else:   # gene-sharded (the trend is that of all ranks' genes) or large: power sums, 11 numbers all-reduced
+            pooled = _fit_mv_sums(mean_cat, var_cat, st.dist)
     mem["mv_regressor"] = {"all": pooled}
     for g in groups:
         mem["mv_regressor"][g] = pooled.copy()
@@ -611,7 +689,8 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
     mem = adata.uns["memento"]
     st = _state(adata)
     if "size_factor" not in mem:
-        _bin_size_factor(adata)
+        with _Section(st, "compute_1d_moments: bin size factors"):
+            _bin_size_factor(adata)
     groups = mem["groups"]
     names = adata.var.index
     pos = pd.Series(np.arange(len(names)), index=names)

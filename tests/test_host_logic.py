@@ -52,3 +52,35 @@ def test_tile_plan_respects_grid_and_workspace_limits():
     assert engine.tile_plan_groups(4000, B, 24 << 30) == 65535 // 4000
     assert engine.tile_plan_groups(70000, B, 24 << 30) == 1                               # one gene always fits the plan
     assert engine.tile_plan_groups(16, B, 1) == 1
+
+
+def test_trend_fit_from_power_sums_equals_polyfit():
+    """main._fit_mv_sums (3 + 8 all-reduced numbers in the gene-sharded runs) against np.polyfit on the pairs
+    (reference estimator.py:84-93), including entries the reference drops (mean or variance <= 0)."""
+    from memento_b200 import main as mmain
+    rng = np.random.default_rng(4)
+    mean = np.exp(rng.normal(-1.0, 1.8, 50000))
+    var = np.exp(1.3 * np.log(mean) + 0.04 * np.log(mean) ** 2 + 0.2 + rng.normal(0, 0.5, mean.size))
+    mean[::97] = 0.0
+    var[::89] = -1.0
+    want = mmain._fit_mv(mean, var)
+    got = mmain._fit_mv_sums(mean, var)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+    # sharded: the sums of the parts are the sums of the whole
+    class TwoRanks:
+        def __init__(self, other):
+            self.other, self.calls = other, 0
+        def all_reduce_sum(self, a):
+            self.calls += 1
+            return a + self.other[self.calls - 1]
+    keep = (mean > 0) & (var > 0)
+    x, y = np.log(mean[keep]), np.log(var[keep])
+    h = x.size // 3
+    xa, ya, xb, yb = x[:h], y[:h], x[h:], y[h:]
+    n, xbar = x.size, x.mean()
+    scale = np.sqrt((x * x).mean() - xbar * xbar)
+    zb = (xb - xbar) / scale
+    other = [np.array([xb.size, xb.sum(), (xb * xb).sum()]),
+             np.array([zb.sum(), (zb ** 2).sum(), (zb ** 3).sum(), (zb ** 4).sum(), yb.sum(), (yb * zb).sum(), (yb * zb ** 2).sum()])]
+    part = mmain._fit_mv_sums(np.exp(xa), np.exp(ya), TwoRanks(other))
+    np.testing.assert_allclose(part, want, rtol=1e-9, atol=1e-11)
