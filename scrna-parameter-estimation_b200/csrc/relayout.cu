@@ -18,9 +18,9 @@
 //
 // That generic path scatters lone 4-byte stores and has one warp per chunk (round 1: 0.16 TB/s, 2.5 % of HBM).  When
 // the column indices of every CSR row ascend (scipy's canonical form) passes 1 and 3 run as a TILED transposition
-// through shared memory instead (relayout_tile_kernel): a CTA owns a chunk of <= 256 rows and walks a range of
-// 256-gene blocks.  Per block: every row's nonzeros of the block are found by walking the sorted row from where the
-// previous block ended (no search), their (gene, row) incidence goes into a 256 x 256 bit matrix in shared memory,
+// through shared memory instead (relayout_tile_kernel): a CTA owns a chunk of <= 256 rows (one per thread) and walks a
+// range of 256-gene blocks.  Per block: every row's nonzeros of the block are found by walking the sorted row from where
+// the previous block ended (no search), their (gene, row) incidence goes into a 256 x 256 bit matrix in shared memory,
 // rank of an element inside its gene's run = popcount of the lower rows' bits -- so the block's nonzeros are placed
 // in a shared staging buffer sorted by (gene, row) with no ordering constraint between warps, and go out as one
 // coalesced run per gene (chunk rows x density elements: ~240 B on the 25k x 10k matrix) instead of 4-byte scatters.
@@ -98,18 +98,15 @@ relayout_fill_kernel(RelayoutParams P, const long long* __restrict__ seg_ptr, fl
 // ------------------------------------------------------------------ tiled path (sorted column indices)
 constexpr int kTileRows = 256;       // rows per chunk (bit-matrix height); chunks may be shorter
 constexpr int kTileGenes = 256;      // genes per block (bit-matrix width)
-constexpr int kTileThreads = 512;
+constexpr int kTileThreads = 256;    // thread t <-> row t of the chunk (phases 1, 3), gene t of the block (phase 2)
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kStageCap = 12288;     // staged nonzeros per pass (96 KB); a denser block takes several passes
+constexpr int kStageCap = 6144;      // staged nonzeros per pass (48 KB); a denser block takes several passes
 
 struct TileSmem {
     unsigned mask[kTileRows / 32][kTileGenes];          // bit (row & 31) of word [row >> 5][gene]
     unsigned short wpre[kTileRows / 32][kTileGenes];    // nonzeros of the gene in the lower row words
     int off[kTileGenes + 1];                            // exclusive scan of the block's per-gene counts
     int wsum[kTileWarps];
-    long long cur[kTileRows];                           // next unread nonzero of every row
-    long long nxt[kTileRows];                           // ... after the current block
-    long long hi[kTileRows];                            // end of the row
     float sval[kStageCap];
     int srow[kStageCap];
 };
@@ -117,6 +114,10 @@ struct TileSmem {
 // grid = (n_chunks, n_split): CTA (c, s) handles the gene blocks [s * per, (s + 1) * per) of chunk c.
 // kFill == false: per-chunk per-gene counts -> cnt[c][gene];  kFill == true: cnt holds the exclusive prefix over the
 // group's chunks (relayout_scan_kernel) and the nonzeros are written to their final positions.
+//
+// Every THREAD walks its own row (round 2: one warp per row with 32-index loads was a chain of dependent loads per
+// warp -- 16 rows x 2 loads x ~1 us per block -- and ran at 0.4 TB/s; a lane per row keeps 256 independent loads in
+// flight per CTA, the 32-byte sectors a lane walks through stay in L1 between its consecutive 4-byte loads).
 template <bool kFill>
 __global__ void __launch_bounds__(kTileThreads)
 relayout_tile_kernel(RelayoutParams P, int blocks_per_cta, const long long* __restrict__ seg_ptr,
@@ -132,58 +133,59 @@ relayout_tile_kernel(RelayoutParams P, int blocks_per_cta, const long long* __re
     const int grp = P.chunk_group[chunk];
     int* cnt = P.cnt + (long long)chunk * P.n_genes;
 
-    // row extents; the first block's start by binary search (the column indices of a row ascend)
-    for (int rl = tid; rl < n_rows; rl += kTileThreads) {
-        const long long cell = P.order ? P.order[r0 + rl] : r0 + rl;
-        long long lo = P.indptr[cell];
-        const long long hi = P.indptr[cell + 1];
+    // this thread's row: extent, and the first block's start by binary search (the column indices of a row ascend)
+    long long cur = 0, row_hi = 0;
+    if (tid < n_rows) {
+        const long long cell = P.order ? P.order[r0 + tid] : r0 + tid;
+        cur = P.indptr[cell];
+        row_hi = P.indptr[cell + 1];
         if (b_lo > 0) {
             const int g0 = b_lo * kTileGenes;
-            long long a = lo, b = hi;
+            long long a = cur, b = row_hi;
             while (a < b) {
                 const long long m = (a + b) >> 1;
                 if (__ldg(P.indices + m) < g0) a = m + 1; else b = m;
             }
-            lo = a;
+            cur = a;
         }
-        S.cur[rl] = lo;
-        S.hi[rl] = hi;
     }
     for (int i = tid; i < (kTileRows / 32) * kTileGenes; i += kTileThreads) (&S.mask[0][0])[i] = 0u;
     __syncthreads();
+    const unsigned bit = 1u << (tid & 31), below = bit - 1u;
+    const int w_row = tid >> 5;
 
     for (int b = b_lo; b < b_hi; ++b) {
         const int g0 = b * kTileGenes, g1 = min(P.n_genes, g0 + kTileGenes);
-        // ---- phase 1: incidence bits
-        for (int rl = warp; rl < n_rows; rl += kTileWarps) {
-            long long p = S.cur[rl];
-            const long long hi = S.hi[rl];
-            const unsigned bit = 1u << (rl & 31);
-            unsigned* mrow = S.mask[rl >> 5];
-            while (true) {
-                const long long e = p + lane;
-                const int idx = e < hi ? __ldg(P.indices + e) : 0x7fffffff;
-                const bool in = idx < g1;
-                if (in && idx >= g0) atomicOr(mrow + (idx - g0), bit);
-                else if (in && P.err) *P.err = 1;           // an earlier block's gene after a later one: not sorted
-                const int n_in = __popc(__ballot_sync(kFull, in));
-                p += n_in;
-                if (n_in < 32) break;
+        // ---- phase 1: incidence bits of the block, one row per thread
+        // (128-bit loads once the position is 16-byte aligned: a lane's 4-byte loads would fetch every 32-byte
+        // sector eight times over)
+        long long nxt = cur;
+        {
+            auto visit = [&](int idx) -> bool {             // false: the row has left the block
+                if (idx >= g1) return false;
+                if (idx >= g0) atomicOr(&S.mask[w_row][idx - g0], bit);
+                else if (P.err) *P.err = 1;                 // an earlier block's gene after a later one: not sorted
+                ++nxt;
+                return true;
+            };
+            bool in = true;
+            while (in && nxt < row_hi && (nxt & 3)) in = visit(__ldg(P.indices + nxt));
+            while (in && nxt + 4 <= row_hi) {
+                const int4 q = __ldg(reinterpret_cast<const int4*>(P.indices + nxt));
+                in = visit(q.x) && visit(q.y) && visit(q.z) && visit(q.w);
             }
-            if (lane == 0) S.nxt[rl] = p;
+            while (in && nxt < row_hi) in = visit(__ldg(P.indices + nxt));
         }
         __syncthreads();
-        // ---- phase 2: per-gene counts, word prefixes, exclusive scan over the block's genes
+        // ---- phase 2: per-gene counts, word prefixes, exclusive scan over the block's genes (thread = gene)
         int c = 0;
-        if (tid < kTileGenes) {
 #pragma unroll
-            for (int w = 0; w < kTileRows / 32; ++w) {
-                S.wpre[w][tid] = (unsigned short)c;
-                c += __popc(S.mask[w][tid]);
-            }
+        for (int w = 0; w < kTileRows / 32; ++w) {
+            S.wpre[w][tid] = (unsigned short)c;
+            c += __popc(S.mask[w][tid]);
         }
         if (!kFill) {
-            if (tid < kTileGenes && g0 + tid < g1) cnt[g0 + tid] = c;
+            if (g0 + tid < g1) cnt[g0 + tid] = c;
         } else {
             int incl = c;
 #pragma unroll
@@ -191,52 +193,54 @@ relayout_tile_kernel(RelayoutParams P, int blocks_per_cta, const long long* __re
                 const int v = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl += v;
             }
-            if (tid < kTileGenes && lane == 31) S.wsum[warp] = incl;
+            if (lane == 31) S.wsum[warp] = incl;
             __syncthreads();
-            if (tid < kTileGenes) {
-                int base = 0;
-                for (int w = 0; w < warp; ++w) base += S.wsum[w];
-                S.off[tid] = base + incl - c;
-                if (tid == kTileGenes - 1) S.off[kTileGenes] = base + incl;
-            }
+            int base = 0;
+            for (int w = 0; w < warp; ++w) base += S.wsum[w];
+            S.off[tid] = base + incl - c;
+            if (tid == kTileGenes - 1) S.off[kTileGenes] = base + incl;
             __syncthreads();
             const int n_t = S.off[kTileGenes];
             for (int win = 0; win < n_t; win += kStageCap) {
-                // ---- phase 3: stage the block's nonzeros sorted by (gene, row)
-                for (int rl = warp; rl < n_rows; rl += kTileWarps) {
-                    const long long lo = S.cur[rl], hi = S.nxt[rl];
-                    const unsigned below = (1u << (rl & 31)) - 1u;
-                    const int w = rl >> 5;
-                    for (long long e = lo + lane; e < hi; e += 32) {
-                        const int j = __ldg(P.indices + e) - g0;
-                        if (j < 0) continue;                // unsorted input: reported by the count pass
-                        const int slot = S.off[j] + S.wpre[w][j] + __popc(S.mask[w][j] & below) - win;
+                // ---- phase 3: stage the block's nonzeros sorted by (gene, row), one row per thread
+                {
+                    auto place = [&](int idx, float v) {
+                        const int j = idx - g0;
+                        if (j < 0) return;                  // unsorted input: reported by the count pass
+                        const int slot = S.off[j] + S.wpre[w_row][j] + __popc(S.mask[w_row][j] & below) - win;
                         if (slot >= 0 && slot < kStageCap) {
-                            S.sval[slot] = ld_stream(P.data + e);
-                            S.srow[slot] = r0 + rl;
+                            S.sval[slot] = v;
+                            S.srow[slot] = r0 + tid;
                         }
+                    };
+                    long long e = cur;
+                    for (; e < nxt && (e & 3); ++e) place(__ldg(P.indices + e), __ldg(P.data + e));
+                    for (; e + 4 <= nxt; e += 4) {
+                        const int4 q = __ldg(reinterpret_cast<const int4*>(P.indices + e));
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(P.data + e));
+                        place(q.x, v.x); place(q.y, v.y); place(q.z, v.z); place(q.w, v.w);
                     }
+                    for (; e < nxt; ++e) place(__ldg(P.indices + e), __ldg(P.data + e));
                 }
                 __syncthreads();
                 // ---- phase 4: one coalesced run per gene
                 for (int j = warp; j < g1 - g0; j += kTileWarps) {
                     const int lo = max(S.off[j], win), hi = min(S.off[j + 1], win + kStageCap);
                     if (lo >= hi) continue;
-                    const long long base = __ldg(seg_ptr + (long long)(g0 + j) * P.R + grp) + cnt[g0 + j] - S.off[j];
+                    const long long base_o = __ldg(seg_ptr + (long long)(g0 + j) * P.R + grp) + cnt[g0 + j] - S.off[j];
                     for (int i = lo + lane; i < hi; i += 32) {
-                        vals_out[base + i] = S.sval[i - win];
-                        rows_out[base + i] = S.srow[i - win];
+                        vals_out[base_o + i] = S.sval[i - win];
+                        rows_out[base_o + i] = S.srow[i - win];
                     }
                 }
                 __syncthreads();
             }
         }
         // ---- next block
-        if (tid < kTileGenes) {
+        __syncthreads();
 #pragma unroll
-            for (int w = 0; w < kTileRows / 32; ++w) S.mask[w][tid] = 0u;
-        }
-        for (int rl = tid; rl < n_rows; rl += kTileThreads) S.cur[rl] = S.nxt[rl];
+        for (int w = 0; w < kTileRows / 32; ++w) S.mask[w][tid] = 0u;
+        cur = nxt;
         __syncthreads();
     }
 }
@@ -262,8 +266,8 @@ using namespace mm;
 
 static int tile_launch_shape(int n_chunks, int n_genes, int* blocks_per_cta, dim3* grid) {
     const int n_blocks = (n_genes + kTileGenes - 1) / kTileGenes;
-    // enough CTAs for ~4 per SM; a CTA walks at least one gene block
-    int split = (148 * 4 + n_chunks - 1) / (n_chunks > 0 ? n_chunks : 1);
+    // enough CTAs for two waves of 3 per SM; a CTA walks at least one gene block
+    int split = (148 * 6 + n_chunks - 1) / (n_chunks > 0 ? n_chunks : 1);
     if (split < 1) split = 1;
     if (split > n_blocks) split = n_blocks;
     if (split > 65535) split = 65535;
@@ -299,6 +303,7 @@ MM_EXPORT int mm_relayout_count(int device, void* stream, const int64_t* indptr,
     if (err_flag) MM_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int32_t), st));
     if (n_chunks > 0 && sorted_rows) {      // tiled path: chunks of at most kTileRows rows (checked by the fill call too)
         MM_REQUIRE(indices, "null pointer");
+        MM_REQUIRE(((uintptr_t)indices & 15) == 0, "tiled path: indices must be 16-byte aligned");
         int per; dim3 grid;
         tile_launch_shape(n_chunks, n_genes, &per, &grid);
         MM_CUDA(cudaFuncSetAttribute(relayout_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -331,6 +336,7 @@ MM_EXPORT int mm_relayout_fill(int device, void* stream, const int64_t* indptr, 
     P.chunk_row_lo = chunk_row_lo; P.chunk_group = chunk_group; P.n_chunks = n_chunks; P.n_genes = n_genes; P.R = R;
     P.cnt = cnt; P.err = nullptr;
     if (sorted_rows) {
+        MM_REQUIRE((((uintptr_t)indices | (uintptr_t)data) & 15) == 0, "tiled path: indices / data must be 16-byte aligned");
         int per; dim3 grid;
         tile_launch_shape(n_chunks, n_genes, &per, &grid);
         MM_CUDA(cudaFuncSetAttribute(relayout_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
