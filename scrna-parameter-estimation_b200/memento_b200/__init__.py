@@ -14,5 +14,6 @@ from .getters import (fdrcorrect, get_1d_ht_result, get_1d_moments, get_2d_ht_re
                       get_groups, prepare_to_save)
 from .anndata_lite import AnnDataLite  # noqa: F401
 from .io import load_results, read_10x_mtx, save_results, write_10x_mtx  # noqa: F401
+from . import simulate  # noqa: F401  (reference memento/simulate.py semantics, on the device)
 
 __version__ = "0.1.0"

@@ -692,10 +692,7 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
         with _Section(st, "compute_1d_moments: bin size factors"):
             _bin_size_factor(adata)
     groups = mem["groups"]
-    names = adata.var.index
-    pos = pd.Series(np.arange(len(names)), index=names)
-    idx1 = pos.loc[[a for a, _ in gene_pairs]].values.astype(int)
-    idx2 = pos.loc[[b for _, b in gene_pairs]].values.astype(int)
+    idx1, idx2 = _pair_indices(adata.var.index, gene_pairs)
     out = {"gene_pairs": gene_pairs, "gene_idx_1": idx1, "gene_idx_2": idx2}
     n_cells = np.diff(st.group_start).astype(np.float64)
     sums_d = st.seg.moments(st.inv_sf_sorted, st.timer)                                     # (5, G, R) on the device
@@ -728,6 +725,37 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
     mem["2d_moments"] = out
     if not inplace:
         return adata
+
+
+def _pair_indices(names, gene_pairs):
+    """Column positions of the two genes of every pair (reference main.py:310-318, a Python loop over the pairs).
+    ``gene_pairs``: the reference's list of (gene_1, gene_2) name tuples, or an (n, 2) array of names.  One transposing
+    ``zip`` and two hashed look-ups of whole arrays -- the 1.5k x 10k block of BASELINE configs[2] is 15 M tuples."""
+    if isinstance(gene_pairs, np.ndarray):
+        first, second = gene_pairs[:, 0], gene_pairs[:, 1]
+    elif len(gene_pairs) == 0:
+        first, second = [], []
+    else:
+        first, second = zip(*gene_pairs)
+    idx1 = names.get_indexer(pd.Index(first))
+    idx2 = names.get_indexer(pd.Index(second))
+    if (idx1 < 0).any() or (idx2 < 0).any():
+        bad = [g for g, i in zip(list(first) + list(second), np.concatenate([idx1, idx2])) if i < 0][:5]
+        raise KeyError("gene_pairs: genes not in adata.var.index (after filtering): %s" % bad)
+    return idx1.astype(int), idx2.astype(int)
+
+
+def _first_unordered(idx1, idx2):
+    """Unordered de-duplication of the pairs (reference main.py:467-482: a frozenset per pair): ``owner[k]`` = first
+    pair with the same two genes (-1 for i == j pairs, which stay NaN) and the sorted list of those first pairs."""
+    n = idx1.shape[0]
+    lo, hi = np.minimum(idx1, idx2).astype(np.int64), np.maximum(idx1, idx2).astype(np.int64)
+    key = lo * (int(hi.max()) + 1 if n else 1) + hi
+    _, first, inverse = np.unique(key, return_index=True, return_inverse=True)      # first occurrence of every key
+    owner = first[inverse.reshape(-1)].astype(np.int64)
+    owner[idx1 == idx2] = -1
+    uniq = np.unique(owner[owner >= 0])
+    return owner, uniq
 
 
 DENSE_BLOCK_MIN_PAIRS = 4096     # below this the per-pair merge join is cheaper than building the panels
@@ -845,16 +873,7 @@ def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     idx1, idx2 = mem["2d_moments"]["gene_idx_1"], mem["2d_moments"]["gene_idx_2"]
     n_all = idx1.shape[0]
     # unordered de-duplication, first occurrence computes (main.py:467-482)
-    first, owner = {}, np.full(n_all, -1, dtype=np.int64)
-    for k in range(n_all):
-        a, b = int(idx1[k]), int(idx2[k])
-        if a == b:
-            continue
-        key = (a, b) if a < b else (b, a)
-        if key not in first:
-            first[key] = k
-        owner[k] = first[key]
-    uniq = np.array(sorted(set(first.values())), dtype=np.int64)
+    owner, uniq = _first_unordered(idx1, idx2)
     true_corr = np.stack([mem["2d_moments"][g]["corr"] for g in groups], axis=1)       # (n_all, R)
     out = {k: np.full(n_all, np.nan) for k in ("coef", "se", "asl")}
     per_item = 8 * (num_boot + 1) * (3 if not approx else 2)

@@ -309,3 +309,31 @@ def test_resample_rep_column_parallel_equals_one_cta_per_gene(pair, T):
     assert np.isfinite(out[1]["mean_asl"]).sum() > 50 * T
     for k in HT_KEYS:
         assert_close(out[0][k], out[1][k], 1e-8, atol=1e-10, what="%s T=%d" % (k, T))
+
+
+def test_treatment_for_gene_wide_frame_vs_oracle(pair):
+    """The eQTL call pattern (reference analysis/lupus/run_memento.py:99-109): a 500-column genotype frame, every gene
+    tested on 5 of its columns.  Results equal the oracle's and only 5 slots per gene exist -- the work and the memory
+    follow the columns a gene uses, not the width of the frame."""
+    g, o = pair
+    cov, tr = _designs(g.uns["memento"]["groups"], n_extra=499, seed=7)
+    assert tr.shape[1] == 500
+    rng = np.random.default_rng(11)
+    cols = tr.columns.to_numpy()
+    tfg = {n: cols[np.sort(rng.choice(500, size=5, replace=False))].tolist() for n in g.var.index}
+    st = g.uns["memento"]["_b200"]
+    memento.ht_1d_moments(g, cov, tr, treatment_for_gene=tfg, num_boot=600, resampling="bootstrap", approx=True,
+                          resample_rep=True, seed=3)
+    np.random.seed(0)
+    o_pipe.ht_1d_moments(o, cov, tr, treatment_for_gene=tfg, num_boot=600, num_cpus=1, resampling="bootstrap",
+                         approx=True, resample_rep=True)
+    hg, ho = g.uns["memento"]["1d_ht"], o.uns["memento"]["1d_ht"]
+    assert hg["mean_coef"].shape == (5 * g.shape[1],) == ho["mean_coef"].shape
+    assert_close(hg["mean_coef"], ho["mean_coef"], 1e-8, atol=1e-10, what="mean_coef")
+    assert_close(hg["var_coef"], ho["var_coef"], 1e-7, atol=1e-9, what="var_coef")
+    ok = np.isfinite(ho["mean_se"]) & (ho["mean_se"] > 0)
+    ratio = hg["mean_se"][ok] / ho["mean_se"][ok]
+    assert 0.9 < np.median(ratio) < 1.1, np.median(ratio)
+    df = memento.get_1d_ht_result(g)
+    assert df.shape[0] == 5 * g.shape[1] and df["tx"].tolist()[:5] == tfg[g.var.index[0]]
+    assert st is g.uns["memento"]["_b200"]

@@ -84,3 +84,30 @@ def test_trend_fit_from_power_sums_equals_polyfit():
              np.array([zb.sum(), (zb ** 2).sum(), (zb ** 3).sum(), (zb ** 4).sum(), yb.sum(), (yb * zb).sum(), (yb * zb ** 2).sum()])]
     part = mmain._fit_mv_sums(np.exp(xa), np.exp(ya), TwoRanks(other))
     np.testing.assert_allclose(part, want, rtol=1e-9, atol=1e-11)
+
+
+def test_pair_index_helpers_equal_the_reference_loops():
+    """main._pair_indices / _first_unordered (vectorised) against the reference's per-pair Python loops
+    (main.py:310-318 name look-up, :467-482 frozenset de-duplication)."""
+    import pandas as pd
+    from memento_b200 import main as mmain
+    rng = np.random.default_rng(8)
+    names = pd.Index(["g%d" % i for i in range(50)])
+    pairs = [("g%d" % a, "g%d" % b) for a, b in rng.integers(0, 50, size=(3000, 2))]
+    i1, i2 = mmain._pair_indices(names, pairs)
+    assert i1.tolist() == [int(a[1:]) for a, _ in pairs] and i2.tolist() == [int(b[1:]) for _, b in pairs]
+    j1, j2 = mmain._pair_indices(names, np.asarray(pairs, dtype=object))
+    assert np.array_equal(i1, j1) and np.array_equal(i2, j2)
+    with pytest.raises(KeyError):
+        mmain._pair_indices(names, [("g1", "nope")])
+    owner, uniq = mmain._first_unordered(i1, i2)
+    first, want = {}, np.full(len(pairs), -1)
+    for k, (a, b) in enumerate(zip(i1, i2)):
+        if a == b:
+            continue
+        key = frozenset((int(a), int(b)))
+        first.setdefault(key, k)
+        want[k] = first[key]
+    assert np.array_equal(owner, want)
+    assert uniq.tolist() == sorted(set(first.values()))
+    assert mmain._pair_indices(names, [])[0].size == 0
