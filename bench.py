@@ -107,6 +107,7 @@ def parse():
     ap.add_argument("--approx", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="genes in the CPU sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the moment-kernel rooflines of the larger shapes")
     ap.add_argument("--workload", default="c2", choices=["c2"] + sorted(WORKLOADS),
                     help="c2 (default): the headline metric's configuration; the others time the whole API "
                          "pipeline of a larger BASELINE shape, gene-sharded over the ranks (strong scaling)")
@@ -359,6 +360,58 @@ def cpu_baseline(a, ad_host, gpu_names, gpu_ht):
 
 
 # ----------------------------------------------------------------------------------- our arm
+def kernel_ms(fn, dev, reps=10, warm=3):
+    """Mean CUDA-event time of ``fn`` (launches on the current stream) over ``reps`` calls after ``warm`` warm-ups."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / reps
+
+
+def shape_rooflines(dev, peak):
+    """The HBM-bound ingest / moment kernels on one GPU's gene shard of the larger BASELINE shapes, timed live (inputs
+    4.8 - 7 GB, far above L2): per-group moments (mm_seg_moments), masked row sums (mm_csr_row_sums) and the re-layout
+    (count + scan + fill).  Algorithmic bytes: DESIGN.md section 4."""
+    import torch
+    import memento_b200 as memento
+    from memento_b200 import synth, device as dev_mod
+    out = {}
+    for name in ("northstar", "c5"):
+        w = WORKLOADS[name]
+        ad = synth.make_counts_fast(w["cells"], 2500, n_conditions=w["conditions"], n_types=w["types"], q=w["q"],
+                                    seed=7, n_donors=w["donors"], device=dev)
+        memento.setup_memento(ad, "q")
+        st = ad.uns["memento"]["_b200"]
+        csr = st.csr
+        mask = torch.ones(2500, dtype=torch.uint8, device=dev)
+        res = {"cells": w["cells"], "genes": 2500, "nnz": int(csr.nnz)}
+
+        def entry(ms, nbytes):
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            return {"ms": ms, "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes": int(nbytes)}
+        res["csr_row_sums"] = entry(kernel_ms(lambda: csr.row_sums(mask), dev),
+                                    csr.nnz * 8 + (w["cells"] + 1) * 8 + w["cells"] * 8 + 2500)
+        res["relayout"] = entry(kernel_ms(lambda: dev_mod.SegMatrix.from_csr_grouped(csr), dev, reps=3, warm=1),
+                                csr.nnz * 20 + (w["cells"] + 1) * 16)       # indices twice, data once, vals + rows out
+        memento.create_groups(ad, w["labels"])
+        memento.compute_1d_moments(ad, min_perc_group=0.7, filter_genes=False)
+        seg = st.seg
+        res["groups"] = seg.R
+        res["mean_segment_nnz"] = seg.nnz / max(1, seg.n_seg)
+        res["seg_moments"] = entry(kernel_ms(lambda: seg.moments(st.inv_sf_sorted), dev), seg.moments_bytes())
+        out[name + " shard (2500 genes)"] = res
+        del ad, st, csr, seg
+        torch.cuda.empty_cache()
+    return out
+
+
 def sharded_parity(ctx, dev, rank, world):
     """N > 1, after the timed region: a fixed 6000-cell x 400-gene data set is tested gene-SHARDED over the N ranks
     (work-balanced contiguous gene blocks, NCCL all-reduce / all-gather in setup, results all-gathered) and, on rank
@@ -511,6 +564,26 @@ def run_ours(a):
     uniq_gbs = last.get("unique_bytes", 0) / (uniq_ms * 1e-3) / 1e9 if uniq_ms > 0 else None
     boot_ms = stage_ms.get("bootstrap_1d", 0.0) / a.steps
     traffic, traffic_src = ncu_traffic(seg.nnz)
+    csr_ms = relayout_ms = None
+    roofline_shapes = {}
+    if rank == 0 and world == 1:
+        # the other HBM-bound passes on this configuration: masked row sums and the re-layout of a fresh upload
+        from memento_b200 import device as dev_mod
+        X = ad_host.X if ad_host is not None else None
+        if X is not None:
+            csr = dev_mod.CsrOnDevice(X, dev)
+            gmask = torch.ones(X.shape[1], dtype=torch.uint8, device=dev)
+            csr_ms = kernel_ms(lambda: csr.row_sums(gmask), dev)
+            relayout_ms = kernel_ms(lambda: dev_mod.SegMatrix.from_csr_grouped(csr), dev, reps=3, warm=1)
+            roofline_shapes["c2 (25k x 10k)"] = {
+                "csr_row_sums": {"ms": csr_ms, "achieved": (csr.nnz * 8 + X.shape[0] * 16) / (csr_ms * 1e-3) / 1e9,
+                                 "unit": "GB/s", "frac": (csr.nnz * 8 + X.shape[0] * 16) / (csr_ms * 1e-3) / 1e9 / peak},
+                "relayout": {"ms": relayout_ms, "achieved": csr.nnz * 20 / (relayout_ms * 1e-3) / 1e9, "unit": "GB/s",
+                             "frac": csr.nnz * 20 / (relayout_ms * 1e-3) / 1e9 / peak},
+                "seg_moments": {"ms": mom_ms, "achieved": mom_gbs, "unit": "GB/s", "frac": mom_gbs / peak}}
+            del csr
+        if not a.no_shapes:
+            roofline_shapes.update(shape_rooflines(dev, peak))
     roofline = {"kernel": "mm_seg_moments (per-(gene,group) sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2)",
                 "bound": "hbm", "achieved": mom_gbs, "peak": peak, "unit": "GB/s", "frac": mom_gbs / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -561,6 +634,8 @@ def run_ours(a):
                "roofline": roofline, "cpu_baseline": cpu, "parity_on_bench_config": parity, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clk}
         out.update(extra)
+        if roofline_shapes:
+            out["roofline_shapes"] = roofline_shapes
         if shard_check is not None:
             out["sharded_parity"] = shard_check
         emit(json.dumps(out))

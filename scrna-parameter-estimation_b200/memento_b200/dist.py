@@ -6,10 +6,12 @@ per-gene process pool, main.py:379-397), so each rank owns a contiguous block of
 SAME cells and runs the whole pipeline on it.  The only exchanges are tiny and sit between kernels:
 
   * per-cell UMI totals need all genes        -> all-reduce(SUM) of an Nc-vector, twice (setup_memento)
-  * the mean-variance trend and the trim quantile need all genes' (mean, var)
-                                               -> all-gather of G-length vectors (setup_memento) and of the
-                                                  per-group (G x R) moments (compute_1d_moments)
-  * results                                    -> optional all-gather of 6 * T * G doubles (ht_1d_moments)
+  * the mean-variance trend needs all genes' (mean, var) pairs
+                                               -> all-reduce of 3 + 7 power sums (main._fit_mv_sums), in setup_memento
+                                                  and compute_1d_moments; the trim quantile of setup_memento still
+                                                  all-gathers one G-length vector
+  * results                                    -> one all-gather of 7 doubles per test (ht_1d_moments); gene names and
+                                                  per-rank sizes are exchanged once per gene set
 
 No collective is inside a hot kernel, so there is nothing to fuse with one.
 """
@@ -67,6 +69,24 @@ class DistContext:
         elif np.issubdtype(kind, np.integer):
             out = np.rint(out).astype(kind)
         return np.moveaxis(out, 0, axis), sizes
+
+    def all_gather_known(self, a, sizes):
+        """Concatenate per-rank float64 arrays whose leading sizes (``sizes``, one per rank) are already known to every
+        rank: ONE collective (all_gather_into_tensor of a padded block) and one device-to-host copy -- no size
+        exchange, no per-rank host round trips.  Used for the per-call result gather of ht_1d_moments."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        n_max = max(1, max(sizes))
+        block = torch.zeros((n_max,) + a.shape[1:], dtype=torch.float64)
+        block[:a.shape[0]] = torch.from_numpy(a)
+        block = block.to(self.device) if self.device is not None else block
+        out = torch.empty((self.world,) + tuple(block.shape), dtype=torch.float64, device=block.device)
+        if self.device is not None:
+            tdist.all_gather_into_tensor(out, block, group=self.group)
+        else:       # gloo (CPU tests): the list form, into views of the same buffer
+            tdist.all_gather(list(out.unbind(0)), block, group=self.group)
+        self.bytes_gathered += out.numel() * 8
+        host = out.cpu().numpy()
+        return np.concatenate([host[r, :n] for r, n in enumerate(sizes)], axis=0)
 
     def all_gather_names(self, names):
         """Concatenate per-rank lists of strings (gene names) in rank order."""

@@ -664,16 +664,18 @@ def _gather_1d_ht(adata, t_gene):
     st = _state(adata)
     ht = mem["1d_ht"]
     names_local = adata.var.index
-    key = (len(names_local), hash(tuple(names_local[:: max(1, len(names_local) // 64)])))
-    if getattr(st, "all_names_key", None) != key:
-        counts, _ = st.dist.all_gather_concat(np.array([len(names_local)], dtype=np.int64))
-        st.all_names = st.dist.all_gather_names(names_local.tolist())
-        st.all_names_lo = int(counts[:st.dist.rank].sum())
-        st.all_names_key = key
     n_local = int(t_gene.sum())
+    key = (len(names_local), n_local, hash(tuple(names_local[:: max(1, len(names_local) // 64)])))
+    if getattr(st, "all_names_key", None) != key:       # once per gene set / treatment_for_gene: names and sizes
+        counts, _ = st.dist.all_gather_concat(np.array([len(names_local), n_local], dtype=np.int64))
+        counts = counts.reshape(-1, 2)
+        st.all_names = st.dist.all_gather_names(names_local.tolist())
+        st.all_names_lo = int(counts[:st.dist.rank, 0].sum())
+        st.all_tests = [int(c) for c in counts[:, 1]]
+        st.all_names_key = key
     gene_pos = np.repeat(st.all_names_lo + np.arange(t_gene.size), t_gene).astype(np.float64)
     packed = np.stack([ht[k][:n_local] for k in _HT_KEYS] + [gene_pos], axis=1)     # (tests, 7)
-    allv, _ = st.dist.all_gather_concat(packed)
+    allv = st.dist.all_gather_known(packed, st.all_tests)
     pos = np.rint(allv[:, 6]).astype(np.int64)
     res = {"gene": st.all_names, "n_tests": np.bincount(pos, minlength=len(st.all_names)).astype(np.int64)}
     for j, k in enumerate(_HT_KEYS):
