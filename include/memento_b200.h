@@ -39,6 +39,19 @@ const char* mm_last_error(void);
 int mm_csr_row_sums(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                     const float* data, int64_t n_rows, const uint8_t* gene_mask, double* out);
 
+/* Host -> device copy of a large PAGEABLE buffer (the caller's scipy arrays) on n_threads (1..8) host threads through a
+ * pinned ring with overlapped cudaMemcpyAsync; ordered after the work already queued on `stream`, and later work on
+ * `stream` sees the data.  The ring (n_threads x 16 MB pinned, side streams, events) is created on first use and is
+ * the only persistent state the library owns; mm_upload_release() frees it.  Host pointers: src.
+ * Replaces: the implicit host copies of scipy / numpy in the reference (it has no device). */
+int mm_upload(int device, void* stream, void* dst, const void* src, int64_t bytes, int32_t n_threads);
+int mm_upload_release(void);
+
+/* Canonical-form check of an uploaded CSR: flag[0] = 1 when some row's column indices are not strictly ascending
+ * (unsorted or duplicate entries).  Replaces scipy's single-threaded has_canonical_format scan. */
+int mm_csr_check_sorted(int device, void* stream, const int64_t* indptr, const int32_t* indices, int64_t n_rows,
+                        int32_t* flag);
+
 /* Ingest check: counts must be non-negative integers below 2^24 (the compression keys of mm_seg_unique /
  * mm_pair_unique hold the count in 24 bits; the reference's _unique_expr, memento/bootstrap.py:62-71, takes any
  * value).  flags[0]: bit 0 = a negative or NaN value, bit 1 = a fractional value, bit 2 = a value >= 2^24. */

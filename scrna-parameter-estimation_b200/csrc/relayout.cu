@@ -26,6 +26,10 @@
 // coalesced run per gene (chunk rows x density elements: ~240 B on the 25k x 10k matrix) instead of 4-byte scatters.
 // Bit-identical to the generic path and to the stable sort (tests/test_gpu_relayout.py).
 #include "common.cuh"
+#include <string.h>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 namespace mm {
 
@@ -260,9 +264,142 @@ __global__ void validate_counts_kernel(const float* __restrict__ data, long long
     if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
 }
 
+// canonical-form check of an uploaded CSR: column indices strictly ascending inside every row (sorted, no duplicates).
+// scipy's own has_canonical_format is a single-threaded host scan of the index array (0.2 s at 6e8 nonzeros).
+__global__ void csr_check_sorted_kernel(const long long* __restrict__ indptr, const int* __restrict__ indices,
+                                        long long n_rows, int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const long long lo = indptr[row], hi = indptr[row + 1];
+    bool bad = false;
+    for (long long e = lo + lane; e + 1 < hi; e += 32) bad |= ld_stream(indices + e) >= ld_stream(indices + e + 1);
+    if (__any_sync(kFull, bad) && lane == 0) *flag = 1;
+}
+
 }  // namespace mm
 
 using namespace mm;
+
+// ------------------------------------------------------------------ host -> device upload of large pageable buffers
+// cudaMemcpy from pageable memory runs at ~6 GB/s (one driver thread copies through its bounce buffers): the upload of
+// a rank's 4.8 GB CSR shard was the largest term of the north-star pipeline.  Here n_threads host threads copy 8 MB
+// chunks into a pinned ring (two slots per thread) and queue cudaMemcpyAsync on their own streams, so the host copies
+// run in parallel and overlap the DMA.  The ring (n_threads x 16 MB of pinned memory, streams, events) is created on
+// first use and kept until mm_upload_release(): the one piece of persistent state this library owns.
+namespace {
+constexpr int kUpMaxThreads = 8;
+constexpr size_t kUpSlot = 8u << 20;
+struct UploadRing {
+    std::mutex mu;
+    int device = -1;
+    void* slot[kUpMaxThreads][2] = {};
+    cudaEvent_t ev[kUpMaxThreads][2] = {};
+    cudaEvent_t done[kUpMaxThreads] = {};
+    cudaEvent_t start = nullptr;
+    cudaStream_t st[kUpMaxThreads] = {};
+};
+UploadRing g_up;
+
+void upload_release_locked() {
+    if (g_up.device < 0) return;
+    cudaSetDevice(g_up.device);
+    for (int t = 0; t < kUpMaxThreads; ++t) {
+        if (g_up.st[t]) cudaStreamSynchronize(g_up.st[t]);
+        for (int b = 0; b < 2; ++b) {
+            if (g_up.slot[t][b]) cudaFreeHost(g_up.slot[t][b]);
+            if (g_up.ev[t][b]) cudaEventDestroy(g_up.ev[t][b]);
+            g_up.slot[t][b] = nullptr; g_up.ev[t][b] = nullptr;
+        }
+        if (g_up.done[t]) cudaEventDestroy(g_up.done[t]);
+        if (g_up.st[t]) cudaStreamDestroy(g_up.st[t]);
+        g_up.done[t] = nullptr; g_up.st[t] = nullptr;
+    }
+    if (g_up.start) cudaEventDestroy(g_up.start);
+    g_up.start = nullptr;
+    g_up.device = -1;
+}
+}  // namespace
+
+MM_EXPORT int mm_upload_release(void) {
+    std::lock_guard<std::mutex> lock(g_up.mu);
+    upload_release_locked();
+    return 0;
+}
+
+MM_EXPORT int mm_upload(int device, void* stream, void* dst, const void* src, int64_t bytes, int32_t n_threads) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(bytes >= 0 && (bytes == 0 || (dst && src)), "dst/src/bytes");
+    if (bytes == 0) return 0;
+    cudaStream_t user = (cudaStream_t)stream;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > kUpMaxThreads) n_threads = kUpMaxThreads;
+    const long long n_chunks = (bytes + (long long)kUpSlot - 1) / (long long)kUpSlot;
+    if (n_chunks < 4) {          // small: the driver's own staged copy, ordered on the caller's stream
+        MM_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, user));
+        return 0;
+    }
+    if (n_threads > n_chunks) n_threads = (int)n_chunks;
+    std::lock_guard<std::mutex> lock(g_up.mu);
+    if (g_up.device != device) {
+        upload_release_locked();
+        MM_CUDA(cudaSetDevice(device));
+        g_up.device = device;
+        MM_CUDA(cudaEventCreateWithFlags(&g_up.start, cudaEventDisableTiming));
+    }
+    for (int t = 0; t < n_threads; ++t) {
+        if (g_up.st[t]) continue;
+        MM_CUDA(cudaStreamCreateWithFlags(&g_up.st[t], cudaStreamNonBlocking));
+        MM_CUDA(cudaEventCreateWithFlags(&g_up.done[t], cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) {
+            MM_CUDA(cudaHostAlloc(&g_up.slot[t][b], kUpSlot, cudaHostAllocPortable));
+            MM_CUDA(cudaEventCreateWithFlags(&g_up.ev[t][b], cudaEventDisableTiming));
+        }
+    }
+    // the destination may be a freshly recycled block with work still queued on the caller's stream
+    MM_CUDA(cudaEventRecord(g_up.start, user));
+    std::vector<std::thread> workers;
+    std::vector<cudaError_t> errs(n_threads, cudaSuccess);
+    for (int t = 0; t < n_threads; ++t) {
+        workers.emplace_back([&, t]() {
+            cudaError_t e = cudaSetDevice(device);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(g_up.st[t], g_up.start, 0);
+            for (long long c = t; c < n_chunks && e == cudaSuccess; c += n_threads) {
+                const int b = (int)((c / n_threads) & 1);
+                const size_t off = (size_t)c * kUpSlot;
+                const size_t sz = (size_t)bytes - off < kUpSlot ? (size_t)bytes - off : kUpSlot;
+                e = cudaEventSynchronize(g_up.ev[t][b]);                 // the slot's previous copy has left it
+                if (e != cudaSuccess) break;
+                memcpy(g_up.slot[t][b], (const char*)src + off, sz);
+                e = cudaMemcpyAsync((char*)dst + off, g_up.slot[t][b], sz, cudaMemcpyHostToDevice, g_up.st[t]);
+                if (e == cudaSuccess) e = cudaEventRecord(g_up.ev[t][b], g_up.st[t]);
+            }
+            errs[t] = e;
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int t = 0; t < n_threads; ++t) {
+        if (errs[t] != cudaSuccess) {
+            set_error("mm_upload worker %d: %s", t, cudaGetErrorString(errs[t]));
+            return 2;
+        }
+        MM_CUDA(cudaEventRecord(g_up.done[t], g_up.st[t]));
+        MM_CUDA(cudaStreamWaitEvent(user, g_up.done[t], 0));             // later work on the caller's stream sees the data
+    }
+    return 0;
+}
+
+MM_EXPORT int mm_csr_check_sorted(int device, void* stream, const int64_t* indptr, const int32_t* indices,
+                                  int64_t n_rows, int32_t* flag) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(n_rows >= 0 && flag && (n_rows == 0 || (indptr && indices)), "indptr/indices/flag");
+    MM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), (cudaStream_t)stream));
+    if (n_rows == 0) return 0;
+    const long long blocks = (n_rows + 7) / 8;
+    MM_REQUIRE(blocks < 2147483647LL, "too many rows");
+    csr_check_sorted_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const long long*)indptr, indices, n_rows, flag);
+    return check_launch("mm_csr_check_sorted");
+}
 
 static int tile_launch_shape(int n_chunks, int n_genes, int* blocks_per_cta, dim3* grid) {
     const int n_blocks = (n_genes + kTileGenes - 1) / kTileGenes;

@@ -20,6 +20,8 @@ SIGNATURES = {
     "mm_seg_moments": [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
     "mm_seg_moments_windows": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "mm_validate_counts": [_vp, _i64, _vp],
+    "mm_upload": [_vp, _vp, _i64, _i32],
+    "mm_csr_check_sorted": [_vp, _vp, _i64, _vp],
     "mm_relayout_count": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "mm_relayout_fill": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32],
     "mm_block_panels": [_vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp],
@@ -47,7 +49,7 @@ SIGNATURES = {
 }
 
 # host-only helpers (no leading device / stream arguments)
-HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp], "mm_launch_count": [], "mm_reload_tuning": []}
+HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp], "mm_launch_count": [], "mm_reload_tuning": [], "mm_upload_release": []}
 
 _lib = None
 

@@ -9,6 +9,8 @@ each group is a contiguous row range, rows ascend inside a segment.  Per-cell ve
 PyTorch is used for device buffers, streams and the ingest-time re-layout (a stable sort of the
 nonzeros by (gene, group) key); every reduction / resampling / regression kernel is ours.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -68,10 +70,25 @@ def require_cuda(device=None):
     return device
 
 
+UPLOAD_MIN_BYTES = 32 << 20      # larger pageable arrays go through mm_upload (threaded pinned ring)
+
+
+def upload_threads():
+    """Host threads of one mm_upload: the cores of the box shared out over the ranks of the node, at most 8."""
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return int(os.environ.get("MM_UPLOAD_THREADS", max(1, min(8, (os.cpu_count() or 1) // ranks))))
+
+
 def to_device(arr, device, dtype=None, pinned=False):
     a = np.ascontiguousarray(arr)
     if dtype is not None and a.dtype != dtype:
         a = a.astype(dtype)
+    if not pinned and a.nbytes >= UPLOAD_MIN_BYTES:
+        out = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, device=device)
+        _lib.call("mm_upload", device, out, int(a.ctypes.data), a.nbytes, upload_threads())
+        # the source must stay alive until the copies have left it: mm_upload returns after its host threads have
+        # copied every chunk into the pinned ring, so ``a`` may be dropped right away
+        return out
     t = torch.from_numpy(a)
     if pinned:
         t = t.pin_memory()
@@ -95,9 +112,11 @@ class CsrOnDevice:
         self.indices = to_device(X.indices, device, np.int32, pinned)
         self.data = to_device(data, device, np.float32, pinned)
         self.nnz = int(self.data.numel())
-        # column indices ascending inside every row and no duplicates (scipy's canonical form; scipy scans the
-        # index arrays once when the flag is not cached): the re-layout then takes its tiled path
-        self.sorted_rows = bool(X.has_canonical_format)
+        # column indices strictly ascending inside every row (scipy's canonical form, checked on the device: scipy's own
+        # has_canonical_format is a single-threaded scan of the index array): the re-layout then takes its tiled path
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        _lib.call("mm_csr_check_sorted", device, self.indptr, self.indices, self.shape[0], flag)
+        self.sorted_rows = int(flag.item()) == 0
         # the compression keys hold a count in 24 bits and the moment kernels read the same values: anything but
         # non-negative integers below 2^24 would make bootstrap tables and moments disagree without an error
         flags = torch.zeros(1, dtype=torch.int32, device=device)

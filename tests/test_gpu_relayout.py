@@ -67,3 +67,33 @@ def test_relayout_equals_stable_sort(shape, canonical):
     new1 = dev_mod.SegMatrix.from_csr_grouped(csr)
     old1 = dev_mod.SegMatrix.from_csr(csr)
     assert torch.equal(new1.seg_ptr, old1.seg_ptr) and torch.equal(new1.rows, old1.rows) and torch.equal(new1.vals, old1.vals)
+
+
+def test_threaded_upload_equals_plain_copy():
+    """mm_upload (host threads -> pinned ring -> cudaMemcpyAsync on side streams) against torch's own copy: sizes
+    below / at / above the chunk size and not a multiple of it, back-to-back calls reusing the ring, and ordering
+    with work queued on the caller's stream before and after."""
+    d = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    for n in (1, 1000, (8 << 20) // 4, 5 * (8 << 20) // 4 + 123, 40_000_003):
+        a = rng.integers(0, 1 << 30, size=n, dtype=np.int32)
+        out = torch.full((n,), -1, dtype=torch.int32, device=d)          # queued before: must not land after the copy
+        dev_mod._lib.call("mm_upload", d, out, int(a.ctypes.data), a.nbytes, 3)
+        doubled = out.to(torch.int64) * 2                                    # queued after: must see the data
+        np.testing.assert_array_equal(out.cpu().numpy(), a)
+        np.testing.assert_array_equal(doubled.cpu().numpy(), a.astype(np.int64) * 2)
+    big = rng.random(9_000_000)
+    t = dev_mod.to_device(big, d, np.float64)                               # 72 MB: goes through mm_upload
+    np.testing.assert_array_equal(t.cpu().numpy(), big)
+    dev_mod._lib.load().mm_upload_release()
+    t2 = dev_mod.to_device(big, d, np.float32)                              # ring re-created
+    np.testing.assert_array_equal(t2.cpu().numpy(), big.astype(np.float32))
+
+
+def test_csr_canonical_check_on_device():
+    X, _ = _case(500, 60, 3, 0.2, seed=1)
+    d = torch.device("cuda", 0)
+    assert dev_mod.CsrOnDevice(X, d).sorted_rows
+    assert not dev_mod.CsrOnDevice(_shuffle_rows(X, 2), d).sorted_rows
+    dup = sp.csr_matrix((np.ones(4, np.float32), np.array([0, 3, 3, 5], np.int32), np.array([0, 4], np.int64)), shape=(1, 8))
+    assert not dev_mod.CsrOnDevice(dup, d).sorted_rows                      # duplicate column entries are not canonical
