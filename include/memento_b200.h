@@ -115,11 +115,44 @@ int mm_seg_moments_windows(int device, void* stream, const float* vals, const in
  * (gene_idx[i], n_genes of them) and every cell c of group `group` (renumbered rows row0 .. row0 + n_cells - 1),
  *   z = (x_ci / sf_c - center[i]) * inv_scale[i]      (float64),   z_hi = fp16(z),   z_lo = fp16((z - z_hi) * 2^11)
  * written K-major as z_hi[i * k_pad + (c - row0)], zero-padded to k_pad (a multiple of 64, >= n_cells).
- * center = the group mean of x / sf, inv_scale = a power of two that makes z O(1). */
+ * center = the group mean of x / sf, inv_scale = a power of two that makes z O(1).
+ * cell_w (nullable) [n_cells_total]: per-cell resampling counts (mm_cell_weights); z is multiplied by cell_w[c] --
+ * the weighted operand of the shared-weight bootstrap. */
 int mm_block_panels(int device, void* stream, const float* vals, const int32_t* rows, const int64_t* seg_ptr,
                     int32_t R, int32_t group, int64_t row0, int32_t n_cells, const double* inv_sf,
                     const int32_t* gene_idx, int32_t n_genes, const double* center, const double* inv_scale,
-                    int32_t k_pad, void* z_hi, void* z_lo);
+                    int32_t k_pad, void* z_hi, void* z_lo, const int32_t* cell_w);
+
+/* Shared-weight ("true") cell bootstrap of a dense gene-pair block (csrc/sharedboot.cu).  Per
+ * replicate: mm_cell_weights -> mm_seg_weighted_stats for the A and the B genes -> per group mm_block_panels (A
+ * weighted by cell_w, B plain and reusable) + mm_block_gemm -> mm_block_boot_update; mm_block_boot_finish at the end.
+ *   mm_cell_weights       : w[c] = how often cell c is drawn when every group g draws N_g of its own cells with
+ *                           replacement (group_start [R + 1] over the renumbered rows); Philox(seed, replicate, draw).
+ *   mm_seg_weighted_stats : for listed gene i and group r (arrays [n_genes][R]; center = the unweighted group mean of
+ *                           x / sf used to centre the panels): out_shift = sum_c w x/sf / N_r - center, out_isd =
+ *                           1 / sqrt(var_w) with var_w = [sum w x^2/sf^2 - (1 - q_r) sum w x/sf^2] / N_r -
+ *                           (sum w x/sf / N_r)^2, NaN when var_w <= 0 (estimator.py:171-174, :283-284).
+ *   mm_block_boot_update  : cross [R][na][nb] = the replicate's weighted centred cross products; corr_r = (cross / N_r -
+ *                           shift_a shift_b) isd_a isd_b clipped to [-1, 1]; coef = sum_r cfun[r] corr_r (one
+ *                           treatment column, every group valid); pairs with stat = NaN are skipped; a replicate with
+ *                           a NaN correlation in some group is dropped for that pair.  Running sums of d = coef - stat:
+ *                           sum, sumsq, n_ext (|d| > |stat|), n_ok.  coef_out (nullable): this replicate's coefficients.
+ *   mm_block_boot_finish  : se = std of d (ddof 0); asl = two-sided normal tail (approx != 0, hypothesis_test.py:77-83)
+ *                           or (n_ext + 1) / (n_ok + 1) (:85-92, without the GEV refinement).
+ * Replaces: memento/bootstrap.py:119-157 + hypothesis_test.py:303-414 for gene_pairs = A x B. */
+int mm_cell_weights(int device, void* stream, const int64_t* group_start, int32_t R, int64_t n_cells, uint64_t seed,
+                    uint32_t replicate, int32_t* w);
+int mm_seg_weighted_stats(int device, void* stream, const float* vals, const int32_t* rows, const int64_t* seg_ptr,
+                          int32_t R, const int32_t* gene_idx, int32_t n_genes, const double* inv_sf,
+                          const int32_t* cell_w, const double* center, const double* group_n, const double* group_q,
+                          double* out_shift, double* out_isd);
+int mm_block_boot_update(int device, void* stream, const double* cross, const double* shift_a, const double* isd_a,
+                         const double* shift_b, const double* isd_b, const double* group_n, const double* cfun,
+                         const double* stat, int32_t R, int32_t na, int32_t nb, double* sum, double* sumsq,
+                         int32_t* n_ext, int32_t* n_ok, double* coef_out);
+int mm_block_boot_finish(int device, void* stream, const double* stat, const double* sum, const double* sumsq,
+                         const int32_t* n_ext, const int32_t* n_ok, int64_t n_pairs, int32_t approx, double* se,
+                         double* asl);
 
 /* Dense gene block, step 2: out[a * ldo + b] = scale_a[a] * scale_b[b] * sum_k z_a[k] z_b[k] for a < m, b < n, with
  * z = z_hi + 2^-11 z_lo, as three fp16 tcgen05.mma products (hi hi, hi lo, lo hi) accumulated in fp32 in tensor

@@ -51,7 +51,7 @@ block_panels_kernel(const float* __restrict__ vals, const int* __restrict__ rows
                     int R, int group, long long row0, int n_cells, const double* __restrict__ inv_sf,
                     const int* __restrict__ gene_idx, const double* __restrict__ center,
                     const double* __restrict__ inv_scale, int k_pad, __half* __restrict__ z_hi,
-                    __half* __restrict__ z_lo) {
+                    __half* __restrict__ z_lo, const int* __restrict__ cell_w) {
     const int i = blockIdx.x;
     const double c = center[i], is = inv_scale[i];
     __half* hi = z_hi + (long long)i * k_pad;
@@ -60,16 +60,26 @@ block_panels_kernel(const float* __restrict__ vals, const int* __restrict__ rows
     const __half h0 = __double2half(z0);
     const __half l0 = __double2half((z0 - (double)__half2float(h0)) * kLoScale);
     const __half zero = __float2half(0.f);
-    for (int k = threadIdx.x; k < k_pad; k += 128) {
-        hi[k] = k < n_cells ? h0 : zero;
-        lo[k] = k < n_cells ? l0 : zero;
+    if (cell_w) {       // shared-weight bootstrap (sharedboot.cu): every cell's value times its resampling count
+        for (int k = threadIdx.x; k < k_pad; k += 128) {
+            const double z = k < n_cells ? z0 * (double)cell_w[row0 + k] : 0.0;
+            const __half h = __double2half(z);
+            hi[k] = h;
+            lo[k] = __double2half((z - (double)__half2float(h)) * kLoScale);
+        }
+    } else {
+        for (int k = threadIdx.x; k < k_pad; k += 128) {
+            hi[k] = k < n_cells ? h0 : zero;
+            lo[k] = k < n_cells ? l0 : zero;
+        }
     }
     __syncthreads();
     const long long s = (long long)gene_idx[i] * R + group;
     const long long a = seg_ptr[s], b = seg_ptr[s + 1];
     for (long long e = a + threadIdx.x; e < b; e += 128) {
         const int r = rows[e];
-        const double z = ((double)vals[e] * __ldg(inv_sf + r) - c) * is;
+        double z = ((double)vals[e] * __ldg(inv_sf + r) - c) * is;
+        if (cell_w) z *= (double)cell_w[r];
         const __half h = __double2half(z);
         const int k = (int)(r - row0);
         hi[k] = h;
@@ -273,7 +283,7 @@ using namespace mm;
 MM_EXPORT int mm_block_panels(int device, void* stream, const float* vals, const int32_t* rows, const int64_t* seg_ptr,
                               int32_t R, int32_t group, int64_t row0, int32_t n_cells, const double* inv_sf,
                               const int32_t* gene_idx, int32_t n_genes, const double* center, const double* inv_scale,
-                              int32_t k_pad, void* z_hi, void* z_lo) {
+                              int32_t k_pad, void* z_hi, void* z_lo, const int32_t* cell_w) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_genes >= 0 && R > 0 && group >= 0 && group < R, "n_genes/R/group");
     MM_REQUIRE(k_pad >= n_cells && k_pad % kBK == 0, "k_pad must be a multiple of 64 and >= n_cells");
@@ -281,7 +291,7 @@ MM_EXPORT int mm_block_panels(int device, void* stream, const float* vals, const
     MM_REQUIRE(vals && rows && seg_ptr && inv_sf && gene_idx && center && inv_scale && z_hi && z_lo, "null pointer");
     block_panels_kernel<<<n_genes, 128, 0, (cudaStream_t)stream>>>(vals, rows, (const long long*)seg_ptr, R, group, row0,
                                                                   n_cells, inv_sf, gene_idx, center, inv_scale, k_pad,
-                                                                  (__half*)z_hi, (__half*)z_lo);
+                                                                  (__half*)z_hi, (__half*)z_lo, cell_w);
     return check_launch("mm_block_panels");
 }
 

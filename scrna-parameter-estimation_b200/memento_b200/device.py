@@ -466,14 +466,14 @@ class SegMatrix:
             ca, inv_a, sc_a = scaling(ia, r, float(n))
             za = pa.view(-1)[:2 * na * k_pad].view(2, na, k_pad)
             _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
-                      ia, na, ca, inv_a, k_pad, za[0], za[1])
+                      ia, na, ca, inv_a, k_pad, za[0], za[1], None)
             if same:
                 zb, sc_b = za, sc_a
             else:
                 cb, inv_b, sc_b = scaling(ib, r, float(n))
                 zb = pb.view(-1)[:2 * nb * k_pad].view(2, nb, k_pad)
                 _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
-                          ib, nb, cb, inv_b, k_pad, zb[0], zb[1])
+                          ib, nb, cb, inv_b, k_pad, zb[0], zb[1], None)
             _lib.call("mm_block_gemm", dev, za[0], za[1], na, zb[0], zb[1], nb, k_pad, sc_a, sc_b, out[j], nb)
         timer.stop("block_cross", ev)
         return out

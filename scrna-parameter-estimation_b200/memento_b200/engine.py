@@ -535,3 +535,89 @@ def ht_2d_tile(seg, design, cell_bin, idx1, idx2, true_corr, covariate, treatmen
         stats["launches"] = stats.get("launches", 0) + 5
         stats["pair_items"] = stats.get("pair_items", 0) + n_items
     return res
+
+
+# --------------------------------------------------------------------------- shared-weight bootstrap of a dense block
+def ht_2d_shared_block(seg, idx_a, idx_b, inv_sf, sums_d, group_q, true_corr, covariate, treatment, num_boot, seed,
+                       approx, one_sample, timer=NULL_TIMER, weights=None, want_coef=False):
+    """The "true" cell bootstrap of a dense gene-pair block A x B (csrc/sharedboot.cu): per
+    replicate one set of per-cell resampling counts shared by all pairs, one weighted tensor-core GEMM per group.
+
+    ``idx_a`` / ``idx_b``: gene indices (numpy int); ``sums_d``: (5, G, R) device tensor of ``seg.moments``;
+    ``true_corr``: (|A|, |B|, R) host array of the observed correlations; pairs with a NaN or +-1 correlation in some
+    group (reference hypothesis_test.py:325 drops such groups per pair) and i == j pairs are left NaN for the caller's
+    per-pair path.  ``weights`` (tests): (num_boot, n_cells) int32 device tensor of resampling counts instead of the
+    Philox draws.  Returns {"coef", "se", "asl"} float64 device tensors (|A|, |B|), "n_ok" and, with ``want_coef``,
+    the last replicate's coefficients."""
+    dev = seg.device
+    R, gs = seg.R, seg.group_start_host
+    n_r = np.diff(gs).astype(np.float64)
+    ia = torch.as_tensor(np.ascontiguousarray(idx_a, dtype=np.int32), device=dev)
+    ib = torch.as_tensor(np.ascontiguousarray(idx_b, dtype=np.int32), device=dev)
+    na, nb = int(ia.numel()), int(ib.numel())
+    # regression functional of the all-groups-valid design (one treatment column)
+    cmat, _ = wls_functional(dev, covariate, treatment, n_r, np.ones((1, R), dtype=np.uint8), one_sample, timer)
+    cfun = cmat[0, 0].contiguous()
+    with np.errstate(invalid="ignore"):
+        usable = ~(np.isnan(true_corr) | (np.abs(true_corr) == 1)).any(axis=2)
+    usable &= np.asarray(idx_a)[:, None] != np.asarray(idx_b)[None, :]
+    tc = torch.as_tensor(np.ascontiguousarray(np.nan_to_num(true_corr), dtype=np.float64), device=dev)
+    stat = (tc * cfun[None, None, :]).sum(dim=2)
+    stat[~torch.as_tensor(usable, device=dev)] = float("nan")
+    stat = stat.contiguous()
+    gn = torch.as_tensor(n_r, device=dev)
+    gq = torch.as_tensor(np.ascontiguousarray(group_q, dtype=np.float64), device=dev)
+
+    def scaling(idx):          # (centre, 1 / scale, scale) per (gene, group): as SegMatrix.block_cross
+        m = sums_d[2][idx.long()] / gn[None, :]
+        second = sums_d[4][idx.long()] / gn[None, :] - m * m
+        e = torch.where(second > 0, torch.round(0.5 * torch.log2(second.clamp(min=1e-300))), torch.zeros_like(second))
+        e = e.clamp(-200, 200)
+        return m.contiguous(), torch.exp2(-e), torch.exp2(e)
+
+    ca, inv_a, sc_a = scaling(ia)                       # (na, R)
+    cb, inv_b, sc_b = scaling(ib)
+    BK = seg.BLOCK_K
+    k_pad = [max(BK, (int(n) + BK - 1) // BK * BK) for n in n_r]
+    # the plain B panels are the same for every replicate: built once per group and kept
+    panels_b = []
+    for r in range(R):
+        zb = torch.empty((2, nb, k_pad[r]), dtype=torch.float16, device=dev)
+        _lib.call("mm_block_panels", dev, seg.vals, seg.rows, seg.seg_ptr, R, r, int(gs[r]), int(n_r[r]), inv_sf, ib, nb,
+                  cb[:, r].contiguous(), inv_b[:, r].contiguous(), k_pad[r], zb[0], zb[1], None)
+        panels_b.append(zb)
+    col = lambda t, r: t[:, r].contiguous()             # noqa: E731
+    ca_r, inv_a_r, sc_a_r, sc_b_r = ([col(t, r) for r in range(R)] for t in (ca, inv_a, sc_a, sc_b))
+    pa = torch.empty(2 * na * max(k_pad), dtype=torch.float16, device=dev)
+    cross = torch.empty((R, na, nb), dtype=torch.float64, device=dev)
+    w = torch.empty(seg.n_cells, dtype=torch.int32, device=dev)
+    shift_a, isd_a = torch.empty((na, R), dtype=torch.float64, device=dev), torch.empty((na, R), dtype=torch.float64, device=dev)
+    shift_b, isd_b = torch.empty((nb, R), dtype=torch.float64, device=dev), torch.empty((nb, R), dtype=torch.float64, device=dev)
+    acc_sum = torch.zeros((na, nb), dtype=torch.float64, device=dev)
+    acc_sq = torch.zeros((na, nb), dtype=torch.float64, device=dev)
+    n_ext = torch.zeros((na, nb), dtype=torch.int32, device=dev)
+    n_ok = torch.zeros((na, nb), dtype=torch.int32, device=dev)
+    coef_last = torch.empty((na, nb), dtype=torch.float64, device=dev) if want_coef else None
+    ev = timer.start()
+    for b in range(num_boot):
+        if weights is None:
+            _lib.call("mm_cell_weights", dev, seg.group_start, R, seg.n_cells, seed, b, w)
+        else:
+            w = weights[b].contiguous()
+        _lib.call("mm_seg_weighted_stats", dev, seg.vals, seg.rows, seg.seg_ptr, R, ia, na, inv_sf, w, ca, gn, gq,
+                  shift_a, isd_a)
+        _lib.call("mm_seg_weighted_stats", dev, seg.vals, seg.rows, seg.seg_ptr, R, ib, nb, inv_sf, w, cb, gn, gq,
+                  shift_b, isd_b)
+        for r in range(R):
+            za = pa[:2 * na * k_pad[r]].view(2, na, k_pad[r])
+            _lib.call("mm_block_panels", dev, seg.vals, seg.rows, seg.seg_ptr, R, r, int(gs[r]), int(n_r[r]), inv_sf, ia,
+                      na, ca_r[r], inv_a_r[r], k_pad[r], za[0], za[1], w)
+            _lib.call("mm_block_gemm", dev, za[0], za[1], na, panels_b[r][0], panels_b[r][1], nb, k_pad[r], sc_a_r[r],
+                      sc_b_r[r], cross[r], nb)
+        _lib.call("mm_block_boot_update", dev, cross, shift_a, isd_a, shift_b, isd_b, gn, cfun, stat, R, na, nb,
+                  acc_sum, acc_sq, n_ext, n_ok, coef_last if (want_coef and b == num_boot - 1) else None)
+    se = torch.empty((na, nb), dtype=torch.float64, device=dev)
+    asl = torch.empty((na, nb), dtype=torch.float64, device=dev)
+    _lib.call("mm_block_boot_finish", dev, stat, acc_sum, acc_sq, n_ext, n_ok, na * nb, 1 if approx else 0, se, asl)
+    timer.stop("shared_block_bootstrap", ev)
+    return {"coef": stat, "se": se, "asl": asl, "n_ok": n_ok, "coef_last": coef_last, "usable": usable}

@@ -841,11 +841,18 @@ def _corr_from_cov(cov, var_1, var_2):
 
 
 def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=True, num_boot=10000,
-                  verbose=3, num_cpus=1, seed=0, workspace_bytes=4 << 30, **kwargs):
+                  verbose=3, num_cpus=1, seed=0, workspace_bytes=4 << 30, bootstrap="pair", **kwargs):
     """Hypothesis test for the correlation of the gene pairs of ``compute_2d_moments``.
     reference: main.py:418-520.  One value per pair (the reference stores a (T,) array into a scalar
     slot, main.py:509, which only works for one treatment column), unordered duplicates share the
-    result of their first occurrence, i == j pairs stay NaN."""
+    result of their first occurrence, i == j pairs stay NaN.
+
+    Build-only ``bootstrap``: ``"pair"`` (default) is the reference's per-pair compressed bootstrap
+    (bootstrap.py:119-157); ``"shared"`` -- for ``gene_pairs`` that are a full block A x B -- is the cell bootstrap that
+    scheme approximates, with ONE set of resampling counts per replicate shared by all pairs and one tensor-core GEMM
+    per group and replicate (csrc/sharedboot.cu); its ASL is the normal approximation (``approx=True``) or the
+    counting estimate (c + 1) / (n + 1) without the GEV refinement of the far tail.  Pairs with an unusable
+    correlation in some group fall back to the per-pair path."""
     if not inplace:
         adata = adata.copy()
     resampling = kwargs.pop("resampling", "bootstrap")
@@ -876,6 +883,30 @@ def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     n_all = idx1.shape[0]
     # unordered de-duplication, first occurrence computes (main.py:467-482)
     owner, uniq = _first_unordered(idx1, idx2)
+    if bootstrap not in ("pair", "shared"):
+        raise ValueError("bootstrap must be 'pair' or 'shared'")
+    shared_done = None
+    if bootstrap == "shared":
+        if resample_rep:
+            raise NotImplementedError("bootstrap='shared' does not combine with resample_rep")
+        block = _as_dense_block(idx1, idx2)
+        if block is None:
+            raise ValueError("bootstrap='shared' needs gene_pairs that form a full block A x B of at least %d pairs"
+                             % DENSE_BLOCK_MIN_PAIRS)
+        genes_a, genes_b, pos = block
+        tc_all = np.stack([mem["2d_moments"][g]["corr"] for g in groups], axis=1)       # (n_all, R), pair order
+        pos_blk = np.arange(n_all) if pos is None else pos
+        tc_blk = np.empty((genes_a.size * genes_b.size, R))
+        tc_blk[pos_blk] = tc_all
+        sums_d = st.seg.moments(st.inv_sf_sorted, st.timer)
+        res = engine.ht_2d_shared_block(st.seg, genes_a, genes_b, st.inv_sf_sorted, sums_d,
+                                        [mem["group_q"][g] for g in groups],
+                                        tc_blk.reshape(genes_a.size, genes_b.size, R), cov, tr, num_boot, seed, approx,
+                                        one_sample, timer=st.timer)
+        shared_done = {k: res[k].reshape(-1).cpu().numpy()[pos_blk] for k in ("coef", "se", "asl")}
+        shared_ok = res["usable"].reshape(-1)[pos_blk]
+        # the per-pair path below only sees the pairs the block path could not take
+        uniq = uniq[~shared_ok[uniq]]
     true_corr = np.stack([mem["2d_moments"][g]["corr"] for g in groups], axis=1)       # (n_all, R)
     out = {k: np.full(n_all, np.nan) for k in ("coef", "se", "asl")}
     per_item = 8 * (num_boot + 1) * (3 if not approx else 2)
@@ -898,6 +929,9 @@ def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     dup = owner >= 0
     for k in out:
         out[k][dup] = out[k][owner[dup]]
+    if shared_done is not None:
+        for k in out:
+            out[k][shared_ok] = shared_done[k][shared_ok]
     st.last_stats = stats_acc
     mem["2d_ht"] = {"treatment": treatment, "covariate": covariate, "corr_coef": out["coef"],
                     "corr_se": out["se"], "corr_asl": out["asl"]}

@@ -101,3 +101,102 @@ def test_compute_2d_moments_dense_block_vs_pair_path(monkeypatch):
             amp = scale[ok] / np.sqrt(np.abs(b["var_1"][ok] * b["var_2"][ok]))
             clipped = np.abs(b["corr"][ok]) == 1
             assert (np.abs(a["corr"][ok] - b["corr"][ok])[~clipped] <= 5e-6 * amp[~clipped] + 1e-12).all(), g
+
+
+# ----------------------------------------------------------------------------- shared-weight bootstrap of a block
+def _weighted_corr_coef(X, inv_sf, w, cells, ga, gb, q, cfun):
+    """numpy restatement of one replicate of the shared-weight bootstrap: per group the weighted covariance estimator of
+    reference estimator.py:214-218 / :171-174 with W = the cell resampling counts, correlation, clip, then the
+    regression functional across groups."""
+    coef = np.zeros((len(ga), len(gb)))
+    for r, idx in enumerate(cells):
+        ww, isf = w[idx].astype(np.float64), inv_sf[idx]
+        n = float(len(idx))
+        A = X[idx][:, ga].toarray() * isf[:, None]
+        B = X[idx][:, gb].toarray() * isf[:, None]
+        ma, mb = (ww[:, None] * A).sum(0) / n, (ww[:, None] * B).sum(0) / n
+        cov = (A * ww[:, None]).T @ B / n - np.outer(ma, mb)
+        def var(M, g):
+            raw = X[idx][:, g].toarray()
+            m2 = (ww[:, None] * (M ** 2 - (1 - q[r]) * raw * isf[:, None] ** 2)).sum(0) / n
+            return m2 - ((ww[:, None] * M).sum(0) / n) ** 2
+        va, vb = var(A, ga), var(B, gb)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            corr = cov / np.sqrt(np.outer(np.where(va > 0, va, np.nan), np.where(vb > 0, vb, np.nan)))
+        coef += cfun[r] * np.clip(corr, -1, 1)
+    return coef
+
+
+def test_shared_weight_bootstrap_replicate_vs_numpy_and_vs_pair_path(monkeypatch):
+    """bootstrap='shared' (csrc/sharedboot.cu): (1) one replicate with KNOWN cell counts equals the numpy restatement of
+    the weighted estimator to the tensor-core block's accuracy; (2) the Philox-drawn counts are a multinomial per
+    group; (3) through ht_2d_moments the standard errors and p-values agree with the reference's per-pair compressed
+    bootstrap (the scheme that approximates this one) within Monte-Carlo error."""
+    import scipy.stats as stats
+    from memento_b200 import engine, synth
+    monkeypatch.setattr(mm_main, "DENSE_BLOCK_MIN_PAIRS", 64)       # the test block is small
+    ad = synth.make_counts(3000, 90, n_conditions=2, n_types=2, q=0.07, seed=12)
+    memento.setup_memento(ad, "q")
+    memento.create_groups(ad, ["stim", "cell"])
+    memento.compute_1d_moments(ad, min_perc_group=0.9)
+    names = ad.var.index.tolist()
+    assert len(names) >= 40
+    A, B = names[:12], names[10:40]                       # overlapping gene sets: i == j pairs stay NaN
+    pairs = [(a, b) for a in A for b in B]
+    memento.compute_2d_moments(ad, pairs)
+    mem = ad.uns["memento"]
+    st, groups = mem["_b200"], mem["groups"]
+    cov, tr = synth.design_from_groups(groups, ["stim", "cell"])
+    R = len(groups)
+    d = st.device
+    # (1) one replicate with given counts
+    rng = np.random.default_rng(5)
+    n_cells = st.seg.n_cells
+    gs = st.seg.group_start_host
+    w = np.concatenate([rng.multinomial(int(gs[r + 1] - gs[r]), np.full(int(gs[r + 1] - gs[r]), 1.0 / (gs[r + 1] - gs[r])))
+                        for r in range(R)]).astype(np.int32)
+    ga = np.array([names.index(a) for a in A]); gb = np.array([names.index(b) for b in B])
+    tc = np.stack([mem["2d_moments"][g]["corr"] for g in groups], axis=1).reshape(len(A), len(B), R)
+    sums_d = st.seg.moments(st.inv_sf_sorted)
+    q = [mem["group_q"][g] for g in groups]
+    res = engine.ht_2d_shared_block(st.seg, ga, gb, st.inv_sf_sorted, sums_d, q, tc, cov.values, tr.values, 1, 0, True,
+                                    False, weights=torch.as_tensor(w[None, :], device=d), want_coef=True)
+    # numpy side in the ORIGINAL cell order: renumbered row k is original cell st.order[k]
+    X = ad.X.tocsr()
+    sf = ad.obs["memento_size_factor"].values
+    w_orig = np.empty(n_cells, dtype=np.int64); w_orig[st.order] = w
+    cells = [st.order[gs[r]:gs[r + 1]] for r in range(R)]
+    cmat, _ = engine.wls_functional(d, cov.values.astype(float), tr.values.astype(float), np.diff(gs).astype(float),
+                                    np.ones((1, R), np.uint8), False)
+    cfun = cmat[0, 0].cpu().numpy()
+    want = _weighted_corr_coef(X, 1.0 / sf, w_orig, cells, ga, gb, q, cfun)
+    got = res["coef_last"].cpu().numpy()
+    ok = res["usable"] & np.isfinite(want)
+    assert ok.sum() > 0.8 * ok.size
+    assert np.isnan(got[~res["usable"]]).all()
+    np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=2e-5)
+    # observed coefficient = the functional applied to the observed correlations
+    np.testing.assert_allclose(res["coef"].cpu().numpy()[ok], (tc * cfun[None, None, :]).sum(2)[ok], rtol=1e-12)
+    # (2) drawn counts: every group's counts sum to its size; cell counts look Poisson(1)-like (multinomial)
+    wd = torch.empty(n_cells, dtype=torch.int32, device=d)
+    dev_mod._lib.call("mm_cell_weights", d, st.seg.group_start, R, n_cells, 7, 3, wd)
+    wh = wd.cpu().numpy()
+    for r in range(R):
+        assert wh[gs[r]:gs[r + 1]].sum() == gs[r + 1] - gs[r]
+    assert abs(wh.var() - 1.0) < 0.08 and abs((wh == 0).mean() - np.exp(-1)) < 0.03
+    wd2 = torch.empty_like(wd)
+    dev_mod._lib.call("mm_cell_weights", d, st.seg.group_start, R, n_cells, 7, 4, wd2)
+    assert not torch.equal(wd, wd2)
+    # (3) end to end against the per-pair path
+    memento.ht_2d_moments(ad, cov, tr, num_boot=1500, resampling="bootstrap", approx=True, seed=1)
+    per_pair = {k: mem["2d_ht"][k].copy() for k in ("corr_coef", "corr_se", "corr_asl")}
+    memento.ht_2d_moments(ad, cov, tr, num_boot=1500, resampling="bootstrap", approx=True, seed=1, bootstrap="shared")
+    shared = mem["2d_ht"]
+    assert np.array_equal(np.isnan(shared["corr_coef"]), np.isnan(per_pair["corr_coef"]))
+    fin = np.isfinite(per_pair["corr_se"]) & np.isfinite(shared["corr_se"])
+    np.testing.assert_allclose(shared["corr_coef"][fin], per_pair["corr_coef"][fin], rtol=1e-9, atol=1e-12)
+    ratio = shared["corr_se"][fin] / per_pair["corr_se"][fin]
+    assert 0.9 < np.median(ratio) < 1.1, np.median(ratio)
+    assert np.percentile(np.abs(np.log(ratio)), 90) < 0.25
+    lg = -np.log10(np.maximum(shared["corr_asl"][fin], 1e-300)); lp = -np.log10(np.maximum(per_pair["corr_asl"][fin], 1e-300))
+    assert stats.spearmanr(lg, lp).statistic > 0.9
