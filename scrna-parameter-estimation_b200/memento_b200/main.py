@@ -711,19 +711,38 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
         i1_d = to_device(idx1, st.device, np.int32)
         i2_d = to_device(idx2, st.device, np.int32)
         prod = st.seg.pair_products(i1_d, i2_d, st.inv_sf_sorted, st.timer).cpu().numpy()  # (n_pairs, R)
-    for r, g in enumerate(groups):
-        q = mem["group_q"][g]
-        if block is not None:
+    if block is not None:
+        # covariance, correlation and the two variance vectors of every group on the device (element-wise glue over
+        # R x n_pairs values: 16 x 11 M for the configs[2] block), one read-back per array
+        dev = st.device
+        same_d = to_device(same, dev)
+        i1_d, i2_d = to_device(idx1, dev, np.int64), to_device(idx2, dev, np.int64)
+        s3_d = sums_d[3]
+        for r, g in enumerate(groups):
+            q = mem["group_q"][g]
             c = cross[r] if pos_d is None else cross[r][pos_d]
-            cov = c.cpu().numpy() / n_cells[r]                                             # centred: :226-231 in one step
-            cov[same] = cov[same] - (1 - q) * sums[3][idx1[same], r] / n_cells[r]         # estimator.py:229-230
-        else:
+            cov_d = c / n_cells[r]                                                         # centred: :226-231 in one step
+            corr_same = (1 - q) * s3_d[i1_d, r] / n_cells[r]                               # estimator.py:229-230
+            cov_d = torch.where(same_d, cov_d - corr_same, cov_d)
+            var_g = to_device(mem["1d_moments"][g][1], dev, np.float64)
+            v1, v2 = var_g[i1_d].clone(), var_g[i2_d].clone()
+            v1[v1 <= 0] = float("nan")                                                     # _corr_from_cov, :281-292
+            v2[v2 <= 0] = float("nan")
+            denom = torch.sqrt(v1 * v2)
+            corr_d = torch.where(torch.isfinite(denom), cov_d / denom, torch.full_like(cov_d, 5.0))
+            corr_d = corr_d.clamp(-1.0, 1.0)
+            # clamp maps NaN to NaN; the reference leaves cov / denom = NaN only where cov is NaN (never here)
+            out[g] = {"cov": cov_d.cpu().numpy(), "corr": corr_d.cpu().numpy(), "var_1": v1.cpu().numpy(),
+                      "var_2": v2.cpu().numpy()}
+    else:
+        for r, g in enumerate(groups):
+            q = mem["group_q"][g]
             p = prod[:, r] / n_cells[r]
             p[same] = p[same] - (1 - q) * sums[3][idx1[same], r] / n_cells[r]             # estimator.py:229-230
             cov = p - (sums[2][idx1, r] / n_cells[r]) * (sums[2][idx2, r] / n_cells[r])    # :231
-        var_1 = mem["1d_moments"][g][1][idx1]
-        var_2 = mem["1d_moments"][g][1][idx2]
-        out[g] = {"cov": cov, "corr": _corr_from_cov(cov, var_1, var_2), "var_1": var_1, "var_2": var_2}
+            var_1 = mem["1d_moments"][g][1][idx1]
+            var_2 = mem["1d_moments"][g][1][idx2]
+            out[g] = {"cov": cov, "corr": _corr_from_cov(cov, var_1, var_2), "var_1": var_1, "var_2": var_2}
     mem["2d_moments"] = out
     if not inplace:
         return adata
@@ -770,6 +789,17 @@ def _as_dense_block(idx1, idx2):
     n = idx1.shape[0]
     if n < DENSE_BLOCK_MIN_PAIRS:
         return None
+    # fast path: the pairs are itertools.product(A, B) in that order (two vectorised comparisons, no sort of n keys)
+    change = np.flatnonzero(idx1[1:] != idx1[:-1])
+    nb = int(change[0]) + 1 if change.size else n
+    if n % nb == 0:
+        ga, gb = idx1[::nb], idx2[:nb]
+        if (np.unique(ga).size == ga.size and np.unique(gb).size == gb.size
+                and np.array_equal(idx1.reshape(-1, nb), np.broadcast_to(ga[:, None], (ga.size, nb)))
+                and np.array_equal(idx2.reshape(-1, nb), np.broadcast_to(gb[None, :], (ga.size, nb)))):
+            order_a, order_b = np.argsort(ga, kind="stable"), np.argsort(gb, kind="stable")
+            if np.array_equal(order_a, np.arange(ga.size)) and np.array_equal(order_b, np.arange(gb.size)):
+                return ga.astype(np.int64), gb.astype(np.int64), None
     genes_a, pa = np.unique(idx1, return_inverse=True)
     genes_b, pb = np.unique(idx2, return_inverse=True)
     if genes_a.size * genes_b.size != n:
