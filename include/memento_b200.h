@@ -65,19 +65,24 @@ int mm_validate_counts(int device, void* stream, const float* data, int64_t nnz,
  *   mm_relayout_count : per-chunk per-gene counts, their exclusive prefix over every group's chunks (left in cnt)
  *                       and seg_len[gene * R + group]; the caller prefix-sums seg_len into seg_ptr [n_genes * R + 1].
  *   mm_relayout_fill  : vals_out / rows_out (new row ids) in segment order, rows ascending inside a segment.
- * sorted_rows != 0 (both calls alike): the column indices of every CSR row ascend (scipy's canonical form) and no
- * chunk has more than 256 rows -- the passes then run as a tiled transposition through shared memory with one
- * coalesced run per (chunk, gene) instead of 4-byte scatters; err_flag (nullable) is set to 1 when a row turns
- * out not to be sorted (the output is then undefined, never out of bounds).  Both paths give identical arrays.
+ * sorted_rows != 0 (both calls alike): the column indices of every CSR row ascend strictly (scipy's canonical form),
+ * no chunk has more than 256 rows and n_genes <= 100000 -- the passes then run as a tiled transposition through
+ * shared memory: mm_relayout_count streams every row once (strict-ascent check, counts, and row_block_ptr
+ * [(ceil(n_genes / 256) + 1)][n_rows] int32 = position inside new row r where every 256-gene block starts),
+ * mm_relayout_fill moves (<= 256 rows) x (256 genes) tiles with one coalesced run per (chunk, gene) instead of
+ * 4-byte scatters.  err_flag (required on this path) is set to 1 when a row turns out not to be canonical (the
+ * output is then undefined, never out of bounds).  n_rows = number of CSR rows.  Both paths give identical arrays.
  * Replaces: memento/main.py:115-132 + util.py:8-13 (per-group boolean scan + X[mask].tocsc() copy). */
 int mm_relayout_count(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                       const int32_t* order, const int32_t* chunk_row_lo, const int32_t* chunk_group,
                       const int32_t* group_chunk_lo, int32_t n_chunks, int32_t n_genes, int32_t R,
-                      int32_t* cnt, int64_t* seg_len, int32_t sorted_rows, int32_t* err_flag);
+                      int32_t* cnt, int64_t* seg_len, int32_t sorted_rows, int32_t* err_flag,
+                      int32_t* row_block_ptr, int64_t n_rows);
 int mm_relayout_fill(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                      const float* data, const int32_t* order, const int32_t* chunk_row_lo,
                      const int32_t* chunk_group, int32_t n_chunks, int32_t n_genes, int32_t R, int32_t* cnt,
-                     const int64_t* seg_ptr, float* vals_out, int32_t* rows_out, int32_t sorted_rows);
+                     const int64_t* seg_ptr, float* vals_out, int32_t* rows_out, int32_t sorted_rows,
+                     int32_t* err_flag, const int32_t* row_block_ptr, int64_t n_rows);
 
 /* One pass over the group-sorted CSC matrix: for every segment s,
  *   out[0*n_seg+s] = sum x          out[1*n_seg+s] = max x

@@ -37,15 +37,11 @@ def entry(ms, nbytes):
 
 VARIANTS = [
     {},
-    {"MM_MOMENTS_DB": "1"},
-    {"MM_MOMENTS_DB": "1", "MM_MOMENTS_THREADS": "640"},
-    {"MM_MOMENTS_DB": "1", "MM_MOMENTS_THREADS": "384"},
-    {"MM_MOMENTS_DB": "1", "MM_MOMENTS_CHUNK": "8"},
-    {"MM_MOMENTS_DB": "1", "MM_MOMENTS_CHUNK": "8", "MM_MOMENTS_THREADS": "768"},
-    {"MM_MOMENTS_DB": "1", "MM_MOMENTS_CHUNK": "8", "MM_MOMENTS_THREADS": "512"},
-    {"MM_MOMENTS_DB": "1", "MM_MOMENTS_KERNEL": "stream_l1"},
-    {"MM_MOMENTS_DB": "1", "MM_MOMENTS_KERNEL": "stream_l1", "MM_MOMENTS_CHUNK": "8"},
     {"MM_MOMENTS_KERNEL": "stream"},
+    {"MM_MOMENTS_KERNEL": "stream_l1"},
+    {"MM_MOMENTS_KERNEL": "stream", "MM_MOMENTS_CHUNK": "8"},
+    {"MM_MOMENTS_KERNEL": "stream", "MM_MOMENTS_CHUNK": "8", "MM_MOMENTS_THREADS": "768"},
+    {"MM_MOMENTS_KERNEL": "tile"},
 ]
 KEYS = sorted({k for v in VARIANTS for k in v})
 

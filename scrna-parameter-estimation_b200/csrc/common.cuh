@@ -24,7 +24,7 @@ struct Tuning {
     int moments_threads;    // MM_MOMENTS_THREADS (stream kernel): 512 / 640 / 768 / 896
     int moments_prefetch;   // MM_MOMENTS_PREFETCH: -1 unset
     int moments_chunk;      // MM_MOMENTS_CHUNK: spans per chunk, 1 / 4 / 8
-    int moments_db;         // MM_MOMENTS_DB (stream kernel): -1 unset, 1 = register double-buffering of the spans
+    int relayout_cfg;       // MM_RELAYOUT_CFG (tiled fill pass): -1 unset, 0..4 tile shapes
     int moments_cfg;        // MM_MOMENTS_CFG (tile kernel): -1 unset
     int moments_regime;     // MM_MOMENTS_REGIME
     int moments_w;          // MM_MOMENTS_W: lanes per segment of the generic kernel

@@ -548,7 +548,7 @@ __device__ __forceinline__ double warp_sum4(double sx, double s1, double s2, dou
     return keep;      // lanes 0-7: sum sx, 8-15: sum s1, 16-23: sum s2, 24-31: sum s3
 }
 
-template <bool kSmemTable, int kStreamThreads, bool kPrefetch, int kC, int kQ, bool kDB = false>
+template <bool kSmemTable, int kStreamThreads, bool kPrefetch, int kC, int kQ>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict__ rows,
                           const long long* __restrict__ seg_ptr, long long n_seg, long long nnz,
@@ -589,30 +589,6 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
     int s0 = first_seg(span), s1 = last_seg(span);
     int bl = window(span, s0, s1 - s0 + 1, 0);
     int s0_nx = first_seg(span + warps_total), s1_nx = last_seg(span + warps_total);
-    // ---- all streaming loads of a span: lane owns elements 128 q + 4 lane + {0..3}, q = 0..kQ-1 (g_lo = index of the
-    // span's first nonzero in the arrays; zeros beyond the end)
-    auto load_span = [&](long long g_lo, float4 (&v)[kQ], int4 (&r)[kQ]) {
-        if (nnz - g_lo >= kSpanQ) {
-            const float4* v4 = reinterpret_cast<const float4*>(vals + g_lo) + lane;
-            const int4* r4 = reinterpret_cast<const int4*>(rows + g_lo) + lane;
-#pragma unroll
-            for (int q = 0; q < kQ; ++q) { v[q] = ld_stream4(v4 + 32 * q); r[q] = ld_stream4(r4 + 32 * q); }
-        } else {     // ragged end of the arrays
-#pragma unroll
-            for (int q = 0; q < kQ; ++q) {
-                const long long e = g_lo + 128 * q + 4 * lane;
-                v[q].x = e < nnz ? vals[e] : 0.f;         r[q].x = e < nnz ? rows[e] : 0;
-                v[q].y = e + 1 < nnz ? vals[e + 1] : 0.f; r[q].y = e + 1 < nnz ? rows[e + 1] : 0;
-                v[q].z = e + 2 < nnz ? vals[e + 2] : 0.f; r[q].z = e + 2 < nnz ? rows[e + 2] : 0;
-                v[q].w = e + 3 < nnz ? vals[e + 3] : 0.f; r[q].w = e + 3 < nnz ? rows[e + 3] : 0;
-            }
-        }
-    };
-    float4 vA[kQ], vB[kQ];
-    int4 rA[kQ], rB[kQ];
-    if constexpr (kDB) {
-        if (span < n_spans) load_span(span * kChunkElems, vA, rA);
-    }
     for (; span < n_spans; span += warps_total) {
         const long long t_lo = span * kChunkElems;
         const int n = (int)((nnz - t_lo < kChunkElems) ? (nnz - t_lo) : kChunkElems);
@@ -664,21 +640,34 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
             advance();
         }
         int from = 0;
-        // ---- the span after (chunk span, offset sp_lo) in this warp's sequence: the next one of the chunk, or the first
-        // one of the warp's next chunk; nothing when the arrays end before it
-        auto load_next = [&](int sp_lo, float4 (&v)[kQ], int4 (&r)[kQ]) {
-            const long long g_nx = sp_lo + kSpanQ < n ? t_lo + sp_lo + kSpanQ : (span + warps_total) * kChunkElems;
-            if (g_nx < nnz) load_span(g_nx, v, r);
-        };
+#pragma unroll 1
+        for (int j = 0; j < kC; ++j) {
+        const int sp_lo = j * kSpanQ;                        // first element of this span inside the chunk
+        if (sp_lo >= n) break;
         // ---- the next span (of this chunk, or the first of the warp's next chunk) goes to L2 now (one 128-byte
         // line per lane and array): a register-free second buffer, so that its loads are L2 hits
-        auto prefetch_ahead = [&](int sp_lo) {
-            if (kPrefetch && (sp_lo & 1023) == 0) {          // one prefetch covers 32 lanes x 32 elements = 1024 nonzeros
-                const long long p_lo = (sp_lo + 1024 < kChunkElems ? t_lo + sp_lo + 1024 : (span + warps_total) * kChunkElems) + 32 * lane;
-                if (p_lo + 32 <= nnz) { prefetch_l2(vals + p_lo); prefetch_l2(rows + p_lo); }
+        if (kPrefetch && (sp_lo & 1023) == 0) {              // one prefetch covers 32 lanes x 32 elements = 1024 nonzeros
+            const long long p_lo = (sp_lo + 1024 < kChunkElems ? t_lo + sp_lo + 1024 : (span + warps_total) * kChunkElems) + 32 * lane;
+            if (p_lo + 32 <= nnz) { prefetch_l2(vals + p_lo); prefetch_l2(rows + p_lo); }
+        }
+        // ---- all streaming loads of the span: lane owns elements 128 q + 4 lane + {0..3}, q = 0..3
+        float4 v[kQ];
+        int4 r[kQ];
+        if (n - sp_lo >= kSpanQ) {
+            const float4* v4 = reinterpret_cast<const float4*>(vals + t_lo + sp_lo) + lane;
+            const int4* r4 = reinterpret_cast<const int4*>(rows + t_lo + sp_lo) + lane;
+#pragma unroll
+            for (int q = 0; q < kQ; ++q) { v[q] = ld_stream4(v4 + 32 * q); r[q] = ld_stream4(r4 + 32 * q); }
+        } else {     // ragged end of the arrays
+#pragma unroll
+            for (int q = 0; q < kQ; ++q) {
+                const int e = sp_lo + 128 * q + 4 * lane;
+                v[q].x = e < n ? vals[t_lo + e] : 0.f;         r[q].x = e < n ? rows[t_lo + e] : 0;
+                v[q].y = e + 1 < n ? vals[t_lo + e + 1] : 0.f; r[q].y = e + 1 < n ? rows[t_lo + e + 1] : 0;
+                v[q].z = e + 2 < n ? vals[t_lo + e + 2] : 0.f; r[q].z = e + 2 < n ? rows[t_lo + e + 2] : 0;
+                v[q].w = e + 3 < n ? vals[t_lo + e + 3] : 0.f; r[q].w = e + 3 < n ? rows[t_lo + e + 3] : 0;
             }
-        };
-        auto reduce_span = [&](int sp_lo, const float4 (&v)[kQ], const int4 (&r)[kQ]) {
+        }
 #pragma unroll
         for (int q = 0; q < kQ; ++q) {
             const int row_lo = sp_lo + 128 * q, row_hi = row_lo + 128;
@@ -714,34 +703,6 @@ seg_moments_stream_kernel(const float* __restrict__ vals, const int* __restrict_
                 if (cur >= np || from >= n || from >= row_hi) break;
             }
         }
-        };
-        if constexpr (kDB) {
-            // register double-buffering: span j + 1's loads are issued before span j is reduced, so a warp always has
-            // one span in flight (buffers alternate roles; a chunk has an even number of spans, and a ragged chunk is
-            // the warp's last, so every chunk starts with its first span in buffer A)
-            static_assert(kC % 2 == 0, "double-buffered chunks need an even number of spans");
-#pragma unroll 1
-            for (int j = 0; j < kC; j += 2) {
-                int sp_lo = j * kSpanQ;
-                if (sp_lo >= n) break;
-                prefetch_ahead(sp_lo);
-                load_next(sp_lo, vB, rB);
-                reduce_span(sp_lo, vA, rA);
-                sp_lo += kSpanQ;
-                if (sp_lo >= n) break;
-                prefetch_ahead(sp_lo);
-                load_next(sp_lo, vA, rA);
-                reduce_span(sp_lo, vB, rB);
-            }
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < kC; ++j) {
-                const int sp_lo = j * kSpanQ;                    // first element of this span inside the chunk
-                if (sp_lo >= n) break;
-                prefetch_ahead(sp_lo);
-                load_span(t_lo + sp_lo, vA, rA);
-                reduce_span(sp_lo, vA, rA);
-            }
         }
         // the last piece continues after the chunk
         if (cur < np && from < n) emit(true);
@@ -1000,7 +961,7 @@ static Tuning read_tuning() {
     u.moments_threads = env_int("MM_MOMENTS_THREADS", 0);
     u.moments_prefetch = env_int("MM_MOMENTS_PREFETCH", -1);
     u.moments_chunk = env_int("MM_MOMENTS_CHUNK", 0);
-    u.moments_db = env_int("MM_MOMENTS_DB", -1);
+    u.relayout_cfg = env_int("MM_RELAYOUT_CFG", -1);
     u.moments_cfg = env_int("MM_MOMENTS_CFG", -1);
     u.moments_regime = env_int("MM_MOMENTS_REGIME", 0);
     u.moments_w = env_int("MM_MOMENTS_W", 0);
@@ -1064,7 +1025,7 @@ static int launch_tile(cudaStream_t st, int n_sm, int regime, const float* vals,
     return check_launch("seg_moments_edge");
 }
 
-template <int kThreads, bool kPrefetch, int kC, int kQ, bool kDB = false>
+template <int kThreads, bool kPrefetch, int kC, int kQ>
 static int launch_stream(cudaStream_t st, int n_sm, const float* vals, const int32_t* rows, const long long* sp,
                          long long n_seg, long long nnz, const int32_t* chunk_seg, const double* inv_sf,
                          long long n_cells, double* out, double* edge, bool smem_table) {
@@ -1076,11 +1037,11 @@ static int launch_stream(cudaStream_t st, int n_sm, const float* vals, const int
     if (grid > need) grid = need;
     if (smem_table) {
         const size_t smem = (size_t)n_cells * sizeof(double);
-        MM_CUDA(cudaFuncSetAttribute(seg_moments_stream_kernel<true, kThreads, kPrefetch, kC, kQ, kDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        seg_moments_stream_kernel<true, kThreads, kPrefetch, kC, kQ, kDB><<<(unsigned)grid, kThreads, smem, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
+        MM_CUDA(cudaFuncSetAttribute(seg_moments_stream_kernel<true, kThreads, kPrefetch, kC, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        seg_moments_stream_kernel<true, kThreads, kPrefetch, kC, kQ><<<(unsigned)grid, kThreads, smem, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
                                                                                         inv_sf, (int)n_cells, out, edge);
     } else {
-        seg_moments_stream_kernel<false, kThreads, kPrefetch, kC, kQ, kDB><<<(unsigned)grid, kThreads, 0, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
+        seg_moments_stream_kernel<false, kThreads, kPrefetch, kC, kQ><<<(unsigned)grid, kThreads, 0, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
                                                                                       inv_sf, (int)n_cells, out, edge);
     }
     if (int s = check_launch("seg_moments_stream")) return s;
@@ -1157,25 +1118,13 @@ MM_EXPORT int mm_seg_moments(int device, void* stream, const float* vals, const 
             if (tune.moments_threads) threads = tune.moments_threads;      // tuning hooks
             if (tune.moments_prefetch >= 0) pf = tune.moments_prefetch != 0;
             const int chunk_spans = (tune.moments_chunk == 1 || tune.moments_chunk == 8) ? tune.moments_chunk : 4;   // 8: 256-nonzero spans
-#define MM_STREAM_ARGS st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table
-            if (tune.moments_db > 0) {       // register double-buffering (always with the L2 prefetch)
-                if (chunk_spans == 8) {      // 256-nonzero spans: 16 + 16 buffer registers
-                    if (threads == 768) return launch_stream<768, true, 8, 2, true>(MM_STREAM_ARGS);
-                    if (threads == 512) return launch_stream<512, true, 8, 2, true>(MM_STREAM_ARGS);
-                    return launch_stream<640, true, 8, 2, true>(MM_STREAM_ARGS);
-                }
-                if (threads == 640) return launch_stream<640, true, 4, 4, true>(MM_STREAM_ARGS);
-                if (threads == 384) return launch_stream<384, true, 4, 4, true>(MM_STREAM_ARGS);
-                return launch_stream<512, true, 4, 4, true>(MM_STREAM_ARGS);
-            }
-#define MM_STREAM(T, PF) (chunk_spans == 1 ? launch_stream<T, PF, 1, 4>(MM_STREAM_ARGS) \
-                        : chunk_spans == 8 ? launch_stream<T, PF, 8, 2>(MM_STREAM_ARGS) \
-                                           : launch_stream<T, PF, 4, 4>(MM_STREAM_ARGS))
+#define MM_STREAM(T, PF) (chunk_spans == 1 ? launch_stream<T, PF, 1, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
+                        : chunk_spans == 8 ? launch_stream<T, PF, 8, 2>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table) \
+                                           : launch_stream<T, PF, 4, 4>(st, n_sm, vals, rows, sp, n_seg, nnz, chunk_seg, inv_sf, n_cells, out, edge, smem_table))
             if (threads == 896) return pf ? MM_STREAM(896, true) : MM_STREAM(896, false);
             if (threads == 768) return pf ? MM_STREAM(768, true) : MM_STREAM(768, false);
             if (threads == 512) return pf ? MM_STREAM(512, true) : MM_STREAM(512, false);
             return pf ? MM_STREAM(640, true) : MM_STREAM(640, false);
-#undef MM_STREAM_ARGS
 #undef MM_STREAM
         }
         int cfg = 1, regime = 0;

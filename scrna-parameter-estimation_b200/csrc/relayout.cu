@@ -17,15 +17,23 @@
 //              + cnt[chunk][gene]++.  Rows ascend inside every segment by construction.
 //
 // That generic path scatters lone 4-byte stores and has one warp per chunk (round 1: 0.16 TB/s, 2.5 % of HBM).  When
-// the column indices of every CSR row ascend (scipy's canonical form) passes 1 and 3 run as a TILED transposition
-// through shared memory instead (relayout_tile_kernel): a CTA owns a chunk of <= 256 rows (one per thread) and walks a
-// range of 256-gene blocks.  Per block: every row's nonzeros of the block are found by walking the sorted row from where
-// the previous block ended (no search), their (gene, row) incidence goes into a 256 x 256 bit matrix in shared memory,
-// rank of an element inside its gene's run = popcount of the lower rows' bits -- so the block's nonzeros are placed
-// in a shared staging buffer sorted by (gene, row) with no ordering constraint between warps, and go out as one
-// coalesced run per gene (chunk rows x density elements: ~240 B on the 25k x 10k matrix) instead of 4-byte scatters.
-// Bit-identical to the generic path and to the stable sort (tests/test_gpu_relayout.py).
+// the column indices of every CSR row ascend strictly (scipy's canonical form) passes 1 and 3 run as a TILED
+// transposition through shared memory instead:
+//   1'. relayout_rowscan_kernel   a cluster of CTAs per chunk (<= 256 rows) streams the chunk's rows once, a warp per
+//       row with coalesced loads: canonical-form check, per-gene counts in shared memory (summed over the cluster's
+//       CTAs through distributed shared memory), and bnd[block][row] = position inside the row where every gene block
+//       starts
+//   3'. relayout_tile_fill_kernel a CTA moves (chunk) x (gene block) tiles: the extent of every (row, block) run is
+//       known from bnd, so a warp reads four runs at a time with independent coalesced loads (the next block's runs
+//       are prefetched to L2 meanwhile); the (row, gene) incidence goes into a 256 x 256 bit matrix in shared memory,
+//       rank of an element inside its gene's run = popcount of the lower rows' bits -- so the tile's nonzeros are
+//       placed in a staging buffer sorted by (gene, row) with no ordering constraint between warps, and go out as one
+//       coalesced run per gene (chunk rows x density elements: ~240 B on the 25k x 10k matrix).
+// Bit-identical to the generic path and to the stable sort (tests/test_gpu_relayout.py).  Measured (scripts/
+// ab_relayout.py, B200): 25k x 10k, 61 M nonzeros: 0.20 + 0.55 ms (round 2's thread-per-row tiles: 0.24 + 1.34 ms);
+// 1 M x 2500, 599 M nonzeros: 2.3 + 4.5 ms (was 14.1 ms).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <string.h>
 #include <mutex>
 #include <thread>
@@ -100,34 +108,179 @@ relayout_fill_kernel(RelayoutParams P, const long long* __restrict__ seg_ptr, fl
 }
 
 // ------------------------------------------------------------------ tiled path (sorted column indices)
+// Pass A (relayout_rowscan_kernel) streams every row ONCE with coalesced warp loads and leaves, besides the per-chunk
+// per-gene counts, the position inside the row where every 256-gene block starts (bnd[block][row]); pass C
+// (relayout_tile_fill_kernel) therefore knows the extent of every (row, block) run up front: a warp per row-run with
+// coalesced, mutually independent loads (round 2's kernel walked the sorted rows with one THREAD per row -- a chain of
+// control-dependent 16-byte loads, 7.2 warp instructions per nonzero at 23 active lanes -- and derived the
+// incidence bits twice).
 constexpr int kTileRows = 256;       // rows per chunk (bit-matrix height); chunks may be shorter
-constexpr int kTileGenes = 256;      // genes per block (bit-matrix width)
-constexpr int kTileThreads = 256;    // thread t <-> row t of the chunk (phases 1, 3), gene t of the block (phase 2)
-constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kStageCap = 6144;      // staged nonzeros per pass (48 KB); a denser block takes several passes
+constexpr int kScanThreads = 256;    // pass A: 8 warps, a warp per row
+constexpr int kScanLoads = 8;        // pass A: 32-index loads in flight per warp
+constexpr int kMaxTiledGenes = 100000;   // pass A keeps 16-bit counters of all genes in shared memory (<= 200 KB)
 
-struct TileSmem {
-    unsigned mask[kTileRows / 32][kTileGenes];          // bit (row & 31) of word [row >> 5][gene]
-    unsigned short wpre[kTileRows / 32][kTileGenes];    // nonzeros of the gene in the lower row words
-    int off[kTileGenes + 1];                            // exclusive scan of the block's per-gene counts
-    int wsum[kTileWarps];
-    float sval[kStageCap];
-    int srow[kStageCap];
+// grid = n_chunks x S CTAs, a thread-block CLUSTER of S CTAs per chunk (S = 1, 2, 4 or 8: a matrix of 25k cells has
+// only 98 chunks).  The cluster's warps share the chunk's rows (a warp per row, 8 x 32 indices in flight): strict-
+// ascent check, block starts, counts.  Counters are 16-bit halves of 32-bit words (a chunk has at most 256 rows, so a
+// count fits) in each CTA's own shared memory, updated with 32-bit shared-memory atomics; at the end every CTA adds
+// up its slice of the genes over the cluster's S counter arrays through distributed shared memory.
+template <bool kPacked>
+__global__ void __launch_bounds__(kScanThreads)
+relayout_rowscan_kernel(RelayoutParams P, int* __restrict__ bnd, long long n_rows_total, int tile_shift) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) unsigned s_cnt[];            // kPacked: [(n_genes + 1) / 2], else [n_genes]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = blockIdx.x / S;
+    const int r0 = P.chunk_row_lo[chunk], n_rows = P.chunk_row_lo[chunk + 1] - r0;
+    const int n_words = kPacked ? (P.n_genes + 1) >> 1 : P.n_genes;
+    const int n_blocks = (P.n_genes + (1 << tile_shift) - 1) >> tile_shift;
+    for (int i = tid; i < n_words; i += kScanThreads) s_cnt[i] = 0u;
+    __syncthreads();
+    bool bad = false;
+    // the warp's next row goes to L2 while it works on the current one (a row is ~10 KB: its loads are then L2 hits)
+    auto prefetch_row = [&](int t) {
+        if (t >= n_rows) return;
+        const long long cell = P.order ? P.order[r0 + t] : (long long)r0 + t;
+        const long long lo = P.indptr[cell], hi = P.indptr[cell + 1];
+        for (long long e = lo + 32 * lane; e < hi; e += 1024) prefetch_l2(P.indices + e);
+    };
+    prefetch_row(rank * (kScanThreads / 32) + warp);
+    for (int t = rank * (kScanThreads / 32) + warp; t < n_rows; t += S * (kScanThreads / 32)) {
+        prefetch_row(t + S * (kScanThreads / 32));
+        const long long r = r0 + t;
+        const long long cell = P.order ? P.order[r] : r;
+        const long long lo = P.indptr[cell];
+        const long long len_ll = P.indptr[cell + 1] - lo;
+        const int len = len_ll > 2147483647LL ? 2147483647 : (int)len_ll;
+        const int* row = P.indices + lo;
+        int* out = bnd + r;                                       // bnd[b * n_rows_total + r]
+        const unsigned long long stride = (unsigned long long)n_rows_total;
+        int prev_idx = -1;                                        // the element before this lane group's first
+        for (int base = 0; base < len; base += 32 * kScanLoads) {
+            int idx[kScanLoads];
+#pragma unroll
+            for (int u = 0; u < kScanLoads; ++u) {
+                const int k = base + 32 * u + lane;
+                idx[u] = k < len ? ld_stream(row + k) : 2147483647;
+            }
+#pragma unroll
+            for (int u = 0; u < kScanLoads; ++u) {
+                const int k = base + 32 * u + lane;
+                if (base + 32 * u >= len) break;
+                int pidx = __shfl_up_sync(kFull, idx[u], 1);
+                if (lane == 0) pidx = prev_idx;
+                prev_idx = __shfl_sync(kFull, idx[u], 31);
+                const bool in_range = (unsigned)idx[u] < (unsigned)P.n_genes;
+                // a lane past the end of the row (or a column index out of range) counts as block n_blocks: it closes
+                // the remaining blocks
+                const int blk = in_range ? idx[u] >> tile_shift : n_blocks;
+                const int pblk = (unsigned)pidx < (unsigned)P.n_genes ? pidx >> tile_shift : (pidx < 0 ? -1 : n_blocks);
+                bad |= in_range ? idx[u] <= pidx : k < len;
+                if (blk > pblk) {                                 // usually the next block: one predicated store
+                    const int pos = k < len ? k : len;
+                    out[(unsigned long long)(unsigned)blk * stride] = pos;
+                    if (blk > pblk + 1)                           // empty blocks in between
+                        for (int b = pblk + 1; b < blk; ++b) out[(unsigned long long)(unsigned)b * stride] = pos;
+                }
+                if (in_range) {
+                    if constexpr (kPacked) atomicAdd(&s_cnt[idx[u] >> 1], 1u << ((idx[u] & 1) << 4));
+                    else atomicAdd(&s_cnt[idx[u]], 1u);
+                }
+            }
+        }
+        const int prev_blk = (unsigned)prev_idx < (unsigned)P.n_genes ? prev_idx >> tile_shift : (prev_idx < 0 ? -1 : n_blocks);
+        // rows whose length is a multiple of 32 (and empty rows) have no lane past the end
+        if (lane == 0)
+            for (int b = prev_blk + 1; b <= n_blocks; ++b) out[(long long)b * n_rows_total] = len;
+    }
+    if (bad && P.err) *P.err = 1;
+    int* cnt = P.cnt + (long long)chunk * P.n_genes;
+    if (S == 1) {
+        __syncthreads();
+        if constexpr (kPacked) {
+            for (int g = tid; g < P.n_genes; g += kScanThreads) cnt[g] = (int)((s_cnt[g >> 1] >> ((g & 1) * 16)) & 0xffffu);
+        } else {
+            for (int g = tid; g < P.n_genes; g += kScanThreads) cnt[g] = (int)s_cnt[g];
+        }
+        return;
+    }
+    cluster.sync();
+    for (int w = rank * kScanThreads + tid; w < n_words; w += S * kScanThreads) {
+        unsigned sum = 0u;                                        // packed: both halves at once (a total is at most 256)
+        for (int q = 0; q < S; ++q) sum += cluster.map_shared_rank(s_cnt, q)[w];
+        if constexpr (kPacked) {
+            cnt[2 * w] = (int)(sum & 0xffffu);
+            if (2 * w + 1 < P.n_genes) cnt[2 * w + 1] = (int)(sum >> 16);
+        } else {
+            cnt[w] = (int)sum;
+        }
+    }
+    cluster.sync();                                               // nobody leaves while its counters are being read
+}
+
+template <int kGenes, int kCap>
+struct FillSmem {
+    unsigned mask[kTileRows / 32][kGenes];              // bit (row & 31) of word [row >> 5][gene]
+    int rank0[kTileRows / 32][kGenes];                  // staging slot of the gene's first nonzero in this row word
+    int off[kGenes + 1];                                // exclusive scan of the block's per-gene counts
+    long long gdelta[kGenes];                           // output position of staging slot s of gene j = gdelta[j] + s
+    int wsum[kGenes / 32];
+    long long run_lo[kTileRows];                        // first element of the row's run in the block
+    int run_len[kTileRows];
+    float sval[kCap];                                   // staged nonzeros of one pass; a denser tile takes several
+    unsigned char srow[kCap];                           // row inside the chunk
 };
 
-// grid = (n_chunks, n_split): CTA (c, s) handles the gene blocks [s * per, (s + 1) * per) of chunk c.
-// kFill == false: per-chunk per-gene counts -> cnt[c][gene];  kFill == true: cnt holds the exclusive prefix over the
-// group's chunks (relayout_scan_kernel) and the nonzeros are written to their final positions.
-//
-// Every THREAD walks its own row (round 2: one warp per row with 32-index loads was a chain of dependent loads per
-// warp -- 16 rows x 2 loads x ~1 us per block -- and ran at 0.4 TB/s; a lane per row keeps 256 independent loads in
-// flight per CTA, the 32-byte sectors a lane walks through stay in L1 between its consecutive 4-byte loads).
-template <bool kFill>
-__global__ void __launch_bounds__(kTileThreads)
-relayout_tile_kernel(RelayoutParams P, int blocks_per_cta, const long long* __restrict__ seg_ptr,
-                     float* __restrict__ vals_out, int* __restrict__ rows_out) {
+// Visits every nonzero of the tile: f(row t, k-th element of the run, position in the arrays).  A warp takes four
+// row-runs at a time, two elements per lane and run, so that eight coalesced loads per array are in flight; the
+// callers issue their loads in `fetch` (all eight before the first `use`).
+template <int kFillWarps, class Smem, class Fetch, class Use>
+__device__ __forceinline__ void for_each_run(const Smem& S, int n_rows, int warp, int lane, Fetch fetch, Use use) {
+    for (int t0 = warp; t0 < n_rows; t0 += 4 * kFillWarps) {
+        long long lo[4];
+        int len[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * kFillWarps;
+            len[u] = t < n_rows ? S.run_len[t] : 0;
+            lo[u] = t < n_rows ? S.run_lo[t] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (lane < len[u]) fetch(2 * u, lo[u] + lane);
+            if (lane + 32 < len[u]) fetch(2 * u + 1, lo[u] + lane + 32);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * kFillWarps;
+            if (lane < len[u]) use(2 * u, t);
+            if (lane + 32 < len[u]) use(2 * u + 1, t);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                           // runs longer than 64 elements
+            const int t = t0 + u * kFillWarps;
+            for (int k = 64 + lane; k < len[u]; k += 32) { fetch(0, lo[u] + k); use(0, t); }
+        }
+    }
+}
+
+// grid = (n_chunks, n_split): CTA (c, s) handles the gene blocks [s * per, (s + 1) * per) of chunk c.  cnt holds the
+// exclusive prefix of the per-chunk counts over the group's chunks (relayout_scan_kernel).  Per block: the (row, gene)
+// incidence goes into a 256 x 256 bit matrix in shared memory, the rank of an element inside its gene's run is the
+// popcount of the lower rows' bits, so the tile's nonzeros are placed in a staging buffer sorted by (gene, row) with
+// no ordering constraint between warps, and go out as one coalesced run per gene.
+template <int kTileGenes, int kStageCap, int kFillThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kFillThreads, kMinBlocks)
+relayout_tile_fill_kernel(RelayoutParams P, const int* __restrict__ bnd, long long n_rows_total, int blocks_per_cta,
+                          const long long* __restrict__ seg_ptr, float* __restrict__ vals_out,
+                          int* __restrict__ rows_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+    using Smem = FillSmem<kTileGenes, kStageCap>;
+    constexpr int kFillWarps = kFillThreads / 32;
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    if (P.err && *P.err) return;                    // pass A found an unsorted row: bnd is not usable
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = blockIdx.x;
     const int r0 = P.chunk_row_lo[chunk], n_rows = P.chunk_row_lo[chunk + 1] - r0;
@@ -135,117 +288,113 @@ relayout_tile_kernel(RelayoutParams P, int blocks_per_cta, const long long* __re
     const int b_lo = blockIdx.y * blocks_per_cta, b_hi = min(n_blocks, b_lo + blocks_per_cta);
     if (b_lo >= b_hi || n_rows <= 0) return;
     const int grp = P.chunk_group[chunk];
-    int* cnt = P.cnt + (long long)chunk * P.n_genes;
+    const int* cnt = P.cnt + (long long)chunk * P.n_genes;
 
-    // this thread's row: extent, and the first block's start by binary search (the column indices of a row ascend)
-    long long cur = 0, row_hi = 0;
+    long long row_base = 0;
+    int pos = 0;                                     // start of the current block inside this thread's row
     if (tid < n_rows) {
         const long long cell = P.order ? P.order[r0 + tid] : r0 + tid;
-        cur = P.indptr[cell];
-        row_hi = P.indptr[cell + 1];
-        if (b_lo > 0) {
-            const int g0 = b_lo * kTileGenes;
-            long long a = cur, b = row_hi;
-            while (a < b) {
-                const long long m = (a + b) >> 1;
-                if (__ldg(P.indices + m) < g0) a = m + 1; else b = m;
-            }
-            cur = a;
-        }
+        row_base = P.indptr[cell];
+        pos = __ldg(bnd + (long long)b_lo * n_rows_total + r0 + tid);
     }
-    for (int i = tid; i < (kTileRows / 32) * kTileGenes; i += kTileThreads) (&S.mask[0][0])[i] = 0u;
-    __syncthreads();
-    const unsigned bit = 1u << (tid & 31), below = bit - 1u;
-    const int w_row = tid >> 5;
+    for (int i = tid; i < (kTileRows / 32) * kTileGenes; i += kFillThreads) (&S.mask[0][0])[i] = 0u;
 
     for (int b = b_lo; b < b_hi; ++b) {
         const int g0 = b * kTileGenes, g1 = min(P.n_genes, g0 + kTileGenes);
-        // ---- phase 1: incidence bits of the block, one row per thread
-        // (128-bit loads once the position is 16-byte aligned: a lane's 4-byte loads would fetch every 32-byte
-        // sector eight times over)
-        long long nxt = cur;
-        {
-            auto visit = [&](int idx) -> bool {             // false: the row has left the block
-                if (idx >= g1) return false;
-                if (idx >= g0) atomicOr(&S.mask[w_row][idx - g0], bit);
-                else if (P.err) *P.err = 1;                 // an earlier block's gene after a later one: not sorted
-                ++nxt;
-                return true;
-            };
-            bool in = true;
-            while (in && nxt < row_hi && (nxt & 3)) in = visit(__ldg(P.indices + nxt));
-            while (in && nxt + 4 <= row_hi) {
-                const int4 q = __ldg(reinterpret_cast<const int4*>(P.indices + nxt));
-                in = visit(q.x) && visit(q.y) && visit(q.z) && visit(q.w);
+        if (tid < n_rows) {
+            const int nxt = __ldg(bnd + (long long)(b + 1) * n_rows_total + r0 + tid);
+            S.run_lo[tid] = row_base + pos;
+            S.run_len[tid] = nxt - pos;
+            pos = nxt;
+            if (b + 1 < b_hi) {      // the row's run of the next block goes to L2 now (at most 8 lines per array)
+                const int nxt2 = __ldg(bnd + (long long)(b + 2) * n_rows_total + r0 + tid);
+                const long long e1 = row_base + min(nxt2, nxt + 256);
+                for (long long e = (row_base + nxt) & ~31LL; e < e1; e += 32) {
+                    prefetch_l2(P.indices + e);
+                    prefetch_l2(P.data + e);
+                }
             }
-            while (in && nxt < row_hi) in = visit(__ldg(P.indices + nxt));
         }
         __syncthreads();
-        // ---- phase 2: per-gene counts, word prefixes, exclusive scan over the block's genes (thread = gene)
-        int c = 0;
-#pragma unroll
-        for (int w = 0; w < kTileRows / 32; ++w) {
-            S.wpre[w][tid] = (unsigned short)c;
-            c += __popc(S.mask[w][tid]);
+        // ---- phase 1: incidence bits
+        {
+            int idx[8];
+            for_each_run<kFillWarps>(S, n_rows, warp, lane,
+                         [&](int slot, long long e) { idx[slot] = __ldg(P.indices + e); },
+                         [&](int slot, int t) { atomicOr(&S.mask[t >> 5][idx[slot] - g0], 1u << (t & 31)); });
         }
-        if (!kFill) {
-            if (g0 + tid < g1) cnt[g0 + tid] = c;
-        } else {
-            int incl = c;
+        __syncthreads();
+        // ---- phase 2: per-gene counts, exclusive scan over the block's genes, first slot per (row word, gene), output
+        // position of the gene's run (thread = gene; the two global loads of all genes are in flight together)
+        int c = 0, incl = 0;
+        long long out_lo = 0;
+        if (tid < kTileGenes) {
+            if (g0 + tid < g1) out_lo = __ldg(seg_ptr + (long long)(g0 + tid) * P.R + grp) + cnt[g0 + tid];
+#pragma unroll
+            for (int w = 0; w < kTileRows / 32; ++w) c += __popc(S.mask[w][tid]);
+            incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int v = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl += v;
             }
             if (lane == 31) S.wsum[warp] = incl;
-            __syncthreads();
+        }
+        __syncthreads();
+        if (tid < kTileGenes) {
             int base = 0;
             for (int w = 0; w < warp; ++w) base += S.wsum[w];
-            S.off[tid] = base + incl - c;
+            int first = base + incl - c;
+            S.off[tid] = first;
+            S.gdelta[tid] = out_lo - first;
             if (tid == kTileGenes - 1) S.off[kTileGenes] = base + incl;
-            __syncthreads();
-            const int n_t = S.off[kTileGenes];
-            for (int win = 0; win < n_t; win += kStageCap) {
-                // ---- phase 3: stage the block's nonzeros sorted by (gene, row), one row per thread
-                {
-                    auto place = [&](int idx, float v) {
-                        const int j = idx - g0;
-                        if (j < 0) return;                  // unsorted input: reported by the count pass
-                        const int slot = S.off[j] + S.wpre[w_row][j] + __popc(S.mask[w_row][j] & below) - win;
-                        if (slot >= 0 && slot < kStageCap) {
-                            S.sval[slot] = v;
-                            S.srow[slot] = r0 + tid;
-                        }
-                    };
-                    long long e = cur;
-                    for (; e < nxt && (e & 3); ++e) place(__ldg(P.indices + e), __ldg(P.data + e));
-                    for (; e + 4 <= nxt; e += 4) {
-                        const int4 q = __ldg(reinterpret_cast<const int4*>(P.indices + e));
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(P.data + e));
-                        place(q.x, v.x); place(q.y, v.y); place(q.z, v.z); place(q.w, v.w);
-                    }
-                    for (; e < nxt; ++e) place(__ldg(P.indices + e), __ldg(P.data + e));
-                }
-                __syncthreads();
-                // ---- phase 4: one coalesced run per gene
-                for (int j = warp; j < g1 - g0; j += kTileWarps) {
-                    const int lo = max(S.off[j], win), hi = min(S.off[j + 1], win + kStageCap);
-                    if (lo >= hi) continue;
-                    const long long base_o = __ldg(seg_ptr + (long long)(g0 + j) * P.R + grp) + cnt[g0 + j] - S.off[j];
-                    for (int i = lo + lane; i < hi; i += 32) {
-                        vals_out[base_o + i] = S.sval[i - win];
-                        rows_out[base_o + i] = S.srow[i - win];
-                    }
-                }
-                __syncthreads();
+#pragma unroll
+            for (int w = 0; w < kTileRows / 32; ++w) {
+                S.rank0[w][tid] = first;
+                first += __popc(S.mask[w][tid]);
             }
         }
+        __syncthreads();
+        const int n_t = S.off[kTileGenes];
+        for (int win = 0; win < n_t; win += kStageCap) {
+            // ---- phase 3: stage the block's nonzeros sorted by (gene, row)
+            {
+                int idx[8];
+                float val[8];
+                for_each_run<kFillWarps>(S, n_rows, warp, lane,
+                             [&](int slot, long long e) { idx[slot] = __ldg(P.indices + e); val[slot] = __ldg(P.data + e); },
+                             [&](int slot, int t) {
+                                 const int j = idx[slot] - g0, w = t >> 5;
+                                 const int s = S.rank0[w][j] + __popc(S.mask[w][j] & ((1u << (t & 31)) - 1u)) - win;
+                                 if ((unsigned)s < (unsigned)kStageCap) {
+                                     S.sval[s] = val[slot];
+                                     S.srow[s] = (unsigned char)t;
+                                 }
+                             });
+            }
+            __syncthreads();
+            // ---- phase 4: the staged slots go out in order, one coalesced run per gene.  A warp owns a range of genes
+            // = a contiguous range of slots; every lane follows its slots' gene with a monotone pointer
+            {
+                constexpr int kGenesPerWarp = (kTileGenes + kFillWarps - 1) / kFillWarps;
+                const int j0 = warp * kGenesPerWarp, j1 = min(j0 + kGenesPerWarp, g1 - g0);
+                if (j0 < j1) {
+                    const int s_lo = max(S.off[j0], win), s_hi = min(S.off[j1], win + kStageCap);
+                    int g = j0;
+#pragma unroll 1
+                    for (int i = s_lo + lane; i < s_hi; i += 32) {
+                        while (i >= S.off[g + 1]) ++g;
+                        const long long d = S.gdelta[g] + i;
+                        vals_out[d] = S.sval[i - win];
+                        rows_out[d] = r0 + S.srow[i - win];
+                    }
+                }
+            }
+            __syncthreads();
+        }
         // ---- next block
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < kTileRows / 32; ++w) S.mask[w][tid] = 0u;
-        cur = nxt;
-        __syncthreads();
+        for (int i = tid; i < (kTileRows / 32) * kTileGenes; i += kFillThreads) (&S.mask[0][0])[i] = 0u;
+        // (the next iteration's first __syncthreads orders these stores before the next phase 1)
     }
 }
 
@@ -401,16 +550,38 @@ MM_EXPORT int mm_csr_check_sorted(int device, void* stream, const int64_t* indpt
     return check_launch("mm_csr_check_sorted");
 }
 
-static int tile_launch_shape(int n_chunks, int n_genes, int* blocks_per_cta, dim3* grid) {
-    const int n_blocks = (n_genes + kTileGenes - 1) / kTileGenes;
-    // enough CTAs for two waves of 3 per SM; a CTA walks at least one gene block
-    int split = (148 * 6 + n_chunks - 1) / (n_chunks > 0 ? n_chunks : 1);
+// Tile shapes of the fill pass (MM_RELAYOUT_CFG, read once at load): genes per block / staged nonzeros per pass / threads /
+// CTAs per SM.  The count pass writes the block starts at the same granularity, so both calls read the same setting.
+static int tile_cfg() {
+    const int c = tuning().relayout_cfg;
+    return (c >= 0 && c <= 4) ? c : 2;      // measured: 256-gene tiles, two 512-thread CTAs per SM (scripts/ab_relayout.py)
+}
+static int tile_genes_of(int cfg) { return (cfg == 2 || cfg == 3) ? 256 : 128; }
+
+static int tile_launch_shape(int n_chunks, int n_genes, int tile_genes, int* blocks_per_cta, dim3* grid) {
+    const int n_blocks = (n_genes + tile_genes - 1) / tile_genes;
+    // enough CTAs for a few waves of 2-3 per SM; a CTA walks at least one gene block
+    int split = (148 * 8 + n_chunks - 1) / (n_chunks > 0 ? n_chunks : 1);
     if (split < 1) split = 1;
     if (split > n_blocks) split = n_blocks;
     if (split > 65535) split = 65535;
     *blocks_per_cta = (n_blocks + split - 1) / split;
     *grid = dim3((unsigned)n_chunks, (unsigned)((n_blocks + *blocks_per_cta - 1) / *blocks_per_cta));
     return 0;
+}
+
+template <int kGenes, int kCap, int kThreads, int kMinBlocks>
+static int launch_tile_fill(cudaStream_t st, const RelayoutParams& P, const int* bnd, long long n_rows,
+                            const long long* seg_ptr, float* vals_out, int* rows_out) {
+    static_assert(kThreads >= kTileRows && kThreads >= kGenes, "a thread per row and per gene of the tile");
+    int per; dim3 grid;
+    tile_launch_shape(P.n_chunks, P.n_genes, kGenes, &per, &grid);
+    const size_t smem = sizeof(FillSmem<kGenes, kCap>);
+    MM_CUDA(cudaFuncSetAttribute(relayout_tile_fill_kernel<kGenes, kCap, kThreads, kMinBlocks>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    relayout_tile_fill_kernel<kGenes, kCap, kThreads, kMinBlocks><<<grid, kThreads, smem, st>>>(
+        P, bnd, n_rows, per, seg_ptr, vals_out, rows_out);
+    return check_launch("relayout_tile_fill");
 }
 
 MM_EXPORT int mm_validate_counts(int device, void* stream, const float* data, int64_t nnz, int32_t* flags) {
@@ -427,28 +598,44 @@ MM_EXPORT int mm_validate_counts(int device, void* stream, const float* data, in
 MM_EXPORT int mm_relayout_count(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                                 const int32_t* order, const int32_t* chunk_row_lo, const int32_t* chunk_group,
                                 const int32_t* group_chunk_lo, int32_t n_chunks, int32_t n_genes, int32_t R,
-                                int32_t* cnt, int64_t* seg_len, int32_t sorted_rows, int32_t* err_flag) {
+                                int32_t* cnt, int64_t* seg_len, int32_t sorted_rows, int32_t* err_flag,
+                                int32_t* row_block_ptr, int64_t n_rows) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_chunks >= 0 && n_genes > 0 && R > 0, "n_chunks/n_genes/R");
     MM_REQUIRE(indptr && chunk_row_lo && chunk_group && group_chunk_lo && cnt && seg_len, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    MM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)(n_chunks > 0 ? n_chunks : 1) * n_genes, st));
     RelayoutParams P;
     P.indptr = (const long long*)indptr; P.indices = indices; P.data = nullptr; P.order = order;
     P.chunk_row_lo = chunk_row_lo; P.chunk_group = chunk_group; P.n_chunks = n_chunks; P.n_genes = n_genes; P.R = R;
     P.cnt = cnt; P.err = err_flag;
     if (err_flag) MM_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int32_t), st));
-    if (n_chunks > 0 && sorted_rows) {      // tiled path: chunks of at most kTileRows rows (checked by the fill call too)
-        MM_REQUIRE(indices, "null pointer");
-        MM_REQUIRE(((uintptr_t)indices & 15) == 0, "tiled path: indices must be 16-byte aligned");
-        int per; dim3 grid;
-        tile_launch_shape(n_chunks, n_genes, &per, &grid);
-        MM_CUDA(cudaFuncSetAttribute(relayout_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TileSmem)));
-        relayout_tile_kernel<false><<<grid, kTileThreads, sizeof(TileSmem), st>>>(P, per, nullptr, nullptr, nullptr);
-        if (int s = check_launch("relayout_tile<count>")) return s;
+    if (n_chunks > 0 && sorted_rows) {      // tiled path: chunks of at most kTileRows rows (not checked: the caller's plan)
+        MM_REQUIRE(indices && row_block_ptr && err_flag, "tiled path: null pointer (indices / row_block_ptr / err_flag)");
+        MM_REQUIRE(n_genes <= kMaxTiledGenes, "tiled path: at most 100000 genes");
+        MM_REQUIRE(n_rows >= 0, "n_rows");
+        // 32-bit counters up to 24k genes (96 KB: two CTAs per SM), 16-bit halves above
+        const bool packed = n_genes > 24576;
+        const size_t smem = sizeof(unsigned) * (size_t)(packed ? (n_genes + 1) / 2 : n_genes);
+        auto kern = packed ? relayout_rowscan_kernel<true> : relayout_rowscan_kernel<false>;
+        MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int S = 1;                              // CTAs per chunk (cluster size): at least ~4 CTAs per SM when possible
+        while (S < 8 && (long long)n_chunks * S < 148 * 4) S *= 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_chunks * S);
+        cfg.blockDim = dim3(kScanThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MM_CUDA(cudaLaunchKernelEx(&cfg, kern, P, (int*)row_block_ptr, (long long)n_rows,
+                                   tile_genes_of(tile_cfg()) == 256 ? 8 : 7));
+        if (int s = check_launch("relayout_rowscan")) return s;
     } else if (n_chunks > 0) {
         MM_REQUIRE(indices, "null pointer");
+        MM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)n_chunks * n_genes, st));
         const int per = kRelayoutThreads / 32;
         relayout_count_kernel<<<(n_chunks + per - 1) / per, kRelayoutThreads, 0, st>>>(P);
         if (int s = check_launch("relayout_count")) return s;
@@ -462,7 +649,8 @@ MM_EXPORT int mm_relayout_count(int device, void* stream, const int64_t* indptr,
 MM_EXPORT int mm_relayout_fill(int device, void* stream, const int64_t* indptr, const int32_t* indices,
                                const float* data, const int32_t* order, const int32_t* chunk_row_lo,
                                const int32_t* chunk_group, int32_t n_chunks, int32_t n_genes, int32_t R, int32_t* cnt,
-                               const int64_t* seg_ptr, float* vals_out, int32_t* rows_out, int32_t sorted_rows) {
+                               const int64_t* seg_ptr, float* vals_out, int32_t* rows_out, int32_t sorted_rows,
+                               int32_t* err_flag, const int32_t* row_block_ptr, int64_t n_rows) {
     if (int s = enter(device)) return s;
     MM_REQUIRE(n_chunks >= 0 && n_genes > 0 && R > 0, "n_chunks/n_genes/R");
     if (n_chunks == 0) return 0;
@@ -471,16 +659,18 @@ MM_EXPORT int mm_relayout_fill(int device, void* stream, const int64_t* indptr, 
     RelayoutParams P;
     P.indptr = (const long long*)indptr; P.indices = indices; P.data = data; P.order = order;
     P.chunk_row_lo = chunk_row_lo; P.chunk_group = chunk_group; P.n_chunks = n_chunks; P.n_genes = n_genes; P.R = R;
-    P.cnt = cnt; P.err = nullptr;
+    P.cnt = cnt; P.err = err_flag;
     if (sorted_rows) {
-        MM_REQUIRE((((uintptr_t)indices | (uintptr_t)data) & 15) == 0, "tiled path: indices / data must be 16-byte aligned");
-        int per; dim3 grid;
-        tile_launch_shape(n_chunks, n_genes, &per, &grid);
-        MM_CUDA(cudaFuncSetAttribute(relayout_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TileSmem)));
-        relayout_tile_kernel<true><<<grid, kTileThreads, sizeof(TileSmem), (cudaStream_t)stream>>>(
-            P, per, (const long long*)seg_ptr, vals_out, rows_out);
-        return check_launch("relayout_tile<fill>");
+        MM_REQUIRE(row_block_ptr && err_flag && n_rows >= 0, "tiled path: row_block_ptr / err_flag / n_rows");
+        cudaStream_t st = (cudaStream_t)stream;
+        const long long* sp = (const long long*)seg_ptr;
+        switch (tile_cfg()) {
+            case 1: return launch_tile_fill<128, 12288, 256, 3>(st, P, row_block_ptr, n_rows, sp, vals_out, rows_out);
+            case 2: return launch_tile_fill<256, 16384, 512, 2>(st, P, row_block_ptr, n_rows, sp, vals_out, rows_out);
+            case 3: return launch_tile_fill<256, 24576, 512, 1>(st, P, row_block_ptr, n_rows, sp, vals_out, rows_out);
+            case 4: return launch_tile_fill<128, 8192, 256, 4>(st, P, row_block_ptr, n_rows, sp, vals_out, rows_out);
+            default: return launch_tile_fill<128, 12288, 384, 3>(st, P, row_block_ptr, n_rows, sp, vals_out, rows_out);
+        }
     }
     const int per = kRelayoutThreads / 32;
     relayout_fill_kernel<<<(n_chunks + per - 1) / per, kRelayoutThreads, 0, (cudaStream_t)stream>>>(

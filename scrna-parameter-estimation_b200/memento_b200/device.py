@@ -257,8 +257,10 @@ class SegMatrix:
         sizes = np.diff(gs)
         # chunks of consecutive rows of one group.  Tiled path (sorted rows): up to 256 rows (the height of the
         # kernel's bit matrix); the generic path: enough chunks to fill the GPU, few enough for the counter array
-        TILE_ROWS = 256         # kTileRows in csrc/relayout.cu
-        tiled = bool(csr.sorted_rows) and n_cells * float(n_genes) * 4 / TILE_ROWS <= 4e9
+        TILE_ROWS, TILE_GENES = 256, 128         # kTileRows and the smallest gene block of csrc/relayout.cu
+        n_blocks = (n_genes + TILE_GENES - 1) // TILE_GENES
+        tiled = (bool(csr.sorted_rows) and n_genes <= 100000 and n_cells * float(n_genes) * 4 / TILE_ROWS <= 4e9
+                 and (n_blocks + 1) * float(n_cells) * 4 <= 4e9)
         if tiled:
             rpc = TILE_ROWS
         else:
@@ -278,14 +280,16 @@ class SegMatrix:
         cnt = torch.empty(max(n_chunks, 1) * n_genes, dtype=torch.int32, device=dev)
         seg_ptr = torch.zeros(n_genes * R + 1, dtype=torch.int64, device=dev)
         err = torch.zeros(1, dtype=torch.int32, device=dev)
+        # tiled path: start of every 256-gene block inside every row, written by the count pass, read by the fill pass
+        bnd = torch.empty((n_blocks + 1) * n_cells, dtype=torch.int32, device=dev) if tiled else None
         ev = timer.start()
         _lib.call("mm_relayout_count", dev, csr.indptr, csr.indices, order_d, crl, cg, gcl, n_chunks, n_genes, R,
-                  cnt, seg_ptr[1:], 1 if tiled else 0, err)
+                  cnt, seg_ptr[1:], 1 if tiled else 0, err, bnd, n_cells)
         torch.cumsum(seg_ptr[1:], 0, out=seg_ptr[1:])
         vals = torch.empty(csr.nnz, dtype=torch.float32, device=dev)
         rows = torch.empty(csr.nnz, dtype=torch.int32, device=dev)
         _lib.call("mm_relayout_fill", dev, csr.indptr, csr.indices, csr.data, order_d, crl, cg, n_chunks, n_genes, R,
-                  cnt, seg_ptr, vals, rows, 1 if tiled else 0)
+                  cnt, seg_ptr, vals, rows, 1 if tiled else 0, err, bnd, n_cells)
         timer.stop("relayout", ev)
         if tiled and int(err.item()) != 0:
             raise _lib.MementoCudaError("adata.X claims canonical format but a row's column indices do not ascend; "
