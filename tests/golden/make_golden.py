@@ -9,7 +9,7 @@ The reference package ``memento`` is imported from /root/reference through the s
 own synthetic generator with fixed seeds; every reference call that consumes the global numpy RNG
 is preceded by an explicit ``np.random.seed`` recorded in the fixture, so the oracle (and the
 CUDA replay mode) can reproduce the exact call sequence.  Outputs: ``stages.npz``, ``ht1d.npz``,
-``ht2d.npz``, ``asl.npz``, ``stages_f32.npz``.
+``ht2d.npz``, ``asl.npz``, ``stages_f32.npz``, ``getters.npz``, ``gev_battery.npz``.
 """
 import os
 import sys
@@ -218,6 +218,25 @@ def asl_cases():
     print("asl.npz:", {k: float(v) for k, v in out.items() if k.endswith("_asl")})
 
 
+def gev_battery(n_cases=60):
+    """_compute_asl (hypothesis_test.py:57-141) on the rows of tests/helpers.py:gev_battery_vector: the fixture keeps
+    the reference's ASL, the extreme count and a checksum of every regenerated row (rows are not stored)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import gev_battery_vector
+    asl, cnt, chk, size = [], [], [], []
+    for i in range(n_cases):
+        x = gev_battery_vector(i)
+        null = x[1:] - x[0]
+        a = abs(x[0])
+        cnt.append(int((null > a).sum() + (null < -a).sum()))
+        asl.append(float(ref_ht._compute_asl(x.copy(), resampling="bootstrap")))
+        chk.append(float(np.sum(x * np.arange(1, x.size + 1))))
+        size.append(x.size)
+    np.savez_compressed(os.path.join(HERE, "gev_battery.npz"), asl=np.array(asl), extreme=np.array(cnt),
+                        checksum=np.array(chk), size=np.array(size))
+    print("gev_battery.npz:", n_cases, "rows,", int((np.array(cnt) <= 10).sum()), "in the GEV branch")
+
+
 def getters():
     """The reference's result getters (main.py:523-670) and BH correction (util.py:22-29) on a small fabricated
     ``uns['memento']`` (the getters only read the dictionary)."""
@@ -284,8 +303,8 @@ def getters():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "getters":
-        getters()
+    if len(sys.argv) > 1 and sys.argv[1] in ("getters", "gev_battery"):
+        {"getters": getters, "gev_battery": gev_battery}[sys.argv[1]]()
         sys.exit(0)
     ad = stages()
     stages_f32()
@@ -293,3 +312,4 @@ if __name__ == "__main__":
     ht2d(ad)
     asl_cases()
     getters()
+    gev_battery()

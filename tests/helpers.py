@@ -39,3 +39,24 @@ def assert_close(a, b, rtol, atol=0.0, what=""):
     err = np.abs(a[ok] - b[ok]) - (atol + rtol * np.abs(b[ok]))
     assert (err <= 0).all(), (what, "max excess", err.max(), "at", np.argmax(err),
                                a[ok][np.argmax(err)], b[ok][np.argmax(err)])
+
+
+def gev_battery_vector(i):
+    """Coefficient row i of the GEV battery (tests/golden/gev_battery.npz): x[0] = statistic, x[1:] = bootstrap
+    values around it.  Normal / Student-t(5) / skewed (centred gamma) nulls of 1000-10000 replicates with effects of
+    3-6 null standard deviations in either direction, i.e. the rows that reach the GEV branch of _compute_asl
+    (hypothesis_test.py:94-141) at the default num_boot."""
+    import numpy as np
+    rng = np.random.default_rng(1000 + i)
+    n = (1000, 2000, 4000, 10000)[i % 4]
+    kind = i % 3
+    z = (3.0, 3.5, 4.0, 5.0, 6.0)[i % 5]
+    sign = 1.0 if (i // 2) % 2 == 0 else -1.0
+    if kind == 0:
+        noise = rng.normal(0, 1, n)
+    elif kind == 1:
+        noise = rng.standard_t(5, n) / np.sqrt(5.0 / 3.0)
+    else:
+        noise = (rng.gamma(4.0, 1.0, n) - 4.0) / 2.0
+    stat = sign * z * 0.1
+    return np.concatenate([[stat], stat + 0.1 * noise])

@@ -469,6 +469,33 @@ def test_gev_tail_vs_reference():
             assert abs(np.log(got) - np.log(want)) < 0.05, (name, got, want)
 
 
+def test_gev_battery_vs_reference():
+    """60 coefficient rows (normal / t(5) / skewed nulls, 1000-10000 replicates, effects of 3-6 null standard
+    deviations; tests/helpers.py:gev_battery_vector) through the reference's _compute_asl (fixture gev_battery.npz):
+    the 42 rows in the GEV branch must be refined on the device too and agree in log p -- 0.05 for nine rows in ten
+    (both Nelder-Mead fits stop at xtol = ftol = 1e-4), 0.25 for every row (a fit that lands on the other side of the
+    KS threshold moves one rung down the tail-size ladder); the rows with more than 10 extreme replicates keep the
+    counting estimate exactly."""
+    from helpers import gev_battery_vector
+    g = load("gev_battery.npz")
+    dlog = []
+    for i in range(g["asl"].shape[0]):
+        x = gev_battery_vector(i)
+        assert x.size == int(g["size"][i])
+        np.testing.assert_allclose(np.sum(x * np.arange(1, x.size + 1)), g["checksum"][i], rtol=1e-12)
+        want, c_ref = float(g["asl"][i]), int(g["extreme"][i])
+        if c_ref > 10:
+            continue
+        got, status, c = _gev_device(x)
+        assert c == c_ref
+        assert status == 1, (i, got, want)
+        dlog.append(abs(np.log(got) - np.log(want)))
+    dlog = np.array(dlog)
+    assert dlog.size == 42
+    assert np.quantile(dlog, 0.9) < 0.05, np.sort(dlog)[-8:]
+    assert dlog.max() < 0.25, np.sort(dlog)[-8:]
+
+
 def test_ht_1d_replay_gev_branch(gpu_prepared, oracle_prepared):
     """Replay mode, default kwargs, B = 200 < 300 usable replicates: the reference's tail slices are
     then the whole null and its N_exec / n factor exceeds 1; the device path keeps the empirical

@@ -172,6 +172,17 @@ def test_asl_branches():
                      what=name + " approx")
 
 
+def test_asl_gev_battery():
+    """The oracle's compute_asl against the reference's on the first 12 rows of the GEV battery (regenerated rows are
+    checked against the fixture's checksums; scipy's fits are deterministic, so the match is to round-off)."""
+    from helpers import gev_battery_vector
+    g = load("gev_battery.npz")
+    for i in range(12):
+        x = gev_battery_vector(i)
+        np.testing.assert_allclose(np.sum(x * np.arange(1, x.size + 1)), g["checksum"][i], rtol=1e-12)
+        assert_close(testing.compute_asl(x.copy(), "bootstrap"), g["asl"][i], 1e-9, what="row %d" % i)
+
+
 def test_parallel_driver_matches_sequential_point_estimates(prepared):
     """num_cpus>1 uses a fork pool; coefficients (RNG-free, column 0) must not depend on it."""
     ad1, ad2 = prepared.copy(), prepared.copy()
