@@ -544,7 +544,7 @@ def ht_2d_shared_block(seg, idx_a, idx_b, inv_sf, sums_d, group_q, true_corr, co
     replicate one set of per-cell resampling counts shared by all pairs, one weighted tensor-core GEMM per group.
 
     ``idx_a`` / ``idx_b``: gene indices (numpy int); ``sums_d``: (5, G, R) device tensor of ``seg.moments``;
-    ``true_corr``: (|A|, |B|, R) host array of the observed correlations; pairs with a NaN or +-1 correlation in some
+    ``true_corr``: (|A|, |B|, R) host array or device tensor (any shape with that many values) of the observed correlations; pairs with a NaN or +-1 correlation in some
     group (reference hypothesis_test.py:325 drops such groups per pair) and i == j pairs are left NaN for the caller's
     per-pair path.  ``weights`` (tests): (num_boot, n_cells) int32 device tensor of resampling counts instead of the
     Philox draws.  Returns {"coef", "se", "asl"} float64 device tensors (|A|, |B|), "n_ok" and, with ``want_coef``,
@@ -558,13 +558,15 @@ def ht_2d_shared_block(seg, idx_a, idx_b, inv_sf, sums_d, group_q, true_corr, co
     # regression functional of the all-groups-valid design (one treatment column)
     cmat, _ = wls_functional(dev, covariate, treatment, n_r, np.ones((1, R), dtype=np.uint8), one_sample, timer)
     cfun = cmat[0, 0].contiguous()
-    with np.errstate(invalid="ignore"):
-        usable = ~(np.isnan(true_corr) | (np.abs(true_corr) == 1)).any(axis=2)
-    usable &= np.asarray(idx_a)[:, None] != np.asarray(idx_b)[None, :]
-    tc = torch.as_tensor(np.ascontiguousarray(np.nan_to_num(true_corr), dtype=np.float64), device=dev)
-    stat = (tc * cfun[None, None, :]).sum(dim=2)
-    stat[~torch.as_tensor(usable, device=dev)] = float("nan")
+    tc = true_corr if torch.is_tensor(true_corr) else torch.as_tensor(
+        np.ascontiguousarray(true_corr, dtype=np.float64), device=dev)
+    tc = tc.reshape(na, nb, R)
+    usable_d = ~(torch.isnan(tc) | (tc.abs() == 1)).any(dim=2)
+    usable_d &= ia[:, None] != ib[None, :]
+    stat = (torch.nan_to_num(tc, nan=0.0, posinf=0.0, neginf=0.0) * cfun[None, None, :]).sum(dim=2)
+    stat[~usable_d] = float("nan")
     stat = stat.contiguous()
+    usable = usable_d.cpu().numpy()
     gn = torch.as_tensor(n_r, device=dev)
     gq = torch.as_tensor(np.ascontiguousarray(group_q, dtype=np.float64), device=dev)
 

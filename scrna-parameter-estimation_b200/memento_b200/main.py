@@ -116,6 +116,43 @@ class LazyGroupCells:
         return getattr(self.materialize(), name)
 
 
+class LazyArrays(dict):
+    """A dict of numpy arrays (``uns['memento']['2d_moments'][group]``: cov, corr, var_1, var_2 per pair) whose values
+    are produced on first access: the dense-block path leaves 4 x R arrays of n_pairs float64 (5.8 GB for the
+    BASELINE configs[2] block) on the device, where ``ht_2d_moments`` reads them (``.dev``), and copies one to the
+    host only when somebody asks for it."""
+
+    def __init__(self, thunks, dev=None):
+        super().__init__({k: None for k in thunks})
+        self._thunks = dict(thunks)
+        self.dev = dict(dev or {})            # name -> device tensor
+
+    def __getitem__(self, key):
+        thunk = self._thunks.pop(key, None)
+        if thunk is not None:
+            super().__setitem__(key, thunk())
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in list(self.keys())]
+
+    def values(self):
+        return [self[k] for k in list(self.keys())]
+
+    def __deepcopy__(self, memo):              # adata.copy(): still lazy (the device tensors are never written to)
+        new = LazyArrays({}, self.dev)
+        for k in self.keys():                  # same key order
+            dict.__setitem__(new, k, None if k in self._thunks else np.array(dict.__getitem__(self, k)))
+        new._thunks = dict(self._thunks)
+        return new
+
+    def __reduce__(self):                      # pickles see plain arrays
+        return (dict, (dict(self.items()),))
+
+
 class _Section:
     """``with _Section(st, name):`` accumulates the wall time of a host-side section (device synchronised on both
     sides) in ``st.host_profile`` when setup_memento was called with ``profile=True``; free otherwise."""
@@ -725,15 +762,15 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
             corr_same = (1 - q) * s3_d[i1_d, r] / n_cells[r]                               # estimator.py:229-230
             cov_d = torch.where(same_d, cov_d - corr_same, cov_d)
             var_g = to_device(mem["1d_moments"][g][1], dev, np.float64)
-            v1, v2 = var_g[i1_d].clone(), var_g[i2_d].clone()
-            v1[v1 <= 0] = float("nan")                                                     # _corr_from_cov, :281-292
-            v2[v2 <= 0] = float("nan")
-            denom = torch.sqrt(v1 * v2)
+            var_g = torch.where(var_g > 0, var_g, torch.full_like(var_g, float("nan")))      # _corr_from_cov, :281-292
+            denom = torch.sqrt(var_g[i1_d] * var_g[i2_d])
             corr_d = torch.where(torch.isfinite(denom), cov_d / denom, torch.full_like(cov_d, 5.0))
             corr_d = corr_d.clamp(-1.0, 1.0)
             # clamp maps NaN to NaN; the reference leaves cov / denom = NaN only where cov is NaN (never here)
-            out[g] = {"cov": cov_d.cpu().numpy(), "corr": corr_d.cpu().numpy(), "var_1": v1.cpu().numpy(),
-                      "var_2": v2.cpu().numpy()}
+            var_h = var_g.cpu().numpy()
+            out[g] = LazyArrays({"cov": (lambda t=cov_d: t.cpu().numpy()), "corr": (lambda t=corr_d: t.cpu().numpy()),
+                                 "var_1": (lambda v=var_h: v[idx1]), "var_2": (lambda v=var_h: v[idx2])},
+                                dev={"cov": cov_d, "corr": corr_d})
     else:
         for r, g in enumerate(groups):
             q = mem["group_q"][g]
@@ -752,6 +789,21 @@ def _pair_indices(names, gene_pairs):
     """Column positions of the two genes of every pair (reference main.py:310-318, a Python loop over the pairs).
     ``gene_pairs``: the reference's list of (gene_1, gene_2) name tuples, or an (n, 2) array of names.  One transposing
     ``zip`` and two hashed look-ups of whole arrays -- the 1.5k x 10k block of BASELINE configs[2] is 15 M tuples."""
+    if isinstance(gene_pairs, np.ndarray) and gene_pairs.ndim == 2 and gene_pairs.shape[0] >= DENSE_BLOCK_MIN_PAIRS:
+        # itertools.product(A, B) as an array: look up |A| + |B| names instead of 2 |A| |B| (three vectorised
+        # comparisons of the name columns; pandas hashes 11 M strings per column in 1.5 s each otherwise)
+        first, second = gene_pairs[:, 0], gene_pairs[:, 1]
+        n = first.shape[0]
+        change = np.flatnonzero(first[1:] != first[:-1])
+        nb = int(change[0]) + 1 if change.size else n
+        if n % nb == 0:
+            a_names, b_names = first[::nb], second[:nb]
+            if ((first.reshape(-1, nb) == a_names[:, None]).all() and (second.reshape(-1, nb) == b_names[None, :]).all()):
+                ia, ib = names.get_indexer(pd.Index(a_names)), names.get_indexer(pd.Index(b_names))
+                if (ia < 0).any() or (ib < 0).any():
+                    bad = [g for g, i in zip(list(a_names) + list(b_names), np.concatenate([ia, ib])) if i < 0][:5]
+                    raise KeyError("gene_pairs: genes not in adata.var.index (after filtering): %s" % bad)
+                return np.repeat(ia.astype(int), nb), np.tile(ib.astype(int), a_names.shape[0])
     if isinstance(gene_pairs, np.ndarray):
         first, second = gene_pairs[:, 0], gene_pairs[:, 1]
     elif len(gene_pairs) == 0:
@@ -766,6 +818,17 @@ def _pair_indices(names, gene_pairs):
     return idx1.astype(int), idx2.astype(int)
 
 
+def _stacked_corr(mem, groups, device):
+    """(n_pairs, R) float64 device tensor of the observed correlations of ``compute_2d_moments``: straight from the
+    device copies the dense-block path keeps (LazyArrays.dev), uploaded otherwise."""
+    cols = []
+    for g in groups:
+        rec = mem["2d_moments"][g]
+        d = rec.dev.get("corr") if isinstance(rec, LazyArrays) else None
+        cols.append(d if d is not None and d.device == device else to_device(np.asarray(rec["corr"]), device, np.float64))
+    return torch.stack(cols, dim=1)
+
+
 def _first_unordered(idx1, idx2):
     """Unordered de-duplication of the pairs (reference main.py:467-482: a frozenset per pair): ``owner[k]`` = first
     pair with the same two genes (-1 for i == j pairs, which stay NaN) and the sorted list of those first pairs."""
@@ -776,6 +839,34 @@ def _first_unordered(idx1, idx2):
     owner = first[inverse.reshape(-1)].astype(np.int64)
     owner[idx1 == idx2] = -1
     uniq = np.unique(owner[owner >= 0])
+    return owner, uniq
+
+
+def _first_unordered_block(genes_a, genes_b, pos):
+    """_first_unordered for the pairs of a full block A x B (sorted unique gene lists, ``pos`` as in _as_dense_block)
+    without sorting the pairs: the mirror image (b, a) of pair (a, b) exists iff a is in B and b is in A, and its
+    position follows from the two positions."""
+    na, nb = genes_a.size, genes_b.size
+    n = na * nb
+
+    def position(of, inside):                  # position of every gene of `of` in `inside`, -1 when absent
+        p = np.searchsorted(inside, of)
+        p[p >= inside.size] = 0
+        return np.where(inside[p] == of, p, -1).astype(np.int64)
+    pa_of_b, pb_of_a = position(genes_b, genes_a), position(genes_a, genes_b)
+    blk = np.arange(n, dtype=np.int64)
+    ia, ib = blk // nb, blk % nb
+    mirror_ok = (pa_of_b[ib] >= 0) & (pb_of_a[ia] >= 0)
+    mirror = np.where(mirror_ok, pa_of_b[ib] * nb + pb_of_a[ia], blk)       # block position of (b, a)
+    if pos is None:
+        owner = np.minimum(blk, mirror)
+    else:                                       # first occurrence in PAIR order: pos[k] = block position of pair k
+        inv = np.empty(n, dtype=np.int64)
+        inv[pos] = np.arange(n, dtype=np.int64)
+        owner = np.minimum(np.arange(n, dtype=np.int64), inv[mirror[pos]])
+        ia, ib = ia[pos], ib[pos]
+    owner[genes_a[ia] == genes_b[ib]] = -1
+    uniq = np.flatnonzero(owner == np.arange(n, dtype=np.int64))
     return owner, uniq
 
 
@@ -911,23 +1002,26 @@ def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
     one_sample = bool((tr == 1).mean() == 1)
     idx1, idx2 = mem["2d_moments"]["gene_idx_1"], mem["2d_moments"]["gene_idx_2"]
     n_all = idx1.shape[0]
-    # unordered de-duplication, first occurrence computes (main.py:467-482)
-    owner, uniq = _first_unordered(idx1, idx2)
     if bootstrap not in ("pair", "shared"):
         raise ValueError("bootstrap must be 'pair' or 'shared'")
+    block = _as_dense_block(idx1, idx2) if bootstrap == "shared" else None
+    # unordered de-duplication, first occurrence computes (main.py:467-482)
+    owner, uniq = _first_unordered(idx1, idx2) if block is None else _first_unordered_block(*block)
     shared_done = None
     if bootstrap == "shared":
         if resample_rep:
             raise NotImplementedError("bootstrap='shared' does not combine with resample_rep")
-        block = _as_dense_block(idx1, idx2)
         if block is None:
             raise ValueError("bootstrap='shared' needs gene_pairs that form a full block A x B of at least %d pairs"
                              % DENSE_BLOCK_MIN_PAIRS)
         genes_a, genes_b, pos = block
-        tc_all = np.stack([mem["2d_moments"][g]["corr"] for g in groups], axis=1)       # (n_all, R), pair order
+        tc_all = _stacked_corr(mem, groups, st.device)                                   # (n_all, R) on the device
         pos_blk = np.arange(n_all) if pos is None else pos
-        tc_blk = np.empty((genes_a.size * genes_b.size, R))
-        tc_blk[pos_blk] = tc_all
+        if pos is None:
+            tc_blk = tc_all
+        else:
+            tc_blk = torch.empty_like(tc_all)
+            tc_blk[to_device(pos_blk, st.device, np.int64)] = tc_all
         sums_d = st.seg.moments(st.inv_sf_sorted, st.timer)
         res = engine.ht_2d_shared_block(st.seg, genes_a, genes_b, st.inv_sf_sorted, sums_d,
                                         [mem["group_q"][g] for g in groups],
@@ -937,7 +1031,7 @@ def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         shared_ok = res["usable"].reshape(-1)[pos_blk]
         # the per-pair path below only sees the pairs the block path could not take
         uniq = uniq[~shared_ok[uniq]]
-    true_corr = np.stack([mem["2d_moments"][g]["corr"] for g in groups], axis=1)       # (n_all, R)
+    true_corr_d = _stacked_corr(mem, groups, st.device)                                  # (n_all, R) on the device
     out = {k: np.full(n_all, np.nan) for k in ("coef", "se", "asl")}
     per_item = 8 * (num_boot + 1) * (3 if not approx else 2)
     pairs_per_tile = int(max(1, min(65535 // R, workspace_bytes // (per_item * R))))
@@ -949,7 +1043,8 @@ def ht_2d_moments(adata, covariate, treatment, treatment_for_gene=None, inplace=
         ga, gb = st.gene_index[a] + st.gene_offset, st.gene_index[b] + st.gene_offset
         pid = np.minimum(ga, gb) * (1 << 31) + np.maximum(ga, gb)                        # order-free stream id
         pair_id = to_device(pid, st.device, np.int64)
-        res = engine.ht_2d_tile(st.seg, st.design, st.cell_bin, a, b, true_corr[sel], cov, tr, num_boot, seed, approx,
+        true_corr = true_corr_d[to_device(sel, st.device, np.int64)].cpu().numpy()
+        res = engine.ht_2d_tile(st.seg, st.design, st.cell_bin, a, b, true_corr, cov, tr, num_boot, seed, approx,
                                 one_sample, want_coef_rows=not approx, pair_id=pair_id, timer=st.timer,
                                 stats=stats_acc, resample_rep=resample_rep)
         if not approx:

@@ -111,3 +111,54 @@ def test_pair_index_helpers_equal_the_reference_loops():
     assert np.array_equal(owner, want)
     assert uniq.tolist() == sorted(set(first.values()))
     assert mmain._pair_indices(names, [])[0].size == 0
+
+
+def test_pair_indices_product_fast_path_and_lazy_arrays():
+    """itertools.product(A, B) as an array takes the |A| + |B| look-up; near-products (one entry changed, a ragged
+    tail) fall back to the per-name look-up with the same answer.  LazyArrays materialises on access only."""
+    import copy
+    import itertools
+    import pandas as pd
+    from memento_b200 import main as mmain
+    names = pd.Index(["g%d" % i for i in range(300)])
+    A, B = ["g%d" % i for i in range(5, 75)], ["g%d" % i for i in range(100, 170)]
+    prod = np.array(list(itertools.product(A, B)))
+    assert prod.shape[0] >= mmain.DENSE_BLOCK_MIN_PAIRS
+    want1 = np.array([int(a[1:]) for a, _ in prod]); want2 = np.array([int(b[1:]) for _, b in prod])
+    for arr in (prod, prod.astype(object)):
+        i1, i2 = mmain._pair_indices(names, arr)
+        assert np.array_equal(i1, want1) and np.array_equal(i2, want2)
+    broken = prod.copy(); broken[777, 1] = "g3"; want2b = want2.copy(); want2b[777] = 3
+    i1, i2 = mmain._pair_indices(names, broken)
+    assert np.array_equal(i1, want1) and np.array_equal(i2, want2b)
+    i1, i2 = mmain._pair_indices(names, prod[:-3])
+    assert np.array_equal(i1, want1[:-3]) and np.array_equal(i2, want2[:-3])
+    with pytest.raises(KeyError):
+        bad = prod.copy(); bad[:, 1][bad[:, 1] == "g100"] = "zzz"
+        mmain._pair_indices(names, bad)
+    calls = []
+    lz = mmain.LazyArrays({"cov": lambda: calls.append("cov") or np.arange(3.0), "corr": lambda: calls.append("corr") or np.ones(3)})
+    assert set(lz.keys()) == {"cov", "corr"} and calls == []
+    assert lz["cov"].tolist() == [0.0, 1.0, 2.0] and lz["cov"] is lz["cov"] and calls == ["cov"]
+    cp = copy.deepcopy(lz)
+    assert calls == ["cov"] and cp["cov"] is not lz["cov"]
+    assert [k for k, _ in cp.items()] == ["cov", "corr"] and calls == ["cov", "corr"]
+    assert lz.get("nope", 7) == 7
+
+
+@pytest.mark.parametrize("shuffled", [False, True])
+def test_first_unordered_block_equals_the_sorting_version(shuffled):
+    """The analytic de-duplication of a full block A x B (A and B overlapping, so mirror pairs exist) against
+    _first_unordered, in product order and in a shuffled pair order."""
+    from memento_b200 import main as mmain
+    rng = np.random.default_rng(3)
+    ga = np.sort(rng.choice(400, 70, replace=False)); gb = np.sort(np.concatenate([ga[::2], rng.choice(np.arange(400, 500), 40, replace=False)]))
+    idx1, idx2 = np.repeat(ga, gb.size), np.tile(gb, ga.size)
+    if shuffled:
+        p = rng.permutation(idx1.size)
+        idx1, idx2 = idx1[p], idx2[p]
+    blk = mmain._as_dense_block(idx1, idx2)
+    assert blk is not None and (blk[2] is None) == (not shuffled)
+    want_owner, want_uniq = mmain._first_unordered(idx1, idx2)
+    owner, uniq = mmain._first_unordered_block(*blk)
+    assert np.array_equal(owner, want_owner) and np.array_equal(uniq, want_uniq)
