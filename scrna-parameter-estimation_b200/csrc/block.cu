@@ -111,6 +111,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    // the tile lands at the same shared-memory offset, and signals the barrier at the same offset, in every CTA of cta_mask
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -125,22 +144,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // kChunkBlocks k-blocks (256 cells, error <= ~4e-6 of the chunk); the epilogue warps add the chunks up in
 // float64 registers while the MMA warp already fills the other accumulator pair (TMEM is double buffered:
 // 2 x (128 + 128) columns = all 512).
+//
+// kCl == 2: the launch groups the tiles into 2 x 2 thread-block clusters.  The two CTAs of a cluster row work on the
+// same 128 rows of A, the two of a cluster column on the same 128 rows of B: every CTA fetches HALF of its A tile
+// and half of its B tile (64 rows each, tensor maps with 64-row boxes) and TMA-multicasts them to the peer that
+// needs the same rows, so a k-block costs 32 KB of L2 reads per CTA instead of 64 KB.  A ring slot may be refilled
+// once this CTA AND the two peers its loads write into have read it: the MMA warp's tcgen05.commit arrives on the
+// empty barrier of all three.  Measured on the configs[2] block: no faster than the single-CTA kernel (the operand
+// traffic is not what limits it), so the launch uses it only on request (MM_BLOCK_CLUSTER=2).
+template <int kCl>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                   int k_blocks, int M, int N, const double* __restrict__ scale_a, const double* __restrict__ scale_b,
-                  double* __restrict__ out, long long ldo, int vec_ok) {
+                  double* __restrict__ out, long long ldo, int vec_ok, int tiles_n, int tiles_m, int debug) {
     extern __shared__ unsigned char smem_raw[];
     // 128-byte-swizzled operand tiles need a 1024-byte aligned base (the launch adds 1 KB of slack)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.y, n_blk = blockIdx.x;
     const int n_chunks = (k_blocks + kChunkBlocks - 1) / kChunkBlocks;
+    // PERSISTENT: the grid is one CTA (kCl == 2: one cluster of four) per SM (group); a CTA walks the units
+    // unit0, unit0 + stride, ...  A unit is one 128 x 128 tile (kCl == 2: a 2 x 2 group of tiles, this CTA's tile is
+    // (2 bx + cx, 2 by + cy)).  The ring-slot and accumulator-buffer counters run on across tiles, so the producer
+    // and the MMA warp are already in the next tile while the epilogue warps scale and store the previous one.
+    constexpr int kCtasPerUnit = kCl == 2 ? 4 : 1;
+    const int units_n = tiles_n / kCl, n_units = units_n * (tiles_m / kCl);
+    const int unit0 = blockIdx.x / kCtasPerUnit, unit_stride = gridDim.x / kCtasPerUnit;
 
+    uint32_t rank = 0;
+    if constexpr (kCl == 2) rank = cluster_ctarank();       // cx + 2 cy: position inside the 2 x 2 group of tiles
+    const int cx = rank & 1, cy = rank >> 1;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCl == 2 ? 3 : 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], kEpiWarps); }
         mbar_init_fence();
     }
@@ -150,98 +187,125 @@ block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kCl == 2) cluster_sync_all();             // the peers' barriers exist before anything is sent to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                const int s = kb % kGemmStages;
-                if (kb >= kGemmStages) mbar_wait(&empty_bar[s], ((kb / kGemmStages) & 1) ^ 1);
-                unsigned char* st = smem + (size_t)s * kStageBytes;
-                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_2d(st, &map_a_hi, &full_bar[s], kb * kBK, m_blk * kBM);
-                tma_load_2d(st + kOperandBytes, &map_a_lo, &full_bar[s], kb * kBK, m_blk * kBM);
-                tma_load_2d(st + 2 * kOperandBytes, &map_b_hi, &full_bar[s], kb * kBK, n_blk * kBN);
-                tma_load_2d(st + 3 * kOperandBytes, &map_b_lo, &full_bar[s], kb * kBK, n_blk * kBN);
+            uint32_t it = 0;                                  // k-blocks issued so far, over all tiles
+            for (int u = unit0; u < n_units; u += unit_stride) {
+                const int n_blk = (u % units_n) * kCl + cx, m_blk = (u / units_n) * kCl + cy;
+                for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const int s = it % kGemmStages;
+                    if (it >= kGemmStages) mbar_wait(&empty_bar[s], ((it / kGemmStages) & 1) ^ 1);
+                    unsigned char* st = smem + (size_t)s * kStageBytes;
+                    if (debug == 2 && it >= kGemmStages) { mbar_arrive(&full_bar[s]); continue; }     // timing experiment: no reloads
+                    mbar_arrive_expect_tx(&full_bar[s], kStageBytes);     // own halves + the peers' halves
+                    if constexpr (kCl == 2) {
+                        constexpr int kHalf = kOperandBytes / 2;           // 64 rows x 128 bytes
+                        const uint16_t mask_a = (uint16_t)(0x3u << (2 * cy)), mask_b = (uint16_t)(0x5u << cx);
+                        tma_load_2d_mc(st + cx * kHalf, &map_a_hi, &full_bar[s], kb * kBK, m_blk * kBM + cx * (kBM / 2), mask_a);
+                        tma_load_2d_mc(st + kOperandBytes + cx * kHalf, &map_a_lo, &full_bar[s], kb * kBK, m_blk * kBM + cx * (kBM / 2), mask_a);
+                        tma_load_2d_mc(st + 2 * kOperandBytes + cy * kHalf, &map_b_hi, &full_bar[s], kb * kBK, n_blk * kBN + cy * (kBN / 2), mask_b);
+                        tma_load_2d_mc(st + 3 * kOperandBytes + cy * kHalf, &map_b_lo, &full_bar[s], kb * kBK, n_blk * kBN + cy * (kBN / 2), mask_b);
+                    } else {
+                        tma_load_2d(st, &map_a_hi, &full_bar[s], kb * kBK, m_blk * kBM);
+                        tma_load_2d(st + kOperandBytes, &map_a_lo, &full_bar[s], kb * kBK, m_blk * kBM);
+                        tma_load_2d(st + 2 * kOperandBytes, &map_b_hi, &full_bar[s], kb * kBK, n_blk * kBN);
+                        tma_load_2d(st + 3 * kOperandBytes, &map_b_lo, &full_bar[s], kb * kBK, n_blk * kBN);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = F16, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-            for (int c = 0; c < n_chunks; ++c) {
-                const int buf = c & 1;
-                if (c >= 2) mbar_wait(&tmem_empty[buf], ((c >> 1) & 1) ^ 1);      // the epilogue has drained this pair
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc0 = tmem_base + buf * (2 * kBN), acc1 = acc0 + kBN;
-                const int kb_end = min(k_blocks, (c + 1) * kChunkBlocks);
-                for (int kb = c * kChunkBlocks; kb < kb_end; ++kb) {
-                    const int s = kb % kGemmStages;
-                    mbar_wait(&full_bar[s], (kb / kGemmStages) & 1);
+            uint32_t it = 0, ch = 0;                          // k-blocks / chunks issued so far, over all tiles
+            for (int u = unit0; u < n_units; u += unit_stride) {
+                for (int c = 0; c < n_chunks; ++c, ++ch) {
+                    const int buf = ch & 1;
+                    if (ch >= 2) mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);    // the epilogue has drained this pair
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
+                    const uint32_t acc0 = tmem_base + buf * (2 * kBN), acc1 = acc0 + kBN;
+                    const int kb_end = min(k_blocks, (c + 1) * kChunkBlocks);
+                    for (int kb = c * kChunkBlocks; kb < kb_end; ++kb, ++it) {
+                        const int s = it % kGemmStages;
+                        mbar_wait(&full_bar[s], (it / kGemmStages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t koff = k * kUmmaK * 2;       // bytes inside the 128-byte swizzled row
-                        const uint64_t a_hi = umma_desc(base + koff), a_lo = umma_desc(base + kOperandBytes + koff);
-                        const uint64_t b_hi = umma_desc(base + 2 * kOperandBytes + koff), b_lo = umma_desc(base + 3 * kOperandBytes + koff);
-                        const uint32_t acc = (kb > c * kChunkBlocks || k > 0) ? 1u : 0u;
-                        umma_f16(acc0, a_hi, b_hi, idesc, acc);               // acc0 (+)= hi hi
-                        umma_f16(acc1, a_hi, b_lo, idesc, acc);               // acc1 (+)= hi lo
-                        umma_f16(acc1, a_lo, b_hi, idesc, 1u);                // acc1 += lo hi
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            const uint32_t koff = k * kUmmaK * 2;       // bytes inside the 128-byte swizzled row
+                            const uint64_t a_hi = umma_desc(base + koff), a_lo = umma_desc(base + kOperandBytes + koff);
+                            const uint64_t b_hi = umma_desc(base + 2 * kOperandBytes + koff), b_lo = umma_desc(base + 3 * kOperandBytes + koff);
+                            const uint32_t acc = (kb > c * kChunkBlocks || k > 0) ? 1u : 0u;
+                            umma_f16(acc0, a_hi, b_hi, idesc, acc);               // acc0 (+)= hi hi
+                            if (debug == 1) continue;                             // timing experiment: one product only
+                            umma_f16(acc1, a_hi, b_lo, idesc, acc);               // acc1 (+)= hi lo
+                            umma_f16(acc1, a_lo, b_hi, idesc, 1u);                // acc1 += lo hi
+                        }
+                        // the ring slot is free once these MMAs have read it (cluster: tell the peers that write into it too)
+                        if constexpr (kCl == 2) umma_commit_mc(&empty_bar[s], (uint16_t)((1u << rank) | (1u << (rank ^ 1)) | (1u << (rank ^ 2))));
+                        else umma_commit(&empty_bar[s]);
                     }
-                    umma_commit(&empty_bar[s]);        // the ring slot is free once these MMAs have read it
+                    umma_commit(&tmem_full[buf]);          // this accumulator pair is complete
                 }
-                umma_commit(&tmem_full[buf]);          // this accumulator pair is complete
             }
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32 (w % 4), 32 (w % 4) + 32); two warps share a lane quarter and
         // take 64 of the 128 columns each
         const int q = warp & 3, half = (warp - 2) >> 2;
-        const int m = m_blk * kBM + q * 32 + lane;
-        double acc[kBN / 2];
+        uint32_t ch = 0;                                      // chunks drained so far, over all tiles
+        for (int u = unit0; u < n_units; u += unit_stride) {
+            const int n_blk = (u % units_n) * kCl + cx, m_blk = (u / units_n) * kCl + cy;
+            const int m = m_blk * kBM + q * 32 + lane;
+            double acc[kBN / 2];
 #pragma unroll
-        for (int j = 0; j < kBN / 2; ++j) acc[j] = 0.0;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int buf = c & 1;
-            mbar_wait(&tmem_full[buf], (c >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * kBN) + half * (kBN / 2);
+            for (int j = 0; j < kBN / 2; ++j) acc[j] = 0.0;
+            for (int c = 0; c < n_chunks; ++c, ++ch) {
+                const int buf = ch & 1;
+                mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * kBN) + half * (kBN / 2);
 #pragma unroll
-            for (int c0 = 0; c0 < kBN / 2; c0 += 16) {
-                uint32_t r0[16], r1[16];
-                tmem_ld16(trow + c0, r0);
-                tmem_ld16(trow + kBN + c0, r1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int c0 = 0; c0 < kBN / 2; c0 += 16) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(trow + c0, r0);
+                    tmem_ld16(trow + kBN + c0, r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (debug == 3) continue;                 // timing experiment: loads only
 #pragma unroll
-                for (int j = 0; j < 16; ++j)     // hi hi + 2^-11 (hi lo + lo hi) in fp32 (24 bits are enough for one chunk), then float64
-                    acc[c0 + j] += (double)fmaf(__uint_as_float(r1[j]), (float)(1.0 / kLoScale), __uint_as_float(r0[j]));
+                    for (int j = 0; j < 16; ++j)     // hi hi + 2^-11 (hi lo + lo hi) in fp32 (24 bits are enough for one chunk), then float64
+                        acc[c0 + j] += (double)fmaf(__uint_as_float(r1[j]), (float)(1.0 / kLoScale), __uint_as_float(r0[j]));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-        }
-        if (m < M) {
-            const double sa = scale_a[m];
-            double* orow = out + (long long)m * ldo;
-            const int n0 = n_blk * kBN + half * (kBN / 2);
+            if (m < M) {
+                const double sa = scale_a[m];
+                double* orow = out + (long long)m * ldo;
+                const int n0 = n_blk * kBN + half * (kBN / 2);
 #pragma unroll
-            for (int j = 0; j < kBN / 2; j += 2) {
-                const int n = n0 + j;
-                if (n + 1 < N && vec_ok) {
-                    *reinterpret_cast<double2*>(orow + n) =
-                        make_double2(acc[j] * sa * __ldg(scale_b + n), acc[j + 1] * sa * __ldg(scale_b + n + 1));
-                } else {
-                    if (n < N) orow[n] = acc[j] * sa * __ldg(scale_b + n);
-                    if (n + 1 < N) orow[n + 1] = acc[j + 1] * sa * __ldg(scale_b + n + 1);
+                for (int j = 0; j < kBN / 2; j += 2) {
+                    const int n = n0 + j;
+                    if (n + 1 < N && vec_ok) {
+                        *reinterpret_cast<double2*>(orow + n) =
+                            make_double2(acc[j] * sa * __ldg(scale_b + n), acc[j + 1] * sa * __ldg(scale_b + n + 1));
+                    } else {
+                        if (n < N) orow[n] = acc[j] * sa * __ldg(scale_b + n);
+                        if (n + 1 < N) orow[n + 1] = acc[j + 1] * sa * __ldg(scale_b + n + 1);
+                    }
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kCl == 2) cluster_sync_all();             // nobody leaves while a peer's commit may still arrive here
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -262,12 +326,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // fp16 matrix [rows][k_pad], k contiguous; box = 64 x 128 with the 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* ptr, int rows, int k_pad) {
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int k_pad, int box_rows) {
     auto fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return 2; }
     cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -305,15 +369,47 @@ MM_EXPORT int mm_block_gemm(int device, void* stream, const void* a_hi, const vo
     MM_REQUIRE((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) & 15) == 0,
                "operand panels must be 16-byte aligned");
     const int vec_ok = (((uintptr_t)out & 15) == 0 && (ldo & 1) == 0) ? 1 : 0;     // 128-bit stores of the block
+    // MM_BLOCK_CLUSTER=2: 2 x 2 clusters with multicast operand halves (needs at least two tiles each way); default:
+    // the single-CTA persistent kernel, which measured faster
+    const int tiles_n = (n + kBN - 1) / kBN, tiles_m = (m + kBM - 1) / kBM;
+    const bool clustered = tuning().block_cluster == 2 && tiles_n >= 2 && tiles_m >= 2;
+    const int box_rows = clustered ? kBM / 2 : kBM;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    if (int s = make_map(&ma_hi, a_hi, m, k_pad)) return s;
-    if (int s = make_map(&ma_lo, a_lo, m, k_pad)) return s;
-    if (int s = make_map(&mb_hi, b_hi, n, k_pad)) return s;
-    if (int s = make_map(&mb_lo, b_lo, n, k_pad)) return s;
+    if (int s = make_map(&ma_hi, a_hi, m, k_pad, box_rows)) return s;
+    if (int s = make_map(&ma_lo, a_lo, m, k_pad, box_rows)) return s;
+    if (int s = make_map(&mb_hi, b_hi, n, k_pad, box_rows)) return s;
+    if (int s = make_map(&mb_lo, b_lo, n, k_pad, box_rows)) return s;
     const size_t smem = (size_t)kGemmStages * kStageBytes + 1024;     // + slack for the 1024-byte alignment
-    MM_CUDA(cudaFuncSetAttribute(block_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((n + kBN - 1) / kBN, (m + kBM - 1) / kBM);
-    block_gemm_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k_pad / kBK, m, n,
-                                                                         scale_a, scale_b, out, ldo, vec_ok);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    const int debug = tuning().block_debug;
+    if (clustered) {
+        const int tn = (tiles_n + 1) / 2 * 2, tm = (tiles_m + 1) / 2 * 2;      // whole 2 x 2 groups (padding tiles store nothing)
+        const int n_units = (tn / 2) * (tm / 2);
+        MM_CUDA(cudaFuncSetAttribute(block_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3(4);
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, block_gemm_kernel<2>, &cfg) != cudaSuccess || max_clusters <= 0) {
+            cudaGetLastError();
+            max_clusters = n_sm / 4;
+        }
+        cfg.gridDim = dim3((unsigned)(4 * (n_units < max_clusters ? n_units : max_clusters)));
+        MM_CUDA(cudaLaunchKernelEx(&cfg, block_gemm_kernel<2>, ma_hi, ma_lo, mb_hi, mb_lo, (int)(k_pad / kBK), (int)m, (int)n,
+                                   scale_a, scale_b, out, (long long)ldo, vec_ok, tn, tm, debug));
+    } else {
+        MM_CUDA(cudaFuncSetAttribute(block_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int n_units = tiles_n * tiles_m;
+        block_gemm_kernel<1><<<(unsigned)(n_units < n_sm ? n_units : n_sm), kGemmThreads, smem, (cudaStream_t)stream>>>(
+            ma_hi, ma_lo, mb_hi, mb_lo, k_pad / kBK, m, n, scale_a, scale_b, out, ldo, vec_ok, tiles_n, tiles_m, debug);
+    }
     return check_launch("mm_block_gemm");
 }

@@ -455,30 +455,34 @@ class SegMatrix:
         pa = torch.empty((2, na, k_cap), dtype=torch.float16, device=dev)
         pb = pa if same else torch.empty((2, nb, k_cap), dtype=torch.float16, device=dev)
 
-        def scaling(idx, r, n):
-            # centre = group mean of x / sf; scale = power of two nearest to the centred root mean square
-            m = sums[2][idx.long(), r] / n
-            second = sums[4][idx.long(), r] / n - m * m
+        gsel = torch.as_tensor(np.asarray(groups, dtype=np.int64), device=dev)
+        n_g = torch.as_tensor(np.asarray([float(gs[r + 1] - gs[r]) for r in groups]), device=dev)
+
+        def scaling(idx):
+            # centre = group mean of x / sf; scale = power of two nearest to the centred root mean square; all groups at
+            # once (per-group torch glue was 190 us per group next to 220 us of kernels): (len(groups), n) each
+            m = (sums[2][idx.long()][:, gsel] / n_g[None, :]).t().contiguous()
+            second = (sums[4][idx.long()][:, gsel] / n_g[None, :]).t() - m * m
             e = torch.where(second > 0, torch.round(0.5 * torch.log2(second.clamp(min=1e-300))), torch.zeros_like(second))
             e = e.clamp(-200, 200)
-            return m.contiguous(), torch.exp2(-e).contiguous(), torch.exp2(e).contiguous()
+            return m, torch.exp2(-e).contiguous(), torch.exp2(e).contiguous()
 
         ev = timer.start()
+        ca, inv_a, sc_a = scaling(ia)
+        cb, inv_b, sc_b = (ca, inv_a, sc_a) if same else scaling(ib)
         for j, r in enumerate(groups):
             n = int(gs[r + 1] - gs[r])
             k_pad = max(self.BLOCK_K, (n + self.BLOCK_K - 1) // self.BLOCK_K * self.BLOCK_K)
-            ca, inv_a, sc_a = scaling(ia, r, float(n))
             za = pa.view(-1)[:2 * na * k_pad].view(2, na, k_pad)
             _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
-                      ia, na, ca, inv_a, k_pad, za[0], za[1], None)
+                      ia, na, ca[j], inv_a[j], k_pad, za[0], za[1], None)
             if same:
-                zb, sc_b = za, sc_a
+                zb = za
             else:
-                cb, inv_b, sc_b = scaling(ib, r, float(n))
                 zb = pb.view(-1)[:2 * nb * k_pad].view(2, nb, k_pad)
                 _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
-                          ib, nb, cb, inv_b, k_pad, zb[0], zb[1], None)
-            _lib.call("mm_block_gemm", dev, za[0], za[1], na, zb[0], zb[1], nb, k_pad, sc_a, sc_b, out[j], nb)
+                          ib, nb, cb[j], inv_b[j], k_pad, zb[0], zb[1], None)
+            _lib.call("mm_block_gemm", dev, za[0], za[1], na, zb[0], zb[1], nb, k_pad, sc_a[j], sc_b[j], out[j], nb)
         timer.stop("block_cross", ev)
         return out
 
