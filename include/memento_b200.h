@@ -169,6 +169,12 @@ int mm_block_gemm(int device, void* stream, const void* a_hi, const void* a_lo, 
                   const void* b_lo, int32_t n, int32_t k_pad, const double* scale_a, const double* scale_b,
                   double* out, int64_t ldo);
 
+/* Diagnostics of mm_block_gemm (host call, synchronises the device): with MM_BLOCK_DEBUG=9 in the environment the
+ * kernel adds up the cycles its roles spend waiting; out8[0..7] = producer on empty ring slots, MMA thread on full
+ * slots, MMA thread on drained accumulators, one epilogue warp on finished accumulators, its TMEM loads + float64
+ * adds, its stores, whole kernel (per CTA), number of CTAs.  The counters are reset by the call. */
+int mm_block_debug_counters(int device, uint64_t* out8);
+
 /* Covariance sums of gene pairs within every group: for pair k and group r,
  *   out[k*R + r] = sum over cells of the group of x_{c,i} * x_{c,j} / sf_c^2
  * by a merge join of the two sorted row-id lists.

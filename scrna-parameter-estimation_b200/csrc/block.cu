@@ -16,15 +16,24 @@
 // with a relative error of ~2^-22 from the dropped lo lo term plus the fp32 accumulation error, both
 // relative to sum |z_a z_b| <= n sqrt(var_a var_b): correlations are good to ~1e-6 absolute.
 //
-// Kernel structure (one 128 x 128 output tile per CTA, cta_group::1, UMMA 128 x 128 x 16, kind::f16):
-//   warp 0   TMA producer: per 64-cell k-block four 16 KB tiles (hi/lo of A and B, K-major, 128-byte
-//            swizzle) into a kGemmStages ring, mbarrier complete_tx;
-//   warp 1   allocates all 512 TMEM columns (two buffers of two fp32 accumulators) and, from one lane,
-//            issues the 12 tcgen05.mma of a k-block; tcgen05.commit frees the ring slot / hands a finished
-//            256-cell chunk to the epilogue;
-//   warps 2-9 epilogue: tcgen05.ld of a chunk's accumulators (each warp its own 32-lane quarter and 64 of the
-//            128 columns), float64 accumulation over the chunks in registers (the tensor core's fp32
-//            accumulation truncates, see block_gemm_kernel), rescale, 128-bit stores of the float64 block.
+// Kernel structure (PERSISTENT: one CTA per SM walks 128 x 128 output tiles; cta_group::1, UMMA 128 x 128 x 16,
+// kind::f16; the ring-slot and accumulator counters run on across tiles, so the next tile's loads and MMAs start
+// while the previous tile is stored):
+//   warp 0     TMA producer: per 64-cell k-block four 16 KB tiles (hi/lo of A and B, K-major, 128-byte
+//              swizzle) into a kGemmStages ring, mbarrier complete_tx;
+//   warp 1     allocates all 512 TMEM columns (two buffers of two fp32 accumulators) and, from one lane,
+//              issues the 12 tcgen05.mma of a k-block; tcgen05.commit frees the ring slot / hands a finished
+//              256-cell chunk to the epilogue;
+//   warps 2-17 epilogue: tcgen05.ld of a chunk's accumulators (each warp its own 32-lane quarter and 32 of the
+//              128 columns), float64 accumulation over the chunks in registers (the tensor core's fp32
+//              accumulation truncates, see block_gemm_kernel), rescale, transposition of 8-column slices through
+//              2 KB of shared memory per warp, coalesced stores of the float64 block.
+// What bounds it (MM_BLOCK_DEBUG=9 wait counters, scripts/diag_block_waits.py, configs[2] block): not the operand
+// traffic (the 2 x 2 cluster variant with multicast halves is no faster; no reloads at all: 4 % faster), not the
+// MMA count (one product of three: 19 % faster) -- the epilogue warps: per tile 17 k cycles of TMEM loads and
+// float64 adds and 15 k cycles in which all SMs store their 128 KB of float64 results at once, against 21 k cycles
+// of MMAs.  Round 2: 182 -> 119 us per group (8 -> 16 epilogue warps, staged stores instead of 16-byte stores into
+// 32 rows per instruction: 27 k -> 15 k cycles per tile).
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -37,11 +46,13 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmStages = 3;
 constexpr int kOperandBytes = kBM * kBK * 2;      // 16 KB
 constexpr int kStageBytes = 4 * kOperandBytes;    // hi_A, lo_A, hi_B, lo_B
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;                   // four per TMEM lane quarter, 32 of the 128 columns each
+constexpr int kEpiCols = kBN / (kEpiWarps / 4);
 constexpr int kGemmThreads = (2 + kEpiWarps) * 32;
 constexpr int kTmemCols = 512;                  // two buffers x (hi hi | hi lo + lo hi) x 128 fp32 columns
 constexpr int kChunkBlocks = 4;                 // k-blocks (of 64 cells) accumulated in fp32 before float64 takes over
 constexpr double kLoScale = 2048.0;               // 2^11
+constexpr int kStoreStageBytes = 32 * 64;         // per epilogue warp: 32 rows x 8 float64 columns, transposed before the stores
 
 // ------------------------------------------------------------------ panels
 // One CTA per listed gene: row = the cells of group `group` (renumbered rows [row0, row0 + n_cells)), padded
@@ -87,6 +98,14 @@ block_panels_kernel(const float* __restrict__ vals, const int* __restrict__ rows
     }
 }
 
+// MM_BLOCK_DEBUG=9: cycles the roles of block_gemm_kernel spend waiting, summed over the CTAs (read and reset with
+// mm_block_debug_counters): [0] producer on empty slots, [1] MMA thread on full slots, [2] MMA thread on drained
+// accumulators, [3] epilogue warp 2 on finished accumulators, [4] its TMEM loads + float64 adds, [5] its stores,
+// [6] whole kernel (thread 0), [7] CTAs
+__device__ unsigned long long g_blk_dbg[8];
+#define MM_DBG_T0(var) long long var = 0; if (debug == 9) var = clock64();
+#define MM_DBG_ADD(slot, var) if (debug == 9) atomicAdd(&g_blk_dbg[slot], (unsigned long long)(clock64() - var));
+
 // ------------------------------------------------------------------ tcgen05 helpers
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     // K-major operand tile, 128-byte swizzle: 8-row groups 1024 bytes apart; descriptor version 1 (sm_100)
@@ -129,6 +148,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -190,6 +215,7 @@ block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if constexpr (kCl == 2) cluster_sync_all();             // the peers' barriers exist before anything is sent to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    MM_DBG_T0(t_kernel)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -198,7 +224,9 @@ block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int n_blk = (u % units_n) * kCl + cx, m_blk = (u / units_n) * kCl + cy;
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = it % kGemmStages;
+                    MM_DBG_T0(t0)
                     if (it >= kGemmStages) mbar_wait(&empty_bar[s], ((it / kGemmStages) & 1) ^ 1);
+                    MM_DBG_ADD(0, t0)
                     unsigned char* st = smem + (size_t)s * kStageBytes;
                     if (debug == 2 && it >= kGemmStages) { mbar_arrive(&full_bar[s]); continue; }     // timing experiment: no reloads
                     mbar_arrive_expect_tx(&full_bar[s], kStageBytes);     // own halves + the peers' halves
@@ -226,13 +254,17 @@ block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             for (int u = unit0; u < n_units; u += unit_stride) {
                 for (int c = 0; c < n_chunks; ++c, ++ch) {
                     const int buf = ch & 1;
+                    MM_DBG_T0(t2)
                     if (ch >= 2) mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);    // the epilogue has drained this pair
+                    MM_DBG_ADD(2, t2)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t acc0 = tmem_base + buf * (2 * kBN), acc1 = acc0 + kBN;
                     const int kb_end = min(k_blocks, (c + 1) * kChunkBlocks);
                     for (int kb = c * kChunkBlocks; kb < kb_end; ++kb, ++it) {
                         const int s = it % kGemmStages;
+                        MM_DBG_T0(t1)
                         mbar_wait(&full_bar[s], (it / kGemmStages) & 1);
+                        MM_DBG_ADD(1, t1)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
 #pragma unroll
@@ -257,54 +289,82 @@ block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     } else {
         // epilogue: warp w may touch TMEM lanes [32 (w % 4), 32 (w % 4) + 32); two warps share a lane quarter and
         // take 64 of the 128 columns each
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int q = warp & 3, part = (warp - 2) >> 2;        // lane quarter (fixed by the warp id) and column part
         uint32_t ch = 0;                                      // chunks drained so far, over all tiles
         for (int u = unit0; u < n_units; u += unit_stride) {
             const int n_blk = (u % units_n) * kCl + cx, m_blk = (u / units_n) * kCl + cy;
             const int m = m_blk * kBM + q * 32 + lane;
-            double acc[kBN / 2];
+            double acc[kEpiCols];
 #pragma unroll
-            for (int j = 0; j < kBN / 2; ++j) acc[j] = 0.0;
+            for (int j = 0; j < kEpiCols; ++j) acc[j] = 0.0;
             for (int c = 0; c < n_chunks; ++c, ++ch) {
                 const int buf = ch & 1;
+                MM_DBG_T0(t3)
                 mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
+                if (warp == 2 && lane == 0) { MM_DBG_ADD(3, t3) }
+                MM_DBG_T0(t4)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * kBN) + half * (kBN / 2);
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * kBN) + part * kEpiCols;
 #pragma unroll
-                for (int c0 = 0; c0 < kBN / 2; c0 += 16) {
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(trow + c0, r0);
-                    tmem_ld16(trow + kBN + c0, r1);
+                for (int c0 = 0; c0 < kEpiCols; c0 += 8) {
+                    uint32_t r0[8], r1[8];
+                    tmem_ld8(trow + c0, r0);
+                    tmem_ld8(trow + kBN + c0, r1);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (debug == 3) continue;                 // timing experiment: loads only
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)     // hi hi + 2^-11 (hi lo + lo hi) in fp32 (24 bits are enough for one chunk), then float64
+                    for (int j = 0; j < 8; ++j)      // hi hi + 2^-11 (hi lo + lo hi) in fp32 (24 bits are enough for one chunk), then float64
                         acc[c0 + j] += (double)fmaf(__uint_as_float(r1[j]), (float)(1.0 / kLoScale), __uint_as_float(r0[j]));
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (warp == 2 && lane == 0) { MM_DBG_ADD(4, t4) }
             }
-            if (m < M) {
-                const double sa = scale_a[m];
-                double* orow = out + (long long)m * ldo;
-                const int n0 = n_blk * kBN + half * (kBN / 2);
+            MM_DBG_T0(t5)
+            // ---- scale and store.  A thread holds 32 columns of ONE row, so storing from the registers writes 16 bytes
+            // into 32 different rows per instruction (measured: 27 k cycles per tile, 44 % of the kernel).  Instead
+            // the warp transposes 8-column slices through its own 2 KB of shared memory (16-byte chunks XOR-swizzled
+            // with the row pair, so that both directions are conflict-free) and every store instruction writes eight
+            // 64-byte row segments.
+            {
+                unsigned char* stage = smem + (size_t)kGemmStages * kStageBytes + (size_t)(warp - 2) * kStoreStageBytes;
+                const double sa = m < M ? scale_a[m] : 0.0;
+                const int n_base = n_blk * kBN + part * kEpiCols;
+                const int m_base = m_blk * kBM + q * 32;
 #pragma unroll
-                for (int j = 0; j < kBN / 2; j += 2) {
-                    const int n = n0 + j;
-                    if (n + 1 < N && vec_ok) {
-                        *reinterpret_cast<double2*>(orow + n) =
-                            make_double2(acc[j] * sa * __ldg(scale_b + n), acc[j + 1] * sa * __ldg(scale_b + n + 1));
-                    } else {
-                        if (n < N) orow[n] = acc[j] * sa * __ldg(scale_b + n);
-                        if (n + 1 < N) orow[n + 1] = acc[j + 1] * sa * __ldg(scale_b + n + 1);
+                for (int c0 = 0; c0 < kEpiCols; c0 += 8) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = n_base + c0 + 2 * k;
+                        const double v0 = n < N ? acc[c0 + 2 * k] * sa * __ldg(scale_b + n) : 0.0;
+                        const double v1 = n + 1 < N ? acc[c0 + 2 * k + 1] * sa * __ldg(scale_b + n + 1) : 0.0;
+                        *reinterpret_cast<double2*>(stage + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = make_double2(v0, v1);
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = 8 * i + (lane >> 2), k = lane & 3;
+                        const double2 v = *reinterpret_cast<const double2*>(stage + row * 64 + ((k ^ ((row >> 1) & 3)) << 4));
+                        const int mm_ = m_base + row, n = n_base + c0 + 2 * k;
+                        if (mm_ < M) {
+                            double* dst = out + (long long)mm_ * ldo + n;
+                            if (vec_ok && n + 1 < N) *reinterpret_cast<double2*>(dst) = v;
+                            else {
+                                if (n < N) dst[0] = v.x;
+                                if (n + 1 < N) dst[1] = v.y;
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
+            if (warp == 2 && lane == 0) { MM_DBG_ADD(5, t5) }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) { MM_DBG_ADD(6, t_kernel) if (debug == 9) atomicAdd(&g_blk_dbg[7], 1ull); }
     if constexpr (kCl == 2) cluster_sync_all();             // nobody leaves while a peer's commit may still arrive here
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -359,6 +419,16 @@ MM_EXPORT int mm_block_panels(int device, void* stream, const float* vals, const
     return check_launch("mm_block_panels");
 }
 
+MM_EXPORT int mm_block_debug_counters(int device, uint64_t* out8) {
+    if (int s = enter(device)) return s;
+    MM_REQUIRE(out8, "null pointer");
+    MM_CUDA(cudaDeviceSynchronize());
+    MM_CUDA(cudaMemcpyFromSymbol(out8, g_blk_dbg, sizeof(unsigned long long) * 8));
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    MM_CUDA(cudaMemcpyToSymbol(g_blk_dbg, zero, sizeof(zero)));
+    return 0;
+}
+
 MM_EXPORT int mm_block_gemm(int device, void* stream, const void* a_hi, const void* a_lo, int32_t m, const void* b_hi,
                             const void* b_lo, int32_t n, int32_t k_pad, const double* scale_a, const double* scale_b,
                             double* out, int64_t ldo) {
@@ -379,7 +449,8 @@ MM_EXPORT int mm_block_gemm(int device, void* stream, const void* a_hi, const vo
     if (int s = make_map(&ma_lo, a_lo, m, k_pad, box_rows)) return s;
     if (int s = make_map(&mb_hi, b_hi, n, k_pad, box_rows)) return s;
     if (int s = make_map(&mb_lo, b_lo, n, k_pad, box_rows)) return s;
-    const size_t smem = (size_t)kGemmStages * kStageBytes + 1024;     // + slack for the 1024-byte alignment
+    // operand ring + the epilogue warps' store staging + slack for the 1024-byte alignment
+    const size_t smem = (size_t)kGemmStages * kStageBytes + (size_t)kEpiWarps * kStoreStageBytes + 1024;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     const int debug = tuning().block_debug;

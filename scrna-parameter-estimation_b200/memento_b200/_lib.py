@@ -53,7 +53,8 @@ SIGNATURES = {
 }
 
 # host-only helpers (no leading device / stream arguments)
-HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp], "mm_launch_count": [], "mm_reload_tuning": [], "mm_upload_release": []}
+HOST_SIGNATURES = {"mm_poisson_table_size": [_i32, _vp, _vp], "mm_launch_count": [], "mm_reload_tuning": [], "mm_upload_release": [],
+                   "mm_block_debug_counters": [_i32, _vp]}
 
 _lib = None
 
