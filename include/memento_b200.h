@@ -169,6 +169,30 @@ int mm_block_gemm(int device, void* stream, const void* a_hi, const void* a_lo, 
                   const void* b_lo, int32_t n, int32_t k_pad, const double* scale_a, const double* scale_b,
                   double* out, int64_t ldo);
 
+/* Centring and power-of-two scaling of the panels of mm_block_panels for n_groups groups at once:
+ * center[g][i] = sums[2][genes[i]][r] / n_r, scale = 2^round(log2(centred second moment) / 2), inv_scale = 1 / scale,
+ * r = group_ids[g] (NULL: g); sums = the (5, G, R) output of mm_seg_moments, group_start [R + 1] (device). */
+int mm_block_scaling(int device, void* stream, const double* sums, int32_t G, int32_t R, const int64_t* group_start,
+                     const int32_t* group_ids, int32_t n_groups, const int32_t* genes, int32_t n, double* center,
+                     double* inv_scale, double* scale);
+
+/* mm_block_panels (A, and B unless prebuilt or equal to A) + mm_block_gemm for n_groups groups, queued back to back
+ * by ONE call (a Python loop over 16 groups spends as long between the launches as the kernels run).  HOST arrays:
+ * group_ids / group_row0 / group_cells [n_groups] (group index, its first row, its cell count); b_panels (nullable)
+ * [n_groups] device addresses of prebuilt (2, nb, k_pad_g) B panels.  DEVICE arrays: center_* / inv_scale_* / scale_*
+ * [n_groups][na | nb]; gene_b == NULL and b_panels == NULL: B = A.  panel_a / panel_b: scratch for 2 * na (nb) *
+ * k_cap halves per buffer (k_cap >= every group's padded cell count, a multiple of 64); n_bufs = 1, or 2: two such
+ * buffers each, and the panels of group g + 1 are built on a side stream of the library while the GEMM of group g
+ * runs.  cell_w (nullable): resampling counts folded into the A panels (shared-weight bootstrap).
+ * out + g * group_stride = the (na, ldo) float64 block of group g. */
+int mm_block_cross_batch(int device, void* stream, const float* vals, const int32_t* rows, const int64_t* seg_ptr,
+                         int32_t R, int32_t n_groups, const int32_t* group_ids, const int64_t* group_row0,
+                         const int32_t* group_cells, const double* inv_sf, const int32_t* gene_a, int32_t na,
+                         const double* center_a, const double* inv_scale_a, const double* scale_a,
+                         const int32_t* gene_b, int32_t nb, const double* center_b, const double* inv_scale_b,
+                         const double* scale_b, void* panel_a, void* panel_b, int32_t k_cap, int32_t n_bufs,
+                         const uint64_t* b_panels, const int32_t* cell_w, double* out, int64_t ldo, int64_t group_stride);
+
 /* Diagnostics of mm_block_gemm (host call, synchronises the device): with MM_BLOCK_DEBUG=9 in the environment the
  * kernel adds up the cycles its roles spend waiting; out8[0..7] = producer on empty ring slots, MMA thread on full
  * slots, MMA thread on drained accumulators, one epilogue warp on finished accumulators, its TMEM loads + float64

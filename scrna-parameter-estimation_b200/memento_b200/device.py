@@ -452,37 +452,33 @@ class SegMatrix:
         gs = self.group_start_host
         k_max = max(int(gs[r + 1] - gs[r]) for r in groups)
         k_cap = max(self.BLOCK_K, (k_max + self.BLOCK_K - 1) // self.BLOCK_K * self.BLOCK_K)
-        pa = torch.empty((2, na, k_cap), dtype=torch.float16, device=dev)
-        pb = pa if same else torch.empty((2, nb, k_cap), dtype=torch.float16, device=dev)
+        n_bufs = 2 if len(groups) > 1 else 1           # two panel buffers: the next group's panels under this group's GEMM
+        pa = torch.empty((n_bufs, 2, na, k_cap), dtype=torch.float16, device=dev)
+        pb = pa if same else torch.empty((n_bufs, 2, nb, k_cap), dtype=torch.float16, device=dev)
 
-        gsel = torch.as_tensor(np.asarray(groups, dtype=np.int64), device=dev)
-        n_g = torch.as_tensor(np.asarray([float(gs[r + 1] - gs[r]) for r in groups]), device=dev)
+        all_groups = groups == list(range(self.R))
+        gsel = None if all_groups else torch.as_tensor(np.asarray(groups, dtype=np.int32), device=dev)
+        sums_c = sums.contiguous()
 
-        def scaling(idx):
-            # centre = group mean of x / sf; scale = power of two nearest to the centred root mean square; all groups at
-            # once (per-group torch glue was 190 us per group next to 220 us of kernels): (len(groups), n) each
-            m = (sums[2][idx.long()][:, gsel] / n_g[None, :]).t().contiguous()
-            second = (sums[4][idx.long()][:, gsel] / n_g[None, :]).t() - m * m
-            e = torch.where(second > 0, torch.round(0.5 * torch.log2(second.clamp(min=1e-300))), torch.zeros_like(second))
-            e = e.clamp(-200, 200)
-            return m, torch.exp2(-e).contiguous(), torch.exp2(e).contiguous()
+        def scaling(idx, n):
+            # centre = group mean of x / sf; scale = power of two nearest to the centred root mean square; one launch for
+            # all groups (len(groups), n)
+            t = torch.empty((3, len(groups), n), dtype=torch.float64, device=dev)
+            _lib.call("mm_block_scaling", dev, sums_c, self.G, self.R, self.group_start, gsel, len(groups), idx, n,
+                      t[0], t[1], t[2])
+            return t[0], t[1], t[2]
 
         ev = timer.start()
-        ca, inv_a, sc_a = scaling(ia)
-        cb, inv_b, sc_b = (ca, inv_a, sc_a) if same else scaling(ib)
-        for j, r in enumerate(groups):
-            n = int(gs[r + 1] - gs[r])
-            k_pad = max(self.BLOCK_K, (n + self.BLOCK_K - 1) // self.BLOCK_K * self.BLOCK_K)
-            za = pa.view(-1)[:2 * na * k_pad].view(2, na, k_pad)
-            _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
-                      ia, na, ca[j], inv_a[j], k_pad, za[0], za[1], None)
-            if same:
-                zb = za
-            else:
-                zb = pb.view(-1)[:2 * nb * k_pad].view(2, nb, k_pad)
-                _lib.call("mm_block_panels", dev, self.vals, self.rows, self.seg_ptr, self.R, r, int(gs[r]), n, inv_sf,
-                          ib, nb, cb[j], inv_b[j], k_pad, zb[0], zb[1], None)
-            _lib.call("mm_block_gemm", dev, za[0], za[1], na, zb[0], zb[1], nb, k_pad, sc_a[j], sc_b[j], out[j], nb)
+        ca, inv_a, sc_a = scaling(ia, na)
+        cb, inv_b, sc_b = (ca, inv_a, sc_a) if same else scaling(ib, nb)
+        # panels + GEMM of every group queued by one library call (host arrays: group index, first row, cell count)
+        g_ids = np.asarray(groups, dtype=np.int32)
+        g_row0 = np.asarray([gs[r] for r in groups], dtype=np.int64)
+        g_cells = np.asarray([gs[r + 1] - gs[r] for r in groups], dtype=np.int32)
+        _lib.call("mm_block_cross_batch", dev, self.vals, self.rows, self.seg_ptr, self.R, len(groups), g_ids.ctypes.data,
+                  g_row0.ctypes.data, g_cells.ctypes.data, inv_sf, ia, na, ca, inv_a, sc_a, None if same else ib, nb,
+                  None if same else cb, None if same else inv_b, sc_b, pa, None if same else pb, k_cap, n_bufs, None, None,
+                  out, nb, na * nb)
         timer.stop("block_cross", ev)
         return out
 

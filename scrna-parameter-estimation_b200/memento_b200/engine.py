@@ -588,9 +588,13 @@ def ht_2d_shared_block(seg, idx_a, idx_b, inv_sf, sums_d, group_q, true_corr, co
         _lib.call("mm_block_panels", dev, seg.vals, seg.rows, seg.seg_ptr, R, r, int(gs[r]), int(n_r[r]), inv_sf, ib, nb,
                   cb[:, r].contiguous(), inv_b[:, r].contiguous(), k_pad[r], zb[0], zb[1], None)
         panels_b.append(zb)
-    col = lambda t, r: t[:, r].contiguous()             # noqa: E731
-    ca_r, inv_a_r, sc_a_r, sc_b_r = ([col(t, r) for r in range(R)] for t in (ca, inv_a, sc_a, sc_b))
-    pa = torch.empty(2 * na * max(k_pad), dtype=torch.float16, device=dev)
+    # per-group rows for the batched panels + GEMM call: (R, na) / (R, nb), and the host-side group table
+    ca_g, inv_a_g, sc_a_g, sc_b_g = (t.t().contiguous() for t in (ca, inv_a, sc_a, sc_b))
+    g_ids = np.arange(R, dtype=np.int32)
+    g_row0 = np.ascontiguousarray(gs[:-1], dtype=np.int64)
+    g_cells = np.ascontiguousarray(n_r, dtype=np.int32)
+    b_ptrs = np.asarray([p.data_ptr() for p in panels_b], dtype=np.uint64)
+    pa = torch.empty(2 * 2 * na * max(k_pad), dtype=torch.float16, device=dev)      # two buffers of (hi | lo) panels
     cross = torch.empty((R, na, nb), dtype=torch.float64, device=dev)
     w = torch.empty(seg.n_cells, dtype=torch.int32, device=dev)
     shift_a, isd_a = torch.empty((na, R), dtype=torch.float64, device=dev), torch.empty((na, R), dtype=torch.float64, device=dev)
@@ -610,12 +614,10 @@ def ht_2d_shared_block(seg, idx_a, idx_b, inv_sf, sums_d, group_q, true_corr, co
                   shift_a, isd_a)
         _lib.call("mm_seg_weighted_stats", dev, seg.vals, seg.rows, seg.seg_ptr, R, ib, nb, inv_sf, w, cb, gn, gq,
                   shift_b, isd_b)
-        for r in range(R):
-            za = pa[:2 * na * k_pad[r]].view(2, na, k_pad[r])
-            _lib.call("mm_block_panels", dev, seg.vals, seg.rows, seg.seg_ptr, R, r, int(gs[r]), int(n_r[r]), inv_sf, ia,
-                      na, ca_r[r], inv_a_r[r], k_pad[r], za[0], za[1], w)
-            _lib.call("mm_block_gemm", dev, za[0], za[1], na, panels_b[r][0], panels_b[r][1], nb, k_pad[r], sc_a_r[r],
-                      sc_b_r[r], cross[r], nb)
+        # A panels with the counts folded in + one GEMM per group against the kept B panels, queued by one call
+        _lib.call("mm_block_cross_batch", dev, seg.vals, seg.rows, seg.seg_ptr, R, R, g_ids.ctypes.data, g_row0.ctypes.data,
+                  g_cells.ctypes.data, inv_sf, ia, na, ca_g, inv_a_g, sc_a_g, None, nb, None, None, sc_b_g, pa, None,
+                  max(k_pad), 2, b_ptrs.ctypes.data, w, cross, nb, na * nb)
         _lib.call("mm_block_boot_update", dev, cross, shift_a, isd_a, shift_b, isd_b, gn, cfun, stat, R, na, nb,
                   acc_sum, acc_sq, n_ext, n_ok, coef_last if (want_coef and b == num_boot - 1) else None)
     se = torch.empty((na, nb), dtype=torch.float64, device=dev)
