@@ -58,18 +58,21 @@ def emit(line):
 
 def ncu_traffic(nnz):
     """DRAM bytes per mm_seg_moments launch from the committed `ncu --set full` capture of the same matrix
-    (profiles/r01_seg_moments_stream.json: dram__bytes_read.sum + dram__bytes_write.sum of the span kernel and
-    the edge fix-up kernel).  None when the capture is absent or was taken on another matrix."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_seg_moments_stream.json")
-    if not os.path.exists(path) or nnz != 58873218:
+    (profiles/r02_prof_moments.json, else round 1's r01_seg_moments_stream.json: dram__bytes_read.sum +
+    dram__bytes_write.sum of the span kernel and the edge fix-up kernel).  None when the capture is absent or was
+    taken on another matrix."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    name = next((n for n in ("r02_prof_moments.json", "r01_seg_moments_stream.json") if os.path.exists(os.path.join(here, n))), None)
+    if name is None or nnz != 58873218:
         return None, None
+    path = os.path.join(here, name)
     tot = 0.0
     for l in json.load(open(path))["launches"]:
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             m = l.get(k)
             if m:
                 tot += m["value"] * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m["unit"]]
-    return tot, "profiles/r01_seg_moments_stream.json (ncu --set full, same matrix, stream + edge kernels)"
+    return tot, "profiles/%s (ncu --set full, same matrix, stream + edge kernels)" % name
 
 
 # BASELINE.json shapes beyond the headline configuration (SURVEY.md section 8d).  ``labels`` = create_groups columns of

@@ -9,5 +9,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --csv --log-fi
 tail -1 gpurun_out/ncu_l_r02.log | cut -c1-200
 ncu --set full --clock-control none --import-source on -k regex:bootstrap_1d_poisson -s 4 -c 1 -o gpurun_out/r02_prof_boot $CMD > gpurun_out/ncu_b_r02.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'seg_moments_stream|seg_moments_edge' -s 6 -c 2 -o gpurun_out/r02_prof_moments $CMD > gpurun_out/ncu_m_r02.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'relayout_tile|csr_row_sums' -c 4 -o gpurun_out/r02_prof_ingest $CMD > gpurun_out/ncu_i_r02.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'relayout_tile|relayout_rowscan|csr_row_sums' -c 4 -o gpurun_out/r02_prof_ingest $CMD > gpurun_out/ncu_i_r02.log 2>&1
 ls -la gpurun_out/*.ncu-rep
