@@ -30,7 +30,7 @@ static_assert(sizeof(BootEntry) == 32, "BootEntry layout");
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr int kWarpCap = 1024, kWarpMaxNnz = 768;
-constexpr int kCtaCap = 8192, kCtaMaxNnz = 6144;
+constexpr int kCtaCap = 8192, kCtaMaxNnz = 6144, kCtaSmallCap = 2048;
 constexpr int kUniqThreads = 256;
 constexpr int kBtrsMin = 24;  // expected count above which the BTRS sampler is used
 
@@ -67,38 +67,72 @@ __device__ __forceinline__ void group_sync() {
 }
 
 // Processes one segment with NT cooperating threads (t = thread index in the group).
-// keys/cnts: hash table of `cap` slots (shared or global memory), zeroed/emptied here.
+// keys/cnts: hash table of `cap` slots (shared or global memory), zeroed/emptied here.  `limit` = most distinct keys
+// the table may take: when more turn up the function gives up and returns false (nothing has been written to the
+// outputs) and the caller retries with a larger table -- so a segment of 6000 nonzeros with its usual few hundred
+// distinct (count, bin) values runs in a 2048-slot shared-memory table instead of a global one sized for 6000
+// distinct keys.  Lanes of a warp that hold the same key are combined first (MATCH.ANY): in a dense segment a
+// handful of keys (count 1-3 x the common bins) take most of the nonzeros, and 32 atomics on one shared-memory word
+// serialise.
 template <int NT>
-__device__ void unique_segment(const UniqueParams& P, long long seg_rel, uint32_t* keys, int* cnts, int cap,
-                               int t, int* s_misc /* >= 2 ints of shared memory for this group */) {
+__device__ bool unique_segment(const UniqueParams& P, long long seg_rel, uint32_t* keys, int* cnts, int cap, int limit,
+                               int t, int* s_misc /* >= 4 ints of shared memory for this group */) {
     const long long seg = P.seg_lo + seg_rel;
     const long long lo = P.seg_ptr[seg], hi = P.seg_ptr[seg + 1];
     const long long pool = lo - P.seg_ptr[P.seg_lo];
     const int r = (int)(seg % P.R);
     const int mask = cap - 1;
+    const int lane = t & 31;
 
     for (int i = t; i < cap; i += NT) { keys[i] = kEmpty; cnts[i] = 0; }
-    if (t == 0) { s_misc[0] = 0; s_misc[1] = 0; }
+    if (t == 0) { s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; s_misc[3] = 0; }
     group_sync<NT>();
 
     // ---- hash insert of the nonzero entries
     int nz_local = 0;
-    for (long long i = lo + t; i < hi; i += NT) {
-        float v = ld_stream(P.vals + i);
-        if (v > 0.f) {
-            int row = ld_stream(P.rows + i);
-            uint32_t key = ((uint32_t)v << 8) | (uint32_t)__ldg(P.cell_bin + row);
-            uint32_t h = hash32(key) & mask;
-            while (true) {
-                uint32_t prev = atomicCAS(keys + h, kEmpty, key);
-                if (prev == kEmpty || prev == key) { atomicAdd(cnts + h, 1); break; }
-                h = (h + 1) & mask;
+    volatile int* overflow = s_misc + 3;
+    constexpr int kUnroll = 4;                 // independent (value, row, bin) load chains in flight per thread
+    for (long long base = lo; base < hi; base += kUnroll * NT) {
+        float v[kUnroll];
+        int row[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = base + u * NT + t;
+            v[u] = i < hi ? ld_stream(P.vals + i) : 0.f;
+            row[u] = i < hi ? ld_stream(P.rows + i) : 0;
+        }
+        uint32_t key[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            key[u] = v[u] > 0.f ? (((uint32_t)v[u] << 8) | (uint32_t)__ldg(P.cell_bin + row[u])) : kEmpty;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const bool valid = key[u] != kEmpty;
+            const unsigned vmask = __ballot_sync(kFull, valid);
+            if (valid) {
+                const unsigned peers = __match_any_sync(vmask, key[u]);
+                if (lane == __ffs(peers) - 1) {                // one lane per distinct key of the warp
+                    uint32_t h = hash32(key[u]) & mask;
+                    while (!*overflow) {
+                        const uint32_t prev = atomicCAS(keys + h, kEmpty, key[u]);
+                        if (prev == kEmpty || prev == key[u]) {
+                            atomicAdd(cnts + h, __popc(peers));
+                            if (prev == kEmpty && atomicAdd(&s_misc[2], 1) >= limit) *overflow = 1;
+                            break;
+                        }
+                        h = (h + 1) & mask;
+                    }
+                }
+                ++nz_local;
             }
-            ++nz_local;
         }
     }
     if (nz_local) atomicAdd(&s_misc[1], nz_local);
     group_sync<NT>();
+    if (*overflow) {
+        group_sync<NT>();                                        // nobody resets s_misc while it is still being read
+        return false;
+    }
 
     // ---- in-place compaction to the front of the table (chunk reads precede chunk writes)
     int U = 0;
@@ -224,6 +258,7 @@ __device__ void unique_segment(const UniqueParams& P, long long seg_rel, uint32_
         P.seg_U[seg_rel] = all_nan ? -1 : U;
     }
     group_sync<NT>();
+    return true;
 }
 
 __global__ void __launch_bounds__(kUniqThreads)
@@ -233,7 +268,7 @@ unique_warp_kernel(UniqueParams P) {
     constexpr int kWarps = kUniqThreads / 32;
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem) + warp * kWarpCap;
     int* cnts = reinterpret_cast<int*>(smem + kWarps * kWarpCap * 4) + warp * kWarpCap;
-    int* misc = reinterpret_cast<int*>(smem + 2 * kWarps * kWarpCap * 4) + warp * 2;
+    int* misc = reinterpret_cast<int*>(smem + 2 * kWarps * kWarpCap * 4) + warp * 4;
     long long seg_rel = (long long)blockIdx.x * kWarps + warp;
     if (seg_rel >= P.n_seg) return;
     long long seg = P.seg_lo + seg_rel;
@@ -242,7 +277,7 @@ unique_warp_kernel(UniqueParams P) {
         if (lane == 0) P.big_list[1 + atomicAdd(P.big_list, 1)] = (int)seg_rel;
         return;
     }
-    unique_segment<32>(P, seg_rel, keys, cnts, kWarpCap, lane, misc);
+    unique_segment<32>(P, seg_rel, keys, cnts, kWarpCap, kWarpCap, lane, misc);        // nnz <= 768: cannot overflow
 }
 
 __global__ void __launch_bounds__(kUniqThreads)
@@ -250,21 +285,22 @@ unique_cta_kernel(UniqueParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* skeys = reinterpret_cast<uint32_t*>(smem);
     int* scnts = reinterpret_cast<int*>(smem + kCtaCap * 4);
-    __shared__ int misc[2];
+    __shared__ int misc[4];
     const int n_big = P.big_list[0];
     for (int b = blockIdx.x; b < n_big; b += gridDim.x) {
         long long seg_rel = P.big_list[1 + b];
         long long seg = P.seg_lo + seg_rel;
         long long lo = P.seg_ptr[seg];
         long long nnz = P.seg_ptr[seg + 1] - lo;
-        if (nnz <= kCtaMaxNnz) {
-            unique_segment<kUniqThreads>(P, seg_rel, skeys, scnts, kCtaCap, threadIdx.x, misc);
-        } else {
+        // small shared-memory table first (the distinct (count, bin) values of a segment are usually a few hundred),
+        // then the full one, then -- only for segments that may really hold more distinct keys than that -- global memory
+        bool done = unique_segment<kUniqThreads>(P, seg_rel, skeys, scnts, kCtaSmallCap, kCtaSmallCap * 3 / 4, threadIdx.x, misc);
+        if (!done) done = unique_segment<kUniqThreads>(P, seg_rel, skeys, scnts, kCtaCap, kCtaMaxNnz, threadIdx.x, misc);
+        if (!done) {
             int cap = 1;
             while (cap < nnz + (nnz >> 1)) cap <<= 1;           // <= 3 * nnz
             long long off = 3 * (lo - P.seg_ptr[P.seg_lo]);
-            unique_segment<kUniqThreads>(P, seg_rel, P.scratch_key + off, P.scratch_cnt + off, cap,
-                                         threadIdx.x, misc);
+            unique_segment<kUniqThreads>(P, seg_rel, P.scratch_key + off, P.scratch_cnt + off, cap, cap, threadIdx.x, misc);
         }
         __syncthreads();
     }
@@ -297,7 +333,7 @@ MM_EXPORT int mm_seg_unique(int device, void* stream, const float* vals, const i
     P.big_list = big_list; P.scratch_key = scratch_key; P.scratch_cnt = scratch_cnt;
     MM_CUDA(cudaMemsetAsync(big_list, 0, sizeof(int32_t), st));
     constexpr int kWarps = kUniqThreads / 32;
-    size_t smem_warp = 2 * kWarps * kWarpCap * 4 + kWarps * 2 * 4;
+    size_t smem_warp = 2 * kWarps * kWarpCap * 4 + kWarps * 4 * 4;
     size_t smem_cta = 2 * kCtaCap * 4;
     static bool attr_done = false;
     if (!attr_done) {
@@ -309,6 +345,6 @@ MM_EXPORT int mm_seg_unique(int device, void* stream, const float* vals, const i
     MM_REQUIRE(blocks < 2147483647LL, "too many segments for one launch");
     unique_warp_kernel<<<(unsigned)blocks, kUniqThreads, smem_warp, st>>>(P);
     if (int s = check_launch("unique_warp")) return s;
-    unique_cta_kernel<<<148 * 2, kUniqThreads, smem_cta, st>>>(P);
+    unique_cta_kernel<<<148 * 3, kUniqThreads, smem_cta, st>>>(P);
     return check_launch("unique_cta");
 }
