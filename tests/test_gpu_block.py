@@ -59,6 +59,22 @@ def test_block_cross_vs_numpy(sizes, n_genes, na, nb):
         assert (err <= 5e-6 * scale + 1e-12).all(), (r, float((err / (scale + 1e-300)).max()))
 
 
+def test_block_gemm_cluster_variant_equals_the_default(tuning):
+    """The 2 x 2 cluster kernel (TMA-multicast operand halves, MM_BLOCK_CLUSTER=2) performs the same MMAs in the same
+    order as the single-CTA kernel: equal bits, on tile counts that are odd / even / one each way (padding tiles of an
+    incomplete 2 x 2 group must load and multicast but store nothing)."""
+    for sizes, n_genes, na, nb in [([300, 517, 90], 700, 129, 700), ([200, 64], 400, 400, 390), ([150, 70], 300, 128, 300)]:
+        seg, dense, sf, gs = _random_matrix(sizes, n_genes, seed=7, density=0.2)
+        inv_sf = torch.as_tensor(1.0 / sf, device=seg.device)
+        sums = seg.moments(inv_sf)
+        idx_a, idx_b = np.arange(na), np.arange(n_genes - nb, n_genes)
+        tuning(MM_BLOCK_CLUSTER="1")
+        base = seg.block_cross(idx_a, idx_b, inv_sf, sums).clone()
+        tuning(MM_BLOCK_CLUSTER="2")
+        clus = seg.block_cross(idx_a, idx_b, inv_sf, sums)
+        assert torch.equal(base, clus), (sizes, na, nb)
+
+
 def test_compute_2d_moments_dense_block_vs_pair_path(monkeypatch):
     calls = []
     orig = dev_mod.SegMatrix.block_cross
