@@ -88,12 +88,15 @@ def main():
         st = ad.uns["memento"]["_b200"]
         csr = st.csr
         res = {"cells": w["cells"], "genes": w["genes"], "nnz": int(csr.nnz)}
-        for cfg in os.environ.get("AB_RELAYOUT_CFGS", "0").split(","):
-            os.environ["MM_RELAYOUT_CFG"] = cfg
-            _lib.reload_tuning()
-            res["all_cells_cfg" + cfg] = plan_and_time(csr, None, np.asarray([0, w["cells"]], dtype=np.int64))
-            print(name, "cfg", cfg, json.dumps(res["all_cells_cfg" + cfg]), file=sys.stderr, flush=True)
-        os.environ.pop("MM_RELAYOUT_CFG")
+        for cfg in os.environ.get("AB_RELAYOUT_CFGS", "2").split(","):
+            for thr in os.environ.get("AB_RELAYOUT_SCAN_THREADS", "256").split(","):
+                os.environ["MM_RELAYOUT_CFG"] = cfg
+                os.environ["MM_RELAYOUT_SCAN_THREADS"] = thr
+                _lib.reload_tuning()
+                tag = "all_cells_cfg%s_scan%s" % (cfg, thr)
+                res[tag] = plan_and_time(csr, None, np.asarray([0, w["cells"]], dtype=np.int64))
+                print(name, "cfg", cfg, "scan threads", thr, json.dumps(res[tag]), file=sys.stderr, flush=True)
+        os.environ.pop("MM_RELAYOUT_CFG"); os.environ.pop("MM_RELAYOUT_SCAN_THREADS")
         _lib.reload_tuning()
         R = w["conditions"] * w["types"] * w["donors"]
         codes = np.random.default_rng(0).integers(0, R, size=w["cells"]).astype(np.int32)

@@ -26,6 +26,7 @@ struct Tuning {
     int moments_chunk;      // MM_MOMENTS_CHUNK: spans per chunk, 1 / 4 / 8
     int block_cluster;      // MM_BLOCK_CLUSTER (dense-block GEMM): 2 = 2 x 2 clusters with multicast operand halves (default: single-CTA kernel)
     int block_debug;        // MM_BLOCK_DEBUG (timing experiments, wrong results): 1 = one MMA of three, 2 = no TMA reloads, 3 = no float64 accumulation
+    int relayout_scan_threads;   // MM_RELAYOUT_SCAN_THREADS (row scan of the tiled re-layout): 256 / 512 / 1024
     int relayout_cfg;       // MM_RELAYOUT_CFG (tiled fill pass): -1 unset, 0..4 tile shapes
     int moments_cfg;        // MM_MOMENTS_CFG (tile kernel): -1 unset
     int moments_regime;     // MM_MOMENTS_REGIME

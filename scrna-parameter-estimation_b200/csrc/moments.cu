@@ -962,6 +962,7 @@ static Tuning read_tuning() {
     u.moments_prefetch = env_int("MM_MOMENTS_PREFETCH", -1);
     u.moments_chunk = env_int("MM_MOMENTS_CHUNK", 0);
     u.relayout_cfg = env_int("MM_RELAYOUT_CFG", -1);
+    u.relayout_scan_threads = env_int("MM_RELAYOUT_SCAN_THREADS", 0);
     u.block_cluster = env_int("MM_BLOCK_CLUSTER", -1);
     u.block_debug = env_int("MM_BLOCK_DEBUG", 0);
     u.moments_cfg = env_int("MM_MOMENTS_CFG", -1);

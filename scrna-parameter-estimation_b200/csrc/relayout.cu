@@ -115,7 +115,6 @@ relayout_fill_kernel(RelayoutParams P, const long long* __restrict__ seg_ptr, fl
 // control-dependent 16-byte loads, 7.2 warp instructions per nonzero at 23 active lanes -- and derived the
 // incidence bits twice).
 constexpr int kTileRows = 256;       // rows per chunk (bit-matrix height); chunks may be shorter
-constexpr int kScanThreads = 256;    // pass A: 8 warps, a warp per row
 constexpr int kScanLoads = 8;        // pass A: 32-index loads in flight per warp
 constexpr int kMaxTiledGenes = 100000;   // pass A keeps 16-bit counters of all genes in shared memory (<= 200 KB)
 
@@ -124,7 +123,7 @@ constexpr int kMaxTiledGenes = 100000;   // pass A keeps 16-bit counters of all 
 // ascent check, block starts, counts.  Counters are 16-bit halves of 32-bit words (a chunk has at most 256 rows, so a
 // count fits) in each CTA's own shared memory, updated with 32-bit shared-memory atomics; at the end every CTA adds
 // up its slice of the genes over the cluster's S counter arrays through distributed shared memory.
-template <bool kPacked>
+template <bool kPacked, int kScanThreads>
 __global__ void __launch_bounds__(kScanThreads)
 relayout_rowscan_kernel(RelayoutParams P, int* __restrict__ bnd, long long n_rows_total, int tile_shift) {
     namespace cg = cooperative_groups;
@@ -616,13 +615,18 @@ MM_EXPORT int mm_relayout_count(int device, void* stream, const int64_t* indptr,
         // 32-bit counters up to 24k genes (96 KB: two CTAs per SM), 16-bit halves above
         const bool packed = n_genes > 24576;
         const size_t smem = sizeof(unsigned) * (size_t)(packed ? (n_genes + 1) / 2 : n_genes);
-        auto kern = packed ? relayout_rowscan_kernel<true> : relayout_rowscan_kernel<false>;
+        // warps per CTA: a warp walks its rows one after the other (order -> indptr -> row loads is a chain of dependent
+        // loads per row), so more warps = fewer rows per warp (MM_RELAYOUT_SCAN_THREADS: 256 / 512 / 1024; measured on C2:
+        // 0.20 / 0.21 / 0.26 ms, so 256 stays)
+        const int scan_threads = tuning().relayout_scan_threads == 512 ? 512 : tuning().relayout_scan_threads == 1024 ? 1024 : 256;
+        auto kern = packed ? (scan_threads == 256 ? relayout_rowscan_kernel<true, 256> : scan_threads == 512 ? relayout_rowscan_kernel<true, 512> : relayout_rowscan_kernel<true, 1024>)
+                           : (scan_threads == 256 ? relayout_rowscan_kernel<false, 256> : scan_threads == 512 ? relayout_rowscan_kernel<false, 512> : relayout_rowscan_kernel<false, 1024>);
         MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int S = 1;                              // CTAs per chunk (cluster size): at least ~4 CTAs per SM when possible
         while (S < 8 && (long long)n_chunks * S < 148 * 4) S *= 2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)n_chunks * S);
-        cfg.blockDim = dim3(kScanThreads);
+        cfg.blockDim = dim3(scan_threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
