@@ -719,6 +719,9 @@ __global__ void seg_moments_edge_kernel(const long long* __restrict__ seg_ptr, l
                                         double* __restrict__ out) {
     const long long n_chunks = (nnz + kChunk - 1) / kChunk;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // launched with programmatic stream serialisation: the grid may start while the reduction kernel before it is
+    // still draining; nothing of its output is touched before this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (c + 1 >= n_chunks) return;
     const long long t_lo = c * kChunk, t_hi = t_lo + kChunk;
     const long long s = chunk_seg[(c + 1) * (kChunk / kSpanElems)];
@@ -1012,6 +1015,24 @@ static int sm_count(int device) {
     return cached[device];
 }
 
+// the edge fix-up kernel behind a reduction kernel, with programmatic dependent launch: its launch latency overlaps the
+// tail of the reduction (the kernel itself waits for the reduction's completion with griddepcontrol.wait)
+template <int kChunk>
+static int launch_edge(cudaStream_t st, long long n_chunks, const long long* sp, long long n_seg, long long nnz,
+                       const int32_t* chunk_seg, const double* edge, double* out) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((n_chunks + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MM_CUDA(cudaLaunchKernelEx(&cfg, seg_moments_edge_kernel<kChunk>, sp, n_seg, nnz, (const int*)chunk_seg, edge, out));
+    return check_launch("seg_moments_edge");
+}
+
 template <int S, int kBlocksPerSm>
 static int launch_tile(cudaStream_t st, int n_sm, int regime, const float* vals, const int32_t* rows,
                        const long long* sp, long long n_seg, long long nnz, const int32_t* chunk_seg,
@@ -1024,8 +1045,7 @@ static int launch_tile(cudaStream_t st, int n_sm, int regime, const float* vals,
     seg_moments_tile_kernel<S, kBlocksPerSm><<<(unsigned)grid, kTileThreads, smem, st>>>(vals, rows, sp, n_seg, nnz, chunk_seg,
                                                                                        inv_sf, out, edge, regime);
     if (int s = check_launch("seg_moments_tile")) return s;
-    seg_moments_edge_kernel<kTile><<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(sp, n_seg, nnz, chunk_seg, edge, out);
-    return check_launch("seg_moments_edge");
+    return launch_edge<kTile>(st, n_tiles, sp, n_seg, nnz, chunk_seg, edge, out);
 }
 
 template <int kThreads, bool kPrefetch, int kC, int kQ>
@@ -1048,8 +1068,7 @@ static int launch_stream(cudaStream_t st, int n_sm, const float* vals, const int
                                                                                       inv_sf, (int)n_cells, out, edge);
     }
     if (int s = check_launch("seg_moments_stream")) return s;
-    seg_moments_edge_kernel<kChunk><<<(unsigned)((n_spans + 255) / 256), 256, 0, st>>>(sp, n_seg, nnz, chunk_seg, edge, out);
-    return check_launch("seg_moments_edge");
+    return launch_edge<kChunk>(st, n_spans, sp, n_seg, nnz, chunk_seg, edge, out);
 }
 
 MM_EXPORT int mm_seg_moments_windows(int device, void* stream, const float* vals, const int32_t* rows,
