@@ -38,6 +38,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <string.h>
 
 namespace mm {
 
@@ -162,6 +163,12 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
+// TMA store of a shared-memory box into the output tensor (rows / columns outside the tensor are clipped by the unit)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -203,7 +210,7 @@ template <int kCl>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  int k_blocks, int M, int N, const double* __restrict__ scale_a, const double* __restrict__ scale_b,
+                  const __grid_constant__ CUtensorMap map_out, int k_blocks, int M, int N, const double* __restrict__ scale_a, const double* __restrict__ scale_b,
                   double* __restrict__ out, long long ldo, int vec_ok, int tiles_n, int tiles_m, int debug) {
     extern __shared__ unsigned char smem_raw[];
     // 128-byte-swizzled operand tiles need a 1024-byte aligned base (the launch adds 1 KB of slack)
@@ -356,12 +363,24 @@ block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const int m_base = m_blk * kBM + q * 32;
 #pragma unroll
                 for (int c0 = 0; c0 < kEpiCols; c0 += 8) {
+                    // vec_ok == 2: the slice leaves through the TMA unit (one bulk tensor store per slice; the staging
+                    // layout is the unit's 64-byte swizzle): wait until the previous store has READ the buffer
+                    if (vec_ok == 2) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int n = n_base + c0 + 2 * k;
                         const double v0 = n < N ? acc[c0 + 2 * k] * sa * __ldg(scale_b + n) : 0.0;
                         const double v1 = n + 1 < N ? acc[c0 + 2 * k + 1] * sa * __ldg(scale_b + n + 1) : 0.0;
                         *reinterpret_cast<double2*>(stage + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = make_double2(v0, v1);
+                    }
+                    if (vec_ok == 2) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&map_out, stage, n_base + c0, m_base);
+                        continue;
                     }
                     __syncwarp();
 #pragma unroll
@@ -383,6 +402,7 @@ block_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
             if (warp == 2 && lane == 0) { MM_DBG_ADD(5, t5) }
         }
+        if (vec_ok == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -419,6 +439,21 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int k_pad, int 
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return 2; }
+    return 0;
+}
+
+// float64 output matrix [rows][ld], box = 8 columns x 32 rows with the 64-byte swizzle (the epilogue's staging layout)
+static int make_out_map(CUtensorMap* map, const void* ptr, int rows, int cols, long long ld) {
+    auto fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return 2; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {8, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)r); return 2; }
     return 0;
 }
 
@@ -459,7 +494,15 @@ static int block_gemm_launch(int device, cudaStream_t stream, const void* a_hi, 
     MM_REQUIRE(a_hi && a_lo && b_hi && b_lo && scale_a && scale_b && out, "null pointer");
     MM_REQUIRE((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) & 15) == 0,
                "operand panels must be 16-byte aligned");
-    const int vec_ok = (((uintptr_t)out & 15) == 0 && (ldo & 1) == 0) ? 1 : 0;     // 128-bit stores of the block
+    // 0: scalar stores; 1: 128-bit stores (16-byte aligned rows); 2: TMA tensor stores (the same alignment is what the
+    // tensor map needs; MM_BLOCK_DEBUG=4 keeps the 128-bit stores for A/B)
+    int vec_ok = (((uintptr_t)out & 15) == 0 && (ldo & 1) == 0) ? 1 : 0;
+    CUtensorMap m_out;
+    memset(&m_out, 0, sizeof(m_out));
+    if (vec_ok && tuning().block_debug != 4) {
+        if (int s = make_out_map(&m_out, out, m, n, ldo)) return s;
+        vec_ok = 2;
+    }
     // MM_BLOCK_CLUSTER=2: 2 x 2 clusters with multicast operand halves (needs at least two tiles each way); default:
     // the single-CTA persistent kernel, which measured faster
     const int tiles_n = (n + kBN - 1) / kBN, tiles_m = (m + kBM - 1) / kBM;
@@ -499,13 +542,13 @@ static int block_gemm_launch(int device, cudaStream_t stream, const void* a_hi, 
             max_clusters = n_sm / 4;
         }
         cfg.gridDim = dim3((unsigned)(4 * (n_units < max_clusters ? n_units : max_clusters)));
-        MM_CUDA(cudaLaunchKernelEx(&cfg, block_gemm_kernel<2>, ma_hi, ma_lo, mb_hi, mb_lo, (int)(k_pad / kBK), (int)m, (int)n,
+        MM_CUDA(cudaLaunchKernelEx(&cfg, block_gemm_kernel<2>, ma_hi, ma_lo, mb_hi, mb_lo, m_out, (int)(k_pad / kBK), (int)m, (int)n,
                                    scale_a, scale_b, out, (long long)ldo, vec_ok, tn, tm, debug));
     } else {
         MM_CUDA(cudaFuncSetAttribute(block_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int n_units = tiles_n * tiles_m;
         block_gemm_kernel<1><<<(unsigned)(n_units < n_sm ? n_units : n_sm), kGemmThreads, smem, stream>>>(
-            ma_hi, ma_lo, mb_hi, mb_lo, k_pad / kBK, m, n, scale_a, scale_b, out, ldo, vec_ok, tiles_n, tiles_m, debug);
+            ma_hi, ma_lo, mb_hi, mb_lo, m_out, k_pad / kBK, m, n, scale_a, scale_b, out, ldo, vec_ok, tiles_n, tiles_m, debug);
     }
     return check_launch("mm_block_gemm");
 }

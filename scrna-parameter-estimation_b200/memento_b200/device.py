@@ -441,14 +441,18 @@ class SegMatrix:
         out[r, a, b] = sum over the cells c of group r of (x_ca / sf_c - m_a)(x_cb / sf_c - m_b), i.e. n_r times the
         plug-in covariance (reference estimator.py:226-231 / :254-259).  ``idx_a`` / ``idx_b``: gene indices
         (numpy int arrays); ``sums``: the (5, G, R) device tensor of ``moments``; ``groups``: group indices
-        (default all).  Returns a float64 device tensor (len(groups), |A|, |B|)."""
+        (default all).  Returns a float64 device tensor (len(groups), |A|, |B|) -- a view whose rows are padded to a
+        multiple of 8 columns (not contiguous when |B| is not one)."""
         dev = self.device
         groups = list(range(self.R)) if groups is None else list(groups)
         ia = torch.as_tensor(np.ascontiguousarray(idx_a, dtype=np.int32), device=dev)
         same = idx_b is idx_a or (len(idx_a) == len(idx_b) and np.array_equal(idx_a, idx_b))
         ib = ia if same else torch.as_tensor(np.ascontiguousarray(idx_b, dtype=np.int32), device=dev)
         na, nb = int(ia.numel()), int(ib.numel())
-        out = torch.empty((len(groups), na, nb), dtype=torch.float64, device=dev)
+        # rows padded to a multiple of 8 columns: 64-byte aligned row segments, and the 16-byte aligned row stride that
+        # the TMA tensor stores of the GEMM epilogue need; the caller gets the (groups, |A|, |B|) view
+        ldo = (nb + 7) // 8 * 8
+        out = torch.empty((len(groups), na, ldo), dtype=torch.float64, device=dev)
         gs = self.group_start_host
         k_max = max(int(gs[r + 1] - gs[r]) for r in groups)
         k_cap = max(self.BLOCK_K, (k_max + self.BLOCK_K - 1) // self.BLOCK_K * self.BLOCK_K)
@@ -478,9 +482,9 @@ class SegMatrix:
         _lib.call("mm_block_cross_batch", dev, self.vals, self.rows, self.seg_ptr, self.R, len(groups), g_ids.ctypes.data,
                   g_row0.ctypes.data, g_cells.ctypes.data, inv_sf, ia, na, ca, inv_a, sc_a, None if same else ib, nb,
                   None if same else cb, None if same else inv_b, sc_b, pa, None if same else pb, k_cap, n_bufs, None, None,
-                  out, nb, na * nb)
+                  out, ldo, na * ldo)
         timer.stop("block_cross", ev)
-        return out
+        return out[:, :, :nb]
 
     @staticmethod
     def block_flops(n_a, n_b, n_cells_per_group):

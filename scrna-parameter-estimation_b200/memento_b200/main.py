@@ -741,8 +741,7 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
     if block is not None:
         # gene_pairs is a full A x B block: one tensor-core GEMM per group instead of a merge join per pair
         genes_a, genes_b, pos = block
-        cross = st.seg.block_cross(genes_a, genes_b, st.inv_sf_sorted, sums_d, timer=st.timer)    # (R, |A|, |B|)
-        cross = cross.reshape(len(groups), -1)
+        cross = st.seg.block_cross(genes_a, genes_b, st.inv_sf_sorted, sums_d, timer=st.timer)    # (R, |A|, |B|) view
         pos_d = None if pos is None else to_device(pos, st.device, np.int64)
     else:
         i1_d = to_device(idx1, st.device, np.int32)
@@ -757,8 +756,9 @@ def compute_2d_moments(adata, gene_pairs, inplace=True):
         s3_d = sums_d[3]
         for r, g in enumerate(groups):
             q = mem["group_q"][g]
-            c = cross[r] if pos_d is None else cross[r][pos_d]
-            cov_d = c / n_cells[r]                                                         # centred: :226-231 in one step
+            cov_d = (cross[r] / n_cells[r]).reshape(-1)                                    # centred: :226-231 in one step
+            if pos_d is not None:
+                cov_d = cov_d[pos_d]
             corr_same = (1 - q) * s3_d[i1_d, r] / n_cells[r]                               # estimator.py:229-230
             cov_d = torch.where(same_d, cov_d - corr_same, cov_d)
             var_g = to_device(mem["1d_moments"][g][1], dev, np.float64)
