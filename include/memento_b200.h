@@ -137,7 +137,7 @@ int mm_block_panels(int device, void* stream, const float* vals, const int32_t* 
  *                           x / sf used to centre the panels): out_shift = sum_c w x/sf / N_r - center, out_isd =
  *                           1 / sqrt(var_w) with var_w = [sum w x^2/sf^2 - (1 - q_r) sum w x/sf^2] / N_r -
  *                           (sum w x/sf / N_r)^2, NaN when var_w <= 0 (estimator.py:171-174, :283-284).
- *   mm_block_boot_update  : cross [R][na][nb] = the replicate's weighted centred cross products; corr_r = (cross / N_r -
+ *   mm_block_boot_update  : cross [R][na][ld_cross] (ld_cross >= nb: rows may be padded) = the replicate's weighted centred cross products; corr_r = (cross / N_r -
  *                           shift_a shift_b) isd_a isd_b clipped to [-1, 1]; coef = sum_r cfun[r] corr_r (one
  *                           treatment column, every group valid); pairs with stat = NaN are skipped; a replicate with
  *                           a NaN correlation in some group is dropped for that pair.  Running sums of d = coef - stat:
@@ -154,7 +154,7 @@ int mm_seg_weighted_stats(int device, void* stream, const float* vals, const int
 int mm_block_boot_update(int device, void* stream, const double* cross, const double* shift_a, const double* isd_a,
                          const double* shift_b, const double* isd_b, const double* group_n, const double* cfun,
                          const double* stat, int32_t R, int32_t na, int32_t nb, double* sum, double* sumsq,
-                         int32_t* n_ext, int32_t* n_ok, double* coef_out);
+                         int32_t* n_ext, int32_t* n_ok, double* coef_out, int64_t ld_cross);
 int mm_block_boot_finish(int device, void* stream, const double* stat, const double* sum, const double* sumsq,
                          const int32_t* n_ext, const int32_t* n_ok, int64_t n_pairs, int32_t approx, double* se,
                          double* asl);

@@ -71,7 +71,8 @@ seg_weighted_stats_kernel(const float* __restrict__ vals, const int* __restrict_
 }
 
 struct BootUpdate {
-    const double* cross;        // [R][na][nb] weighted centred cross products of the replicate
+    const double* cross;        // [R][na][ld] weighted centred cross products of the replicate (ld >= nb: padded rows)
+    long long ld;
     const double* shift_a; const double* isd_a;     // [na][R]
     const double* shift_b; const double* isd_b;     // [nb][R]
     const double* group_n;      // [R]
@@ -95,7 +96,7 @@ block_boot_update_kernel(BootUpdate P) {
     bool ok = true;
     for (int r = 0; r < P.R; ++r) {
         const double n = P.group_n[r];
-        const double cov = P.cross[(long long)r * n_pairs + k] / n - P.shift_a[(long long)a * P.R + r] * P.shift_b[(long long)b * P.R + r];
+        const double cov = P.cross[((long long)r * P.na + a) * P.ld + b] / n - P.shift_a[(long long)a * P.R + r] * P.shift_b[(long long)b * P.R + r];
         double corr = cov * P.isd_a[(long long)a * P.R + r] * P.isd_b[(long long)b * P.R + r];
         ok = ok && (corr == corr);
         corr = fmin(1.0, fmax(-1.0, corr));                  // estimator.py:289-290
@@ -168,16 +169,16 @@ MM_EXPORT int mm_block_boot_update(int device, void* stream, const double* cross
                                    const double* isd_a, const double* shift_b, const double* isd_b,
                                    const double* group_n, const double* cfun, const double* stat, int32_t R,
                                    int32_t na, int32_t nb, double* sum, double* sumsq, int32_t* n_ext, int32_t* n_ok,
-                                   double* coef_out) {
+                                   double* coef_out, int64_t ld_cross) {
     if (int s = enter(device)) return s;
-    MM_REQUIRE(R > 0 && na >= 0 && nb >= 0, "R/na/nb");
+    MM_REQUIRE(R > 0 && na >= 0 && nb >= 0 && ld_cross >= nb, "R/na/nb/ld_cross");
     if (na == 0 || nb == 0) return 0;
     MM_REQUIRE(cross && shift_a && isd_a && shift_b && isd_b && group_n && cfun && stat && sum && sumsq && n_ext && n_ok,
                "null pointer");
     BootUpdate P;
     P.cross = cross; P.shift_a = shift_a; P.isd_a = isd_a; P.shift_b = shift_b; P.isd_b = isd_b; P.group_n = group_n;
     P.cfun = cfun; P.stat = stat; P.R = R; P.na = na; P.nb = nb; P.sum = sum; P.sumsq = sumsq; P.n_ext = n_ext;
-    P.n_ok = n_ok; P.coef_out = coef_out;
+    P.n_ok = n_ok; P.coef_out = coef_out; P.ld = ld_cross;
     const long long n_pairs = (long long)na * nb;
     block_boot_update_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
     return check_launch("mm_block_boot_update");

@@ -27,7 +27,7 @@ SIGNATURES = {
     "mm_block_panels": [_vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "mm_cell_weights": [_vp, _i32, _i64, _u64, C.c_uint32, _vp],
     "mm_seg_weighted_stats": [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "mm_block_boot_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "mm_block_boot_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64],
     "mm_block_boot_finish": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
     "mm_block_gemm": [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64],
     "mm_block_scaling": [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp],

@@ -595,7 +595,8 @@ def ht_2d_shared_block(seg, idx_a, idx_b, inv_sf, sums_d, group_q, true_corr, co
     g_cells = np.ascontiguousarray(n_r, dtype=np.int32)
     b_ptrs = np.asarray([p.data_ptr() for p in panels_b], dtype=np.uint64)
     pa = torch.empty(2 * 2 * na * max(k_pad), dtype=torch.float16, device=dev)      # two buffers of (hi | lo) panels
-    cross = torch.empty((R, na, nb), dtype=torch.float64, device=dev)
+    ldc = (nb + 7) // 8 * 8                              # padded rows: aligned TMA tensor stores in the GEMM epilogue
+    cross = torch.empty((R, na, ldc), dtype=torch.float64, device=dev)
     w = torch.empty(seg.n_cells, dtype=torch.int32, device=dev)
     shift_a, isd_a = torch.empty((na, R), dtype=torch.float64, device=dev), torch.empty((na, R), dtype=torch.float64, device=dev)
     shift_b, isd_b = torch.empty((nb, R), dtype=torch.float64, device=dev), torch.empty((nb, R), dtype=torch.float64, device=dev)
@@ -617,9 +618,9 @@ def ht_2d_shared_block(seg, idx_a, idx_b, inv_sf, sums_d, group_q, true_corr, co
         # A panels with the counts folded in + one GEMM per group against the kept B panels, queued by one call
         _lib.call("mm_block_cross_batch", dev, seg.vals, seg.rows, seg.seg_ptr, R, R, g_ids.ctypes.data, g_row0.ctypes.data,
                   g_cells.ctypes.data, inv_sf, ia, na, ca_g, inv_a_g, sc_a_g, None, nb, None, None, sc_b_g, pa, None,
-                  max(k_pad), 2, b_ptrs.ctypes.data, w, cross, nb, na * nb)
+                  max(k_pad), 2, b_ptrs.ctypes.data, w, cross, ldc, na * ldc)
         _lib.call("mm_block_boot_update", dev, cross, shift_a, isd_a, shift_b, isd_b, gn, cfun, stat, R, na, nb,
-                  acc_sum, acc_sq, n_ext, n_ok, coef_last if (want_coef and b == num_boot - 1) else None)
+                  acc_sum, acc_sq, n_ext, n_ok, coef_last if (want_coef and b == num_boot - 1) else None, ldc)
     se = torch.empty((na, nb), dtype=torch.float64, device=dev)
     asl = torch.empty((na, nb), dtype=torch.float64, device=dev)
     _lib.call("mm_block_boot_finish", dev, stat, acc_sum, acc_sq, n_ext, n_ok, na * nb, 1 if approx else 0, se, asl)
