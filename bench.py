@@ -586,6 +586,25 @@ def run_ours(a):
                 "seg_moments": {"ms": mom_ms, "achieved": mom_gbs, "unit": "GB/s", "frac": mom_gbs / peak}}
             del csr
         if not a.no_shapes:
+            # configs[2]: the dense 1500 x (all tested genes) covariance block of the same data on the tensor cores
+            # (scaling + panels + persistent tcgen05 GEMM of all 16 groups, float64 block out), against the measured
+            # dense bf16 peak
+            try:
+                tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+                tsrc = "measured (MEASURED_PEAKS.json bf16_tflops)"
+            except Exception:
+                tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md)"
+            idx_a, idx_b = np.arange(min(1500, seg.G)), np.arange(seg.G)
+            sums_blk = seg.moments(st.inv_sf_sorted)
+            blk_ms = kernel_ms(lambda: seg.block_cross(idx_a, idx_b, st.inv_sf_sorted, sums_blk), dev, reps=5, warm=2)
+            flops = seg.block_flops(idx_a.size, idx_b.size, np.diff(seg.group_start_host))
+            roofline_shapes["c2 (25k x 10k)"]["block_cross (configs[2]: 1500 x %d genes, %d groups)" % (seg.G, seg.R)] = {
+                "bound": "tensor", "ms": blk_ms, "achieved": flops / (blk_ms * 1e-3) / 1e12, "peak": tpeak,
+                "unit": "TFLOP/s", "frac": flops / (blk_ms * 1e-3) / 1e12 / tpeak, "peak_source": tsrc,
+                "note": "3 fp16 tcgen05 products per (pair, cell), padding to 64 cells per group included; panels and "
+                        "the float64 block write are inside the timed region"}
+            del sums_blk
+            torch.cuda.empty_cache()
             roofline_shapes.update(shape_rooflines(dev, peak))
     roofline = {"kernel": "mm_seg_moments (per-(gene,group) sum x, max x, sum x/sf, sum x/sf^2, sum x^2/sf^2)",
                 "bound": "hbm", "achieved": mom_gbs, "peak": peak, "unit": "GB/s", "frac": mom_gbs / peak,
