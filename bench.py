@@ -598,7 +598,7 @@ def run_ours(a):
             sums_blk = seg.moments(st.inv_sf_sorted)
             blk_ms = kernel_ms(lambda: seg.block_cross(idx_a, idx_b, st.inv_sf_sorted, sums_blk), dev, reps=5, warm=2)
             flops = seg.block_flops(idx_a.size, idx_b.size, np.diff(seg.group_start_host))
-            roofline_shapes["c2 (25k x 10k)"]["block_cross (configs[2]: 1500 x %d genes, %d groups)" % (seg.G, seg.R)] = {
+            roofline_shapes.setdefault("c2 (25k x 10k)", {})["block_cross (configs[2]: 1500 x %d genes, %d groups)" % (seg.G, seg.R)] = {
                 "bound": "tensor", "ms": blk_ms, "achieved": flops / (blk_ms * 1e-3) / 1e12, "peak": tpeak,
                 "unit": "TFLOP/s", "frac": flops / (blk_ms * 1e-3) / 1e12 / tpeak, "peak_source": tsrc,
                 "note": "3 fp16 tcgen05 products per (pair, cell), padding to 64 cells per group included; panels and "
